@@ -1,4 +1,23 @@
-"""B200-native batched box-QP engine (host-side mirror of the C-ABI).
+"""B200-native batched box-QP engine.
 
-Filled in below; see api.py.
+A drop-in for the ADMM hot path of YangLingyuan/Embedded-qp-solver
+(``admm()`` in qp_solvers/qp_solvers.c:255-319 on top of matrix/matrix_ops):
+hand-written sm_100a kernels behind a C ABI (``include/qp_batch.h``,
+``lib/libqpb200.so``); this package is the ctypes mirror of that ABI.
+
+The CUDA library is loaded on first use; if it is missing the call raises --
+there is no CPU path in this package.
 """
+from .api import (ABI_SYMBOLS, LIB_PATH, QP_MAX_DIM, STATUS_CONVERGED, STATUS_MAX_ITER,
+                  STATUS_NONFINITE, STATUS_SINGULAR, Matrix, Options, QpError, QuadraticForm,
+                  Workspace, admm, admm_many, algorithmic_bytes, algorithmic_flops, eval_batch,
+                  kernel_for, load_library, probe_fp32_tflops, probe_hbm_gbs, solve_batch)
+from . import problems  # noqa: F401
+
+__all__ = [
+    "ABI_SYMBOLS", "LIB_PATH", "QP_MAX_DIM", "STATUS_CONVERGED", "STATUS_MAX_ITER",
+    "STATUS_NONFINITE", "STATUS_SINGULAR", "Matrix", "Options", "QpError", "QuadraticForm",
+    "Workspace", "admm", "admm_many", "algorithmic_bytes", "algorithmic_flops", "eval_batch",
+    "kernel_for", "load_library", "probe_fp32_tflops", "probe_hbm_gbs", "solve_batch",
+    "problems",
+]

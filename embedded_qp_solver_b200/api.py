@@ -1,0 +1,393 @@
+"""Host-side mirror of the C ABI (include/qp_batch.h) over ctypes.
+
+The reference is a C library; its hosts call ``admm(x0, iterations, qf)``
+(/root/reference/qp_solvers/qp_solvers.h:14-16).  This module exposes the same
+operator (``admm``/``QuadraticForm``) plus the batched entry points, all of
+them thin calls into ``libqpb200.so``.  PyTorch is used only as the owner of
+device memory and streams.  There is no CPU fallback: if the CUDA library is
+missing or no GPU is present, calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import os
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libqpb200.so")
+
+QP_MAX_DIM = 64
+STATUS_CONVERGED, STATUS_MAX_ITER, STATUS_SINGULAR, STATUS_NONFINITE = 0, 1, 2, 3
+QP_OK, QP_ERR_INVALID, QP_ERR_UNSUPPORTED, QP_ERR_CUDA, QP_ERR_NO_DEVICE = 0, -1, -2, -3, -4
+MEM_HOST, MEM_DEVICE = 0, 1
+
+_fp = C.POINTER(C.c_float)
+_ip = C.POINTER(C.c_int32)
+
+
+class qp_batch(C.Structure):
+    _fields_ = [("n", C.c_uint32), ("mem", C.c_uint32), ("count", C.c_size_t),
+                ("P", C.c_void_p), ("q", C.c_void_p), ("lb", C.c_void_p), ("ub", C.c_void_p),
+                ("lb_scalar", C.c_float), ("ub_scalar", C.c_float),
+                ("z0", C.c_void_p), ("u0", C.c_void_p)]
+
+
+class qp_batch_solution(C.Structure):
+    _fields_ = [("x", C.c_void_p), ("z", C.c_void_p), ("lam", C.c_void_p),
+                ("status", C.c_void_p), ("iters", C.c_void_p)]
+
+
+class qp_options(C.Structure):
+    _fields_ = [("rho", C.c_float), ("alpha", C.c_float), ("abstol", C.c_float),
+                ("reltol", C.c_float), ("max_iter", C.c_uint32), ("device_mask", C.c_uint32),
+                ("device", C.c_int32), ("stream", C.c_void_p), ("chunk", C.c_uint32),
+                ("reserved", C.c_uint32)]
+
+
+class qp_ref_matrix(C.Structure):
+    """Layout of the reference's ``struct _matrix`` (matrix_type.h:20-23)."""
+    _fields_ = [("dimensions", C.c_uint), ("elements", C.POINTER(C.c_double))]
+
+
+class qp_ref_quadratic_form(C.Structure):
+    """Layout of the reference's ``struct _quadratic_form`` (qp.h:8-13)."""
+    _fields_ = [("p", C.POINTER(qp_ref_matrix)), ("q", C.POINTER(qp_ref_matrix)),
+                ("r", C.c_double)]
+
+
+# every symbol include/qp_batch.h declares (tests check the library exports them all)
+ABI_SYMBOLS = [
+    "qp_options_default", "qp_solve_batch", "qp_workspace_create", "qp_workspace_destroy",
+    "qp_solve_batch_ws", "qp_eval_batch", "qp_admm_qf", "qp_admm_qf_batch", "qp_last_error",
+    "qp_device_count", "qp_kernel_for", "qp_probe_fp32_tflops", "qp_probe_hbm_gbs",
+]
+
+_lib = None
+
+
+class QpError(RuntimeError):
+    def __init__(self, code: int, what: str):
+        super().__init__(f"{what} failed with code {code}: {_describe(code)}")
+        self.code = code
+
+
+def _describe(code: int) -> str:
+    names = {QP_ERR_INVALID: "invalid argument", QP_ERR_UNSUPPORTED: "unsupported dimension",
+             QP_ERR_CUDA: "CUDA error", QP_ERR_NO_DEVICE: "no usable GPU"}
+    s = names.get(code, "?")
+    if code == QP_ERR_CUDA and _lib is not None:
+        s += " (" + _lib.qp_last_error().decode() + ")"
+    return s
+
+
+def load_library(path: Optional[str] = None):
+    """dlopen libqpb200.so.  Raises loudly when it has not been built."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    path = path or LIB_PATH
+    if not os.path.exists(path):
+        raise RuntimeError(
+            f"{path} not found: the CUDA library is not built. Run "
+            "`python -m embedded_qp_solver_b200.build` (needs nvcc). There is no CPU fallback.")
+    lib = C.CDLL(path)
+    lib.qp_options_default.argtypes = [C.POINTER(qp_options)]
+    lib.qp_options_default.restype = None
+    lib.qp_solve_batch.argtypes = [C.POINTER(qp_batch), C.POINTER(qp_batch_solution),
+                                   C.POINTER(qp_options)]
+    lib.qp_solve_batch.restype = C.c_int
+    lib.qp_workspace_create.argtypes = [C.c_uint32, C.c_size_t, C.c_uint32, C.POINTER(C.c_void_p)]
+    lib.qp_workspace_create.restype = C.c_int
+    lib.qp_workspace_destroy.argtypes = [C.c_void_p]
+    lib.qp_workspace_destroy.restype = None
+    lib.qp_solve_batch_ws.argtypes = [C.c_void_p, C.POINTER(qp_batch),
+                                      C.POINTER(qp_batch_solution), C.POINTER(qp_options)]
+    lib.qp_solve_batch_ws.restype = C.c_int
+    lib.qp_eval_batch.argtypes = [C.POINTER(qp_batch), C.c_void_p, C.c_float, C.c_void_p,
+                                  C.POINTER(qp_options)]
+    lib.qp_eval_batch.restype = C.c_int
+    lib.qp_admm_qf.argtypes = [C.POINTER(qp_ref_quadratic_form), C.c_uint, C.c_double, C.c_double,
+                               C.POINTER(C.c_double), _ip, _ip]
+    lib.qp_admm_qf.restype = C.c_int
+    lib.qp_admm_qf_batch.argtypes = [C.POINTER(C.POINTER(qp_ref_quadratic_form)), C.c_size_t,
+                                     C.c_uint, C.c_double, C.c_double,
+                                     C.POINTER(C.POINTER(C.c_double)), _ip, _ip,
+                                     C.POINTER(qp_options)]
+    lib.qp_admm_qf_batch.restype = C.c_int
+    lib.qp_last_error.restype = C.c_char_p
+    lib.qp_device_count.restype = C.c_int
+    lib.qp_kernel_for.argtypes = [C.c_uint32, C.c_int]
+    lib.qp_kernel_for.restype = C.c_char_p
+    lib.qp_probe_fp32_tflops.argtypes = [C.c_int, C.c_int]
+    lib.qp_probe_fp32_tflops.restype = C.c_double
+    lib.qp_probe_hbm_gbs.argtypes = [C.c_int, C.c_size_t, C.c_int]
+    lib.qp_probe_hbm_gbs.restype = C.c_double
+    _lib = lib
+    return lib
+
+
+@dataclass
+class Options:
+    """Mirror of ``qp_options``; defaults are the reference's constants
+    (qp_solvers.c:17-18, :281-282; config.h:38)."""
+    rho: float = 1.0
+    alpha: float = 1.0
+    abstol: float = 1e-4
+    reltol: float = 1e-2
+    max_iter: int = 10000
+    device_mask: int = 0
+    device: int = -1
+    stream: int = 0
+    chunk: int = 0
+
+    def to_c(self) -> qp_options:
+        return qp_options(self.rho, self.alpha, self.abstol, self.reltol, int(self.max_iter),
+                          int(self.device_mask), int(self.device), C.c_void_p(self.stream or None),
+                          int(self.chunk), 0)
+
+
+def _is_torch(t) -> bool:
+    return type(t).__module__.startswith("torch")
+
+
+def _as_f32(a, shape, what):
+    """Return (holder, address, is_cuda) for a float32 contiguous array-like."""
+    if a is None:
+        return None, None, None
+    if _is_torch(a):
+        import torch
+        if a.dtype != torch.float32 or not a.is_contiguous():
+            raise TypeError(f"{what}: need a contiguous float32 tensor")
+        if tuple(a.shape) != tuple(shape):
+            raise ValueError(f"{what}: shape {tuple(a.shape)} != {tuple(shape)}")
+        return a, a.data_ptr(), a.is_cuda
+    arr = np.ascontiguousarray(a, dtype=np.float32)
+    if arr.shape != tuple(shape):
+        raise ValueError(f"{what}: shape {arr.shape} != {tuple(shape)}")
+    return arr, arr.ctypes.data, False
+
+
+def solve_batch(P, q, lb=None, ub=None, z0=None, u0=None, options: Optional[Options] = None,
+                out: Optional[dict] = None, workspace: Optional["Workspace"] = None,
+                want=("x", "z", "lam", "status", "iters")) -> dict:
+    """Solve ``count`` box QPs: the batched replacement of a loop of the
+    reference's ``admm(x0, iterations, qf)`` (qp_solvers.c:255-319).
+
+    P [count,n,n], q [count,n] float32; lb/ub each an array [count,n], a Python
+    scalar, or None (= -/+1e12, the reference's host box, config.h:29-30).
+    CUDA torch tensors take the device path (kernel launched on the current
+    torch stream, no synchronisation, outputs are torch tensors on that
+    device); numpy arrays / CPU tensors take the host path (copies, sharded
+    over ``options.device_mask``) and return numpy arrays.
+    """
+    lib = load_library()
+    opt = options or Options()
+    count, n = int(P.shape[0]), int(P.shape[1])
+    if tuple(P.shape) != (count, n, n):
+        raise ValueError("P must be [count, n, n]")
+    hP, aP, dev = _as_f32(P, (count, n, n), "P")
+    hq, aq, dq = _as_f32(q, (count, n), "q")
+    if dq != dev:
+        raise ValueError("P and q must live on the same side (host or device)")
+
+    pb = qp_batch()
+    pb.n, pb.count = n, count
+    pb.mem = MEM_DEVICE if dev else MEM_HOST
+    pb.P, pb.q = aP, aq
+    pb.lb_scalar, pb.ub_scalar = -1e12, 1e12
+    keep = [hP, hq]
+    for name, val in (("lb", lb), ("ub", ub)):
+        if val is None:
+            continue
+        if isinstance(val, (int, float)):
+            setattr(pb, name + "_scalar", float(val))
+        else:
+            h, a, d = _as_f32(val, (count, n), name)
+            if d != dev:
+                raise ValueError(f"{name} must live where P lives")
+            setattr(pb, name, a)
+            keep.append(h)
+    for name, val in (("z0", z0), ("u0", u0)):
+        if val is not None:
+            h, a, d = _as_f32(val, (count, n), name)
+            if d != dev:
+                raise ValueError(f"{name} must live where P lives")
+            setattr(pb, name, a)
+            keep.append(h)
+
+    res = {} if out is None else out
+    sol = qp_batch_solution()
+    copt = opt.to_c()
+    if dev:
+        import torch
+        device = hP.device
+        copt.device = device.index if device.index is not None else torch.cuda.current_device()
+        if not opt.stream:
+            copt.stream = C.c_void_p(torch.cuda.current_stream(device).cuda_stream or None)
+        for k in want:
+            if k not in res:
+                shape = (count,) if k in ("status", "iters") else (count, n)
+                dt = torch.int32 if k in ("status", "iters") else torch.float32
+                res[k] = torch.empty(shape, dtype=dt, device=device)
+        for k in want:
+            setattr(sol, k, res[k].data_ptr())
+    else:
+        for k in want:
+            if k not in res:
+                shape = (count,) if k in ("status", "iters") else (count, n)
+                dt = np.int32 if k in ("status", "iters") else np.float32
+                res[k] = np.empty(shape, dtype=dt)
+        for k in want:
+            v = res[k]
+            setattr(sol, k, v.data_ptr() if _is_torch(v) else v.ctypes.data)
+
+    if workspace is not None:
+        rc = lib.qp_solve_batch_ws(workspace.handle, C.byref(pb), C.byref(sol), C.byref(copt))
+    else:
+        rc = lib.qp_solve_batch(C.byref(pb), C.byref(sol), C.byref(copt))
+    if rc != QP_OK:
+        raise QpError(rc, "qp_solve_batch")
+    del keep
+    return res
+
+
+class Workspace:
+    """Preallocated device workspace (``qp_workspace_create``), the replacement
+    of the reference's static pools (kmalloc/kmalloc.c:37-66)."""
+
+    def __init__(self, n: int, max_count: int, device_mask: int = 0):
+        lib = load_library()
+        h = C.c_void_p()
+        rc = lib.qp_workspace_create(n, max_count, device_mask, C.byref(h))
+        if rc != QP_OK:
+            raise QpError(rc, "qp_workspace_create")
+        self.handle = h
+
+    def close(self):
+        if self.handle:
+            load_library().qp_workspace_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def eval_batch(P, q, x, r: float = 0.0):
+    """f(x) = x'Px/2 + q'x + r per problem (quadratic_form_eval, qp.c:9-27)."""
+    lib = load_library()
+    count, n = int(P.shape[0]), int(P.shape[1])
+    hP, aP, dev = _as_f32(P, (count, n, n), "P")
+    hq, aq, _ = _as_f32(q, (count, n), "q")
+    hx, ax, _ = _as_f32(x, (count, n), "x")
+    pb = qp_batch()
+    pb.n, pb.count, pb.mem, pb.P, pb.q = n, count, (MEM_DEVICE if dev else MEM_HOST), aP, aq
+    copt = Options().to_c()
+    if dev:
+        import torch
+        f = torch.empty(count, dtype=torch.float32, device=hP.device)
+        copt.device = hP.device.index
+        copt.stream = C.c_void_p(torch.cuda.current_stream(hP.device).cuda_stream or None)
+        af = f.data_ptr()
+    else:
+        f = np.empty(count, np.float32)
+        af = f.ctypes.data
+    rc = lib.qp_eval_batch(C.byref(pb), ax, r, af, C.byref(copt))
+    if rc != QP_OK:
+        raise QpError(rc, "qp_eval_batch")
+    return f
+
+
+# ---- the reference's own operator ------------------------------------------------------
+
+class Matrix:
+    """Python holder of a reference ``struct _matrix`` (double, row-major;
+    rows in bits 31:16 and cols in bits 15:0 of ``dimensions``)."""
+
+    def __init__(self, array):
+        a = np.array(array, dtype=np.float64, order="C")
+        if a.ndim == 1:
+            a = a.reshape(-1, 1)
+        self.array = a
+        self.c = qp_ref_matrix((a.shape[0] << 16) | a.shape[1],
+                               a.ctypes.data_as(C.POINTER(C.c_double)))
+
+
+class QuadraticForm:
+    """Mirror of ``struct _quadratic_form {p, q, r}`` (qp.h:8-13): non-owning."""
+
+    def __init__(self, p, q, r: float = 0.0):
+        self.p = p if isinstance(p, Matrix) else Matrix(p)
+        self.q = q if isinstance(q, Matrix) else Matrix(q)
+        self.r = float(r)
+        self.c = qp_ref_quadratic_form(C.pointer(self.p.c), C.pointer(self.q.c), self.r)
+
+
+def admm(x0, iterations: int, qf: QuadraticForm, lb: float = -1e12, ub: float = 1e12,
+         info: Optional[dict] = None) -> np.ndarray:
+    """``struct _matrix *admm(x0, iterations, qf)`` (qp_solvers.c:255-319) on the
+    GPU.  Like the reference, ``x0`` is accepted and ignored (qp_solvers.c:256),
+    the box is the scalar pair (config.h:29-30) and x is returned as an n x 1
+    float64 array."""
+    lib = load_library()
+    n = qf.p.array.shape[0]
+    x = np.zeros((n, 1))
+    st, it = C.c_int32(), C.c_int32()
+    rc = lib.qp_admm_qf(C.byref(qf.c), int(iterations), float(lb), float(ub),
+                        x.ctypes.data_as(C.POINTER(C.c_double)), C.byref(st), C.byref(it))
+    if rc != QP_OK:
+        raise QpError(rc, "qp_admm_qf")
+    if info is not None:
+        info["status"], info["iters"] = st.value, it.value
+    return x
+
+
+def admm_many(qfs, iterations: int, lb: float = -1e12, ub: float = 1e12):
+    """Array-of-structs entry (``qp_admm_qf_batch``): a list of QuadraticForm
+    solved as one batch.  Returns (x [count,n] float64, status, iters)."""
+    lib = load_library()
+    count = len(qfs)
+    n = qfs[0].p.array.shape[0]
+    arr = (C.POINTER(qp_ref_quadratic_form) * count)(*[C.pointer(f.c) for f in qfs])
+    x = np.zeros((count, n))
+    xp = (C.POINTER(C.c_double) * count)(
+        *[x[i].ctypes.data_as(C.POINTER(C.c_double)) for i in range(count)])
+    st = np.zeros(count, np.int32)
+    it = np.zeros(count, np.int32)
+    rc = lib.qp_admm_qf_batch(arr, count, int(iterations), float(lb), float(ub), xp,
+                              st.ctypes.data_as(_ip), it.ctypes.data_as(_ip), None)
+    if rc != QP_OK:
+        raise QpError(rc, "qp_admm_qf_batch")
+    return x, st, it
+
+
+def kernel_for(n: int, aligned16: bool = True) -> str:
+    return load_library().qp_kernel_for(n, int(aligned16)).decode()
+
+
+def probe_fp32_tflops(device: int = -1, repeats: int = 5) -> float:
+    return float(load_library().qp_probe_fp32_tflops(device, repeats))
+
+
+def probe_hbm_gbs(device: int = -1, nbytes: int = 1 << 30, repeats: int = 5) -> float:
+    return float(load_library().qp_probe_hbm_gbs(device, nbytes, repeats))
+
+
+# ---- roofline bookkeeping --------------------------------------------------
+
+def algorithmic_bytes(n: int, warm: bool = False, with_z: bool = True) -> int:
+    """HBM bytes one problem must move: in (n^2+3n) floats [+2n warm start],
+    out x,lambda (+z) and status,iters."""
+    b = (n * n + 3 * n) * 4 + (2 * n * 4 if warm else 0) + 2 * n * 4 + 8
+    return b + (4 * n if with_z else 0)
+
+
+def algorithmic_flops(n: int, mean_iters: float) -> float:
+    """Reference-algorithm flops per problem, F = 8/3 n^3 + K (2 n^2 + 24 n)."""
+    return 8.0 / 3.0 * n ** 3 + mean_iters * (2 * n * n + 24 * n)

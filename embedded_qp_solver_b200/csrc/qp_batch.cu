@@ -1,0 +1,977 @@
+// qp_batch.cu -- host runtime and C ABI of libqpb200.so (include/qp_batch.h).
+//
+// Replaces, for a whole batch, the reference's per-problem call
+//   struct _matrix *admm(x0, iterations, qf)     /root/reference/qp_solvers/qp_solvers.c:255-319
+// and the static slab pools behind it (/root/reference/kmalloc/kmalloc.c:37-66) with a
+// preallocated device workspace.
+//
+// Two data paths:
+//   QP_MEM_DEVICE  arrays already in HBM: pick the kernel for n, launch it on the
+//                  caller's stream, return without synchronising.  No allocation.
+//   QP_MEM_HOST    arrays in host memory: the batch is split into contiguous shards,
+//                  one per GPU in device_mask (one host thread per GPU), and every
+//                  shard into chunks that flow through a DEPTH-deep ring of
+//                  {H2D copies, kernel, D2H copies} on separate streams, so the
+//                  copy engines and the SMs overlap.  Pinned caller memory is used
+//                  in place; pageable memory is staged through pinned buffers.
+//                  No collective anywhere: problems are independent.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "qp_gpq.cuh"
+#include "qp_tpq.cuh"
+
+using namespace qpb;
+
+// ----------------------------------------------------------------------------------------
+// errors
+// ----------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+
+#define QP_CUDA(call)                                                                          \
+	do {                                                                                   \
+		cudaError_t e_ = (call);                                                       \
+		if (e_ != cudaSuccess) {                                                       \
+			g_err = std::string(#call) + ": " + cudaGetErrorString(e_);            \
+			return QP_ERR_CUDA;                                                    \
+		}                                                                              \
+	} while (0)
+
+extern "C" const char *qp_last_error(void)
+{
+	return g_err.c_str();
+}
+
+extern "C" int qp_device_count(void)
+{
+	int n = 0;
+	if (cudaGetDeviceCount(&n) != cudaSuccess)
+		return 0;
+	return n;
+}
+
+extern "C" void qp_options_default(qp_options *o)
+{
+	if (!o)
+		return;
+	std::memset(o, 0, sizeof(*o));
+	o->rho = 1.0f;        // qp_solvers.c:281
+	o->alpha = 1.0f;      // qp_solvers.c:282
+	o->abstol = 1e-4f;    // qp_solvers.c:17
+	o->reltol = 1e-2f;    // qp_solvers.c:18
+	o->max_iter = 10000;  // ADMM_ITERATIONS, config.h:38
+	o->device_mask = 0;
+	o->device = -1;
+	o->stream = nullptr;
+	o->chunk = 0;
+}
+
+// ----------------------------------------------------------------------------------------
+// kernel selection and launch
+// ----------------------------------------------------------------------------------------
+namespace {
+
+struct DevInfo {
+	int sms = 0;
+	bool ok = false;
+};
+DevInfo g_dev[64];
+std::mutex g_dev_mu;
+
+int dev_sms(int dev)
+{
+	std::lock_guard<std::mutex> lk(g_dev_mu);
+	if (!g_dev[dev].ok) {
+		cudaDeviceProp pr;
+		if (cudaGetDeviceProperties(&pr, dev) != cudaSuccess)
+			return 0;
+		g_dev[dev].sms = pr.multiProcessorCount;
+		g_dev[dev].ok = true;
+	}
+	return g_dev[dev].sms;
+}
+
+inline bool aligned16(const void *p)
+{
+	return (reinterpret_cast<uintptr_t>(p) & 15u) == 0;
+}
+
+bool tpq_eligible(const KernelArgs &a)
+{
+	const int n = a.n;
+	if (!(n == 4 || n == 8 || n == 12 || n == 16))
+		return false;
+	if ((a.lb == nullptr) != (a.ub == nullptr))
+		return false;
+	if ((a.z0 == nullptr) != (a.u0 == nullptr))
+		return false;
+	const void *ptrs[] = { a.P, a.q, a.lb, a.ub, a.z0, a.u0, a.x, a.z, a.lam };
+	for (const void *p : ptrs)
+		if (p && !aligned16(p))
+			return false;
+	return true;
+}
+
+template <int N, bool B, bool W> int launch_tpq(const KernelArgs &a, int dev, cudaStream_t st)
+{
+	using L = TpqLayout<N, B, W>;
+	using Cfg = TpqCfg<N>;
+	auto kern = qp_tpq_kernel<N, B, W>;
+	static bool attr_done[64] = {};
+	if (!attr_done[dev]) {
+		QP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+					     int(L::BYTES)));
+		attr_done[dev] = true;
+	}
+	const unsigned long long nbatch = (a.count + 31ull) / 32ull;
+	unsigned long long grid = (unsigned long long)dev_sms(dev) * Cfg::MINB;
+	// every warp of a CTA should have a batch to work on
+	const unsigned long long need = (nbatch + Cfg::WARPS - 1) / Cfg::WARPS;
+	grid = std::max(1ull, std::min(grid, need));
+	kern<<<dim3((unsigned)grid), dim3(Cfg::WARPS * 32), L::BYTES, st>>>(a);
+	QP_CUDA(cudaGetLastError());
+	return QP_OK;
+}
+
+template <int N> int launch_tpq_n(const KernelArgs &a, int dev, cudaStream_t st)
+{
+	const bool b = a.lb != nullptr, w = a.z0 != nullptr;
+	if (b && w)
+		return launch_tpq<N, true, true>(a, dev, st);
+	if (b)
+		return launch_tpq<N, true, false>(a, dev, st);
+	if (w)
+		return launch_tpq<N, false, true>(a, dev, st);
+	return launch_tpq<N, false, false>(a, dev, st);
+}
+
+template <int NP> int launch_gpq(const KernelArgs &a, int dev, cudaStream_t st)
+{
+	auto kern = qp_gpq_kernel<NP>;
+	static int per_sm[64] = {};
+	if (!per_sm[dev]) {
+		int b = 0;
+		QP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, kern, GPQ_WARPS * 32, 0));
+		per_sm[dev] = std::max(1, b);
+	}
+	const unsigned long long need = (a.count + GPQ_WARPS - 1) / GPQ_WARPS;
+	unsigned long long grid = (unsigned long long)dev_sms(dev) * per_sm[dev];
+	grid = std::max(1ull, std::min(grid, need));
+	kern<<<dim3((unsigned)grid), dim3(GPQ_WARPS * 32), 0, st>>>(a);
+	QP_CUDA(cudaGetLastError());
+	return QP_OK;
+}
+
+int launch_solver(const KernelArgs &a, int dev, cudaStream_t st)
+{
+	if (a.count == 0)
+		return QP_OK;
+	if (tpq_eligible(a)) {
+		switch (a.n) {
+		case 4:  return launch_tpq_n<4>(a, dev, st);
+		case 8:  return launch_tpq_n<8>(a, dev, st);
+		case 12: return launch_tpq_n<12>(a, dev, st);
+		case 16: return launch_tpq_n<16>(a, dev, st);
+		}
+	}
+	const int np = (a.n + 7) / 8 * 8;
+	switch (np) {
+	case 8:  return launch_gpq<8>(a, dev, st);
+	case 16: return launch_gpq<16>(a, dev, st);
+	case 24: return launch_gpq<24>(a, dev, st);
+	case 32: return launch_gpq<32>(a, dev, st);
+	case 40: return launch_gpq<40>(a, dev, st);
+	case 48: return launch_gpq<48>(a, dev, st);
+	case 56: return launch_gpq<56>(a, dev, st);
+	case 64: return launch_gpq<64>(a, dev, st);
+	}
+	return QP_ERR_UNSUPPORTED;
+}
+
+int check_problem(const qp_batch *pb, const qp_batch_solution *sol)
+{
+	if (!pb || !sol)
+		return QP_ERR_INVALID;
+	if (pb->n == 0)
+		return QP_ERR_INVALID;
+	if (pb->n > QP_MAX_DIM)
+		return QP_ERR_UNSUPPORTED;
+	if (pb->mem != QP_MEM_HOST && pb->mem != QP_MEM_DEVICE)
+		return QP_ERR_INVALID;
+	if (pb->count && (!pb->P || !pb->q))
+		return QP_ERR_INVALID;
+	return QP_OK;
+}
+
+int check_options(const qp_options &o)
+{
+	if (!(o.rho > 0.0f) || !std::isfinite(o.rho))
+		return QP_ERR_INVALID;
+	if (!std::isfinite(o.alpha) || !(o.alpha > 0.0f) || !(o.alpha < 2.0f))
+		return QP_ERR_INVALID;
+	if (!(o.abstol >= 0.0f) || !(o.reltol >= 0.0f))
+		return QP_ERR_INVALID;
+	return QP_OK;
+}
+
+KernelArgs make_args(const qp_batch &pb, const qp_batch_solution &sol, const qp_options &o)
+{
+	KernelArgs a;
+	a.P = pb.P, a.q = pb.q, a.lb = pb.lb, a.ub = pb.ub, a.z0 = pb.z0, a.u0 = pb.u0;
+	a.x = sol.x, a.z = sol.z, a.lam = sol.lambda, a.status = sol.status, a.iters = sol.iters;
+	a.count = pb.count;
+	a.n = int(pb.n);
+	a.lb_s = pb.lb_scalar, a.ub_s = pb.ub_scalar;
+	a.rho = o.rho, a.alpha = o.alpha;
+	// sqrt(nrows) * abstol, evaluated in double like qp_solvers.c:242 and rounded once
+	a.eps_abs = float(std::sqrt(double(pb.n)) * double(o.abstol));
+	a.reltol = o.reltol;
+	a.max_iter = o.max_iter;
+	return a;
+}
+
+struct DeviceGuard {
+	int prev = -1;
+	bool changed = false;
+	int enter(int dev)
+	{
+		if (cudaGetDevice(&prev) != cudaSuccess)
+			return QP_ERR_NO_DEVICE;
+		if (dev != prev) {
+			if (cudaSetDevice(dev) != cudaSuccess)
+				return QP_ERR_NO_DEVICE;
+			changed = true;
+		}
+		return QP_OK;
+	}
+	~DeviceGuard()
+	{
+		if (changed)
+			cudaSetDevice(prev);
+	}
+};
+
+int resolve_device(int dev)
+{
+	if (dev >= 0)
+		return dev < qp_device_count() ? dev : -1;
+	int cur = 0;
+	if (cudaGetDevice(&cur) != cudaSuccess)
+		return -1;
+	return cur;
+}
+
+} // namespace
+
+// ----------------------------------------------------------------------------------------
+// workspace for the host-memory path
+// ----------------------------------------------------------------------------------------
+static constexpr int DEPTH = 3;
+
+struct Slot {
+	// device buffers for one chunk
+	float *dP = nullptr, *dq = nullptr, *dlb = nullptr, *dub = nullptr, *dz0 = nullptr,
+	      *du0 = nullptr;
+	float *dx = nullptr, *dz = nullptr, *dlam = nullptr;
+	int32_t *dstatus = nullptr, *diters = nullptr;
+	// pinned staging (allocated on first use with pageable caller memory)
+	float *hin = nullptr;  // P | q | lb | ub | z0 | u0
+	float *hout = nullptr; // x | z | lam | status | iters
+	cudaStream_t stream = nullptr;
+	cudaEvent_t done = nullptr;
+	// bookkeeping of the chunk in flight
+	size_t first = 0, cnt = 0;
+	bool busy = false;
+};
+
+struct DeviceCtx {
+	int dev = 0;
+	Slot slot[DEPTH];
+};
+
+struct qp_workspace {
+	uint32_t n = 0;
+	size_t chunk = 0; // problems per slot
+	std::vector<DeviceCtx> devs;
+	std::mutex mu;
+};
+
+namespace {
+
+size_t in_floats(uint32_t n)
+{
+	return size_t(n) * n + 5ull * n;
+}
+size_t out_floats(uint32_t n)
+{
+	return 3ull * n + 2;
+}
+
+size_t choose_chunk(uint32_t n, size_t per_dev)
+{
+	// ~32 MB of input per chunk, at least 4 chunks per device when the shard allows
+	const size_t bytes = in_floats(n) * 4;
+	size_t c = std::max<size_t>(1024, (32ull << 20) / bytes);
+	if (per_dev / 4 >= 4096)
+		c = std::min(c, per_dev / 4);
+	c = std::max<size_t>(32, std::min(c, std::max<size_t>(per_dev, 32)));
+	return (c + 31) / 32 * 32;
+}
+
+std::vector<int> mask_devices(uint32_t mask, int dflt)
+{
+	std::vector<int> v;
+	const int nd = qp_device_count();
+	if (mask == 0) {
+		if (dflt >= 0 && dflt < nd)
+			v.push_back(dflt);
+		return v;
+	}
+	for (int i = 0; i < 32 && i < nd; ++i)
+		if (mask & (1u << i))
+			v.push_back(i);
+	return v;
+}
+
+void free_ctx(DeviceCtx &c)
+{
+	int prev = 0;
+	cudaGetDevice(&prev);
+	cudaSetDevice(c.dev);
+	for (Slot &s : c.slot) {
+		if (s.stream)
+			cudaStreamSynchronize(s.stream);
+		cudaFree(s.dP);
+		cudaFreeHost(s.hin);
+		cudaFreeHost(s.hout);
+		if (s.done)
+			cudaEventDestroy(s.done);
+		if (s.stream)
+			cudaStreamDestroy(s.stream);
+		s = Slot();
+	}
+	cudaSetDevice(prev);
+}
+
+int alloc_ctx(DeviceCtx &c, uint32_t n, size_t chunk)
+{
+	DeviceGuard g;
+	if (g.enter(c.dev) != QP_OK)
+		return QP_ERR_NO_DEVICE;
+	for (Slot &s : c.slot) {
+		// one allocation per slot, carved up (all offsets are multiples of 16 bytes
+		// because chunk is a multiple of 32)
+		const size_t fl = chunk * (in_floats(n) + out_floats(n));
+		float *base = nullptr;
+		QP_CUDA(cudaMalloc(&base, fl * 4));
+		s.dP = base;
+		s.dq = s.dP + chunk * n * n;
+		s.dlb = s.dq + chunk * n;
+		s.dub = s.dlb + chunk * n;
+		s.dz0 = s.dub + chunk * n;
+		s.du0 = s.dz0 + chunk * n;
+		s.dx = s.du0 + chunk * n;
+		s.dz = s.dx + chunk * n;
+		s.dlam = s.dz + chunk * n;
+		s.dstatus = reinterpret_cast<int32_t *>(s.dlam + chunk * n);
+		s.diters = s.dstatus + chunk;
+		QP_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+		QP_CUDA(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+	}
+	return QP_OK;
+}
+
+bool is_pinned(const void *p)
+{
+	if (!p)
+		return true;
+	cudaPointerAttributes at;
+	if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+		cudaGetLastError();
+		return false;
+	}
+	return at.type == cudaMemoryTypeHost;
+}
+
+// One GPU's share of a host-memory solve: chunks [lo, hi) of the batch.
+int run_shard(qp_workspace *ws, DeviceCtx &ctx, const qp_batch &pb, const qp_batch_solution &sol,
+	      const qp_options &opt, size_t lo, size_t hi)
+{
+	DeviceGuard g;
+	if (g.enter(ctx.dev) != QP_OK)
+		return QP_ERR_NO_DEVICE;
+	const uint32_t n = pb.n;
+	const size_t chunk = ws->chunk;
+	const bool pin_in = is_pinned(pb.P) && is_pinned(pb.q) && is_pinned(pb.lb) &&
+			    is_pinned(pb.ub) && is_pinned(pb.z0) && is_pinned(pb.u0);
+	const bool pin_out = is_pinned(sol.x) && is_pinned(sol.z) && is_pinned(sol.lambda) &&
+			     is_pinned(sol.status) && is_pinned(sol.iters);
+
+	auto retire = [&](Slot &s) -> int {
+		if (!s.busy)
+			return QP_OK;
+		QP_CUDA(cudaEventSynchronize(s.done));
+		if (!pin_out) {
+			const size_t c = s.cnt, f = s.first;
+			const float *h = s.hout;
+			if (sol.x)
+				std::memcpy(sol.x + f * n, h, c * n * 4);
+			if (sol.z)
+				std::memcpy(sol.z + f * n, h + chunk * n, c * n * 4);
+			if (sol.lambda)
+				std::memcpy(sol.lambda + f * n, h + 2 * chunk * n, c * n * 4);
+			const int32_t *hi32 = reinterpret_cast<const int32_t *>(h + 3 * chunk * n);
+			if (sol.status)
+				std::memcpy(sol.status + f, hi32, c * 4);
+			if (sol.iters)
+				std::memcpy(sol.iters + f, hi32 + chunk, c * 4);
+		}
+		s.busy = false;
+		return QP_OK;
+	};
+
+	size_t k = 0;
+	for (size_t first = lo; first < hi; first += chunk, ++k) {
+		Slot &s = ctx.slot[k % DEPTH];
+		int rc = retire(s);
+		if (rc != QP_OK)
+			return rc;
+		const size_t c = std::min(chunk, hi - first);
+		s.first = first, s.cnt = c;
+		cudaStream_t st = s.stream;
+
+		// ---- inputs ----
+		struct In {
+			const float *src;
+			float *dst;
+			size_t per;
+		} ins[] = { { pb.P, s.dP, size_t(n) * n }, { pb.q, s.dq, n },  { pb.lb, s.dlb, n },
+			    { pb.ub, s.dub, n },           { pb.z0, s.dz0, n }, { pb.u0, s.du0, n } };
+		if (pin_in) {
+			for (const In &i : ins)
+				if (i.src)
+					QP_CUDA(cudaMemcpyAsync(i.dst, i.src + first * i.per, c * i.per * 4,
+								cudaMemcpyHostToDevice, st));
+		} else {
+			if (!s.hin)
+				QP_CUDA(cudaMallocHost(&s.hin, chunk * in_floats(n) * 4));
+			size_t off = 0;
+			for (const In &i : ins) {
+				if (i.src) {
+					std::memcpy(s.hin + off, i.src + first * i.per, c * i.per * 4);
+					QP_CUDA(cudaMemcpyAsync(i.dst, s.hin + off, c * i.per * 4,
+								cudaMemcpyHostToDevice, st));
+				}
+				off += chunk * i.per;
+			}
+		}
+
+		// ---- solve ----
+		qp_batch dpb = pb;
+		dpb.mem = QP_MEM_DEVICE;
+		dpb.count = c;
+		dpb.P = s.dP, dpb.q = s.dq;
+		dpb.lb = pb.lb ? s.dlb : nullptr, dpb.ub = pb.ub ? s.dub : nullptr;
+		dpb.z0 = pb.z0 ? s.dz0 : nullptr, dpb.u0 = pb.u0 ? s.du0 : nullptr;
+		qp_batch_solution dsol;
+		dsol.x = sol.x ? s.dx : nullptr, dsol.z = sol.z ? s.dz : nullptr;
+		dsol.lambda = sol.lambda ? s.dlam : nullptr;
+		dsol.status = sol.status ? s.dstatus : nullptr;
+		dsol.iters = sol.iters ? s.diters : nullptr;
+		rc = launch_solver(make_args(dpb, dsol, opt), ctx.dev, st);
+		if (rc != QP_OK)
+			return rc;
+
+		// ---- outputs ----
+		if (pin_out) {
+			if (sol.x)
+				QP_CUDA(cudaMemcpyAsync(sol.x + first * n, s.dx, c * n * 4,
+							cudaMemcpyDeviceToHost, st));
+			if (sol.z)
+				QP_CUDA(cudaMemcpyAsync(sol.z + first * n, s.dz, c * n * 4,
+							cudaMemcpyDeviceToHost, st));
+			if (sol.lambda)
+				QP_CUDA(cudaMemcpyAsync(sol.lambda + first * n, s.dlam, c * n * 4,
+							cudaMemcpyDeviceToHost, st));
+			if (sol.status)
+				QP_CUDA(cudaMemcpyAsync(sol.status + first, s.dstatus, c * 4,
+							cudaMemcpyDeviceToHost, st));
+			if (sol.iters)
+				QP_CUDA(cudaMemcpyAsync(sol.iters + first, s.diters, c * 4,
+							cudaMemcpyDeviceToHost, st));
+		} else {
+			if (!s.hout)
+				QP_CUDA(cudaMallocHost(&s.hout, chunk * out_floats(n) * 4));
+			float *h = s.hout;
+			if (sol.x)
+				QP_CUDA(cudaMemcpyAsync(h, s.dx, c * n * 4, cudaMemcpyDeviceToHost, st));
+			if (sol.z)
+				QP_CUDA(cudaMemcpyAsync(h + chunk * n, s.dz, c * n * 4,
+							cudaMemcpyDeviceToHost, st));
+			if (sol.lambda)
+				QP_CUDA(cudaMemcpyAsync(h + 2 * chunk * n, s.dlam, c * n * 4,
+							cudaMemcpyDeviceToHost, st));
+			int32_t *hi32 = reinterpret_cast<int32_t *>(h + 3 * chunk * n);
+			if (sol.status)
+				QP_CUDA(cudaMemcpyAsync(hi32, s.dstatus, c * 4, cudaMemcpyDeviceToHost,
+							st));
+			if (sol.iters)
+				QP_CUDA(cudaMemcpyAsync(hi32 + chunk, s.diters, c * 4,
+							cudaMemcpyDeviceToHost, st));
+		}
+		QP_CUDA(cudaEventRecord(s.done, st));
+		s.busy = true;
+	}
+	// drain in issue order
+	for (size_t d = 0; d < DEPTH; ++d) {
+		int rc = retire(ctx.slot[(k + d) % DEPTH]);
+		if (rc != QP_OK)
+			return rc;
+	}
+	return QP_OK;
+}
+
+} // namespace
+
+extern "C" int qp_workspace_create(uint32_t n, size_t max_count, uint32_t device_mask,
+				   qp_workspace **out)
+{
+	if (!out || n == 0)
+		return QP_ERR_INVALID;
+	if (n > QP_MAX_DIM)
+		return QP_ERR_UNSUPPORTED;
+	std::vector<int> devs = mask_devices(device_mask, resolve_device(-1));
+	if (devs.empty())
+		return QP_ERR_NO_DEVICE;
+	qp_workspace *ws = new qp_workspace;
+	ws->n = n;
+	const size_t per_dev = (std::max<size_t>(max_count, 1) + devs.size() - 1) / devs.size();
+	ws->chunk = choose_chunk(n, per_dev);
+	ws->devs.resize(devs.size());
+	for (size_t i = 0; i < devs.size(); ++i) {
+		ws->devs[i].dev = devs[i];
+		int rc = alloc_ctx(ws->devs[i], n, ws->chunk);
+		if (rc != QP_OK) {
+			std::string keep = g_err;
+			qp_workspace_destroy(ws);
+			g_err = keep;
+			return rc;
+		}
+	}
+	*out = ws;
+	return QP_OK;
+}
+
+extern "C" void qp_workspace_destroy(qp_workspace *ws)
+{
+	if (!ws)
+		return;
+	for (DeviceCtx &c : ws->devs)
+		free_ctx(c);
+	delete ws;
+}
+
+extern "C" int qp_solve_batch_ws(qp_workspace *ws, const qp_batch *pb,
+				 const qp_batch_solution *sol, const qp_options *opt_in)
+{
+	int rc = check_problem(pb, sol);
+	if (rc != QP_OK)
+		return rc;
+	qp_options opt;
+	if (opt_in)
+		opt = *opt_in;
+	else
+		qp_options_default(&opt);
+	rc = check_options(opt);
+	if (rc != QP_OK)
+		return rc;
+	if (pb->count == 0)
+		return QP_OK;
+
+	if (pb->mem == QP_MEM_DEVICE) {
+		const int dev = resolve_device(opt.device);
+		if (dev < 0)
+			return QP_ERR_NO_DEVICE;
+		DeviceGuard g;
+		if (g.enter(dev) != QP_OK)
+			return QP_ERR_NO_DEVICE;
+		return launch_solver(make_args(*pb, *sol, opt), dev,
+				     static_cast<cudaStream_t>(opt.stream));
+	}
+
+	if (!ws || ws->n != pb->n)
+		return QP_ERR_INVALID;
+	std::lock_guard<std::mutex> lk(ws->mu);
+	const size_t nd = ws->devs.size();
+	if (nd == 1)
+		return run_shard(ws, ws->devs[0], *pb, *sol, opt, 0, pb->count);
+
+	// contiguous shards, remainder to the first devices
+	std::vector<int> rcs(nd, QP_OK);
+	std::vector<std::string> errs(nd);
+	std::vector<std::thread> th;
+	const size_t base = pb->count / nd, rem = pb->count % nd;
+	size_t lo = 0;
+	for (size_t i = 0; i < nd; ++i) {
+		const size_t hi = lo + base + (i < rem ? 1 : 0);
+		if (hi > lo)
+			th.emplace_back([&, i, lo, hi] {
+				rcs[i] = run_shard(ws, ws->devs[i], *pb, *sol, opt, lo, hi);
+				errs[i] = g_err;
+			});
+		lo = hi;
+	}
+	for (std::thread &t : th)
+		t.join();
+	for (size_t i = 0; i < nd; ++i)
+		if (rcs[i] != QP_OK) {
+			g_err = errs[i];
+			return rcs[i];
+		}
+	return QP_OK;
+}
+
+// default workspace kept by qp_solve_batch(): rebuilt when the shape, the device set or
+// the needed capacity changes
+static qp_workspace *g_default_ws = nullptr;
+static uint32_t g_default_mask = 0;
+static int g_default_dev = -1;
+static std::mutex g_default_mu;
+
+extern "C" int qp_solve_batch(const qp_batch *pb, const qp_batch_solution *sol,
+			      const qp_options *opt_in)
+{
+	int rc = check_problem(pb, sol);
+	if (rc != QP_OK)
+		return rc;
+	if (pb->mem == QP_MEM_DEVICE || pb->count == 0)
+		return qp_solve_batch_ws(nullptr, pb, sol, opt_in);
+
+	qp_options opt;
+	if (opt_in)
+		opt = *opt_in;
+	else
+		qp_options_default(&opt);
+	const int dev = resolve_device(opt.device);
+	if (dev < 0)
+		return QP_ERR_NO_DEVICE;
+	qp_workspace *ws = nullptr;
+	{
+		std::lock_guard<std::mutex> lk(g_default_mu);
+		const size_t ndev = std::max<size_t>(1, mask_devices(opt.device_mask, dev).size());
+		const size_t want =
+			opt.chunk ? (size_t(opt.chunk) + 31) / 32 * 32
+				  : choose_chunk(pb->n, (pb->count + ndev - 1) / ndev);
+		if (g_default_ws &&
+		    (g_default_ws->n != pb->n || g_default_mask != opt.device_mask ||
+		     g_default_dev != dev || g_default_ws->chunk != want)) {
+			qp_workspace_destroy(g_default_ws);
+			g_default_ws = nullptr;
+		}
+		if (!g_default_ws) {
+			DeviceGuard g;
+			if (g.enter(dev) != QP_OK)
+				return QP_ERR_NO_DEVICE;
+			rc = qp_workspace_create(pb->n, pb->count, opt.device_mask, &g_default_ws);
+			if (rc != QP_OK)
+				return rc;
+			if (opt.chunk && g_default_ws->chunk != want) {
+				// honour an explicit chunk size
+				for (DeviceCtx &c : g_default_ws->devs)
+					free_ctx(c);
+				g_default_ws->chunk = want;
+				for (DeviceCtx &c : g_default_ws->devs) {
+					rc = alloc_ctx(c, pb->n, want);
+					if (rc != QP_OK)
+						return rc;
+				}
+			}
+			g_default_mask = opt.device_mask;
+			g_default_dev = dev;
+		}
+		ws = g_default_ws;
+	}
+	return qp_solve_batch_ws(ws, pb, sol, &opt);
+}
+
+// ----------------------------------------------------------------------------------------
+// objective evaluation (quadratic_form_eval, /root/reference/qp_solvers/qp.c:9-27)
+// ----------------------------------------------------------------------------------------
+__global__ void qp_eval_kernel(const float *__restrict__ P, const float *__restrict__ q,
+			       const float *__restrict__ x, float r, float *__restrict__ f, int n,
+			       unsigned long long count)
+{
+	const int lane = threadIdx.x & 31;
+	const unsigned long long w = (blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x) >> 5;
+	const unsigned long long nw = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
+	for (unsigned long long c = w; c < count; c += nw) {
+		const float *Pc = P + c * (unsigned long long)n * n;
+		const float *xc = x + c * (unsigned long long)n;
+		const float *qc = q + c * (unsigned long long)n;
+		float quad = 0.0f, lin = 0.0f;
+		// lane j accumulates column j: sum_i x_i P_ij, then times x_j (P symmetric or not)
+		for (int j = lane; j < n; j += 32) {
+			float t = 0.0f;
+			for (int i = 0; i < n; ++i)
+				t = fmaf(xc[i], Pc[(unsigned long long)i * n + j], t);
+			quad = fmaf(t, xc[j], quad);
+			lin = fmaf(qc[j], xc[j], lin);
+		}
+		quad = warp_sum(quad);
+		lin = warp_sum(lin);
+		if (lane == 0)
+			f[c] = fmaf(0.5f, quad, lin) + r;
+	}
+}
+
+extern "C" int qp_eval_batch(const qp_batch *pb, const float *x, float r, float *f,
+			     const qp_options *opt_in)
+{
+	if (!pb || !x || !f || !pb->P || !pb->q || pb->n == 0)
+		return QP_ERR_INVALID;
+	if (pb->count == 0)
+		return QP_OK;
+	qp_options opt;
+	if (opt_in)
+		opt = *opt_in;
+	else
+		qp_options_default(&opt);
+	const int dev = resolve_device(opt.device);
+	if (dev < 0)
+		return QP_ERR_NO_DEVICE;
+	DeviceGuard g;
+	if (g.enter(dev) != QP_OK)
+		return QP_ERR_NO_DEVICE;
+	const size_t n = pb->n, c = pb->count;
+	const unsigned grid = (unsigned)std::min<size_t>((c + 7) / 8, size_t(dev_sms(dev)) * 8);
+	if (pb->mem == QP_MEM_DEVICE) {
+		qp_eval_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(opt.stream)>>>(
+			pb->P, pb->q, x, r, f, int(n), c);
+		QP_CUDA(cudaGetLastError());
+		return QP_OK;
+	}
+	float *d = nullptr;
+	QP_CUDA(cudaMalloc(&d, (c * n * n + 2 * c * n + c) * 4));
+	float *dP = d, *dq = dP + c * n * n, *dx = dq + c * n, *df = dx + c * n;
+	cudaError_t e = cudaMemcpy(dP, pb->P, c * n * n * 4, cudaMemcpyHostToDevice);
+	if (e == cudaSuccess)
+		e = cudaMemcpy(dq, pb->q, c * n * 4, cudaMemcpyHostToDevice);
+	if (e == cudaSuccess)
+		e = cudaMemcpy(dx, x, c * n * 4, cudaMemcpyHostToDevice);
+	if (e == cudaSuccess) {
+		qp_eval_kernel<<<grid, 256>>>(dP, dq, dx, r, df, int(n), c);
+		e = cudaGetLastError();
+	}
+	if (e == cudaSuccess)
+		e = cudaMemcpy(f, df, c * 4, cudaMemcpyDeviceToHost);
+	cudaFree(d);
+	if (e != cudaSuccess) {
+		g_err = std::string("qp_eval_batch: ") + cudaGetErrorString(e);
+		return QP_ERR_CUDA;
+	}
+	return QP_OK;
+}
+
+// ----------------------------------------------------------------------------------------
+// entry points on the reference's structs
+// ----------------------------------------------------------------------------------------
+static inline unsigned ref_rows(const qp_ref_matrix *m)
+{
+	return (m->dimensions >> 16) & 0xffffu; // MATRIX_GET_ROW, matrix_type.h:14
+}
+static inline unsigned ref_cols(const qp_ref_matrix *m)
+{
+	return m->dimensions & 0xffffu; // MATRIX_GET_COL, matrix_type.h:15
+}
+
+extern "C" int qp_admm_qf_batch(const struct qp_ref_quadratic_form *const *qfs, size_t count,
+				unsigned iterations, double lb, double ub, double *const *x_out,
+				int32_t *status, int32_t *iters, const qp_options *opt_in)
+{
+	if (!qfs || !x_out)
+		return QP_ERR_INVALID;
+	if (count == 0)
+		return QP_OK;
+	for (size_t i = 0; i < count; ++i)
+		if (!qfs[i] || !qfs[i]->p || !qfs[i]->q || !qfs[i]->p->elements ||
+		    !qfs[i]->q->elements || !x_out[i])
+			return QP_ERR_INVALID;
+	const unsigned n = ref_rows(qfs[0]->p);
+	if (n == 0)
+		return QP_ERR_INVALID;
+	if (n > QP_MAX_DIM)
+		return QP_ERR_UNSUPPORTED;
+	for (size_t i = 0; i < count; ++i)
+		if (ref_rows(qfs[i]->p) != n || ref_cols(qfs[i]->p) != n ||
+		    ref_rows(qfs[i]->q) * ref_cols(qfs[i]->q) != n)
+			return QP_ERR_INVALID;
+
+	std::vector<float> P(count * n * n), q(count * n), x(count * n);
+	std::vector<int32_t> st(count), it(count);
+	for (size_t i = 0; i < count; ++i) {
+		const double *pe = qfs[i]->p->elements, *qe = qfs[i]->q->elements;
+		for (size_t k = 0; k < size_t(n) * n; ++k)
+			P[i * n * n + k] = float(pe[k]);
+		for (size_t k = 0; k < n; ++k)
+			q[i * n + k] = float(qe[k]);
+	}
+	qp_batch pb;
+	std::memset(&pb, 0, sizeof(pb));
+	pb.n = n, pb.mem = QP_MEM_HOST, pb.count = count;
+	pb.P = P.data(), pb.q = q.data();
+	pb.lb_scalar = float(lb), pb.ub_scalar = float(ub);
+	qp_batch_solution sol;
+	std::memset(&sol, 0, sizeof(sol));
+	sol.x = x.data(), sol.status = st.data(), sol.iters = it.data();
+	qp_options opt;
+	if (opt_in)
+		opt = *opt_in;
+	else
+		qp_options_default(&opt);
+	opt.max_iter = iterations;
+	const int rc = qp_solve_batch(&pb, &sol, &opt);
+	if (rc != QP_OK)
+		return rc;
+	for (size_t i = 0; i < count; ++i) {
+		for (size_t k = 0; k < n; ++k)
+			x_out[i][k] = double(x[i * n + k]);
+		if (status)
+			status[i] = st[i];
+		if (iters)
+			iters[i] = it[i];
+	}
+	return QP_OK;
+}
+
+extern "C" int qp_admm_qf(const struct qp_ref_quadratic_form *qf, unsigned iterations, double lb,
+			  double ub, double *x_out, int32_t *status, int32_t *iters)
+{
+	const struct qp_ref_quadratic_form *one[1] = { qf };
+	double *xo[1] = { x_out };
+	return qp_admm_qf_batch(one, 1, iterations, lb, ub, xo, status, iters, nullptr);
+}
+
+extern "C" const char *qp_kernel_for(uint32_t n, int al16)
+{
+	static thread_local char buf[32];
+	if (n == 0 || n > QP_MAX_DIM)
+		return "unsupported";
+	if (al16 && (n == 4 || n == 8 || n == 12 || n == 16))
+		std::snprintf(buf, sizeof buf, "tpq<%u>", n);
+	else
+		std::snprintf(buf, sizeof buf, "gpq<%u>", (n + 7) / 8 * 8);
+	return buf;
+}
+
+// ----------------------------------------------------------------------------------------
+// roofline probes
+// ----------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) qp_probe_fma_kernel(float *out, int iters, float a, float b)
+{
+	float v[8];
+#pragma unroll
+	for (int k = 0; k < 8; ++k)
+		v[k] = float(threadIdx.x + k);
+	for (int i = 0; i < iters; ++i) {
+#pragma unroll
+		for (int r = 0; r < 8; ++r) {
+#pragma unroll
+			for (int k = 0; k < 8; ++k)
+				v[k] = fmaf(v[k], a, b);
+		}
+	}
+	float s = 0.0f;
+#pragma unroll
+	for (int k = 0; k < 8; ++k)
+		s += v[k];
+	if (s == 12345.678f)
+		out[0] = s;
+}
+
+extern "C" double qp_probe_fp32_tflops(int device, int repeats)
+{
+	const int dev = resolve_device(device);
+	if (dev < 0)
+		return 0.0;
+	DeviceGuard g;
+	if (g.enter(dev) != QP_OK)
+		return 0.0;
+	float *d = nullptr;
+	if (cudaMalloc(&d, 256) != cudaSuccess)
+		return 0.0;
+	const int sms = dev_sms(dev);
+	const int iters = 4096;
+	const dim3 grid(sms * 8), block(256);
+	cudaEvent_t e0, e1;
+	cudaEventCreate(&e0);
+	cudaEventCreate(&e1);
+	double best = 0.0;
+	for (int r = 0; r < std::max(1, repeats) + 1; ++r) {
+		cudaEventRecord(e0);
+		qp_probe_fma_kernel<<<grid, block>>>(d, iters, 0.999f, 0.001f);
+		cudaEventRecord(e1);
+		cudaEventSynchronize(e1);
+		float ms = 0;
+		cudaEventElapsedTime(&ms, e0, e1);
+		const double flops = 2.0 * 64.0 * iters * double(grid.x) * block.x;
+		if (r > 0 && ms > 0)
+			best = std::max(best, flops / (ms * 1e-3) / 1e12);
+	}
+	cudaEventDestroy(e0);
+	cudaEventDestroy(e1);
+	cudaFree(d);
+	return best;
+}
+
+__global__ void qp_probe_copy_kernel(const float4 *__restrict__ src, float4 *__restrict__ dst,
+				     size_t n4)
+{
+	const size_t stride = size_t(gridDim.x) * blockDim.x;
+	for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < n4; i += stride)
+		dst[i] = src[i];
+}
+
+extern "C" double qp_probe_hbm_gbs(int device, size_t bytes, int repeats)
+{
+	const int dev = resolve_device(device);
+	if (dev < 0)
+		return 0.0;
+	DeviceGuard g;
+	if (g.enter(dev) != QP_OK)
+		return 0.0;
+	bytes = std::max<size_t>(bytes, 1 << 20) / 16 * 16;
+	float4 *a = nullptr, *b = nullptr;
+	if (cudaMalloc(&a, bytes) != cudaSuccess)
+		return 0.0;
+	if (cudaMalloc(&b, bytes) != cudaSuccess) {
+		cudaFree(a);
+		return 0.0;
+	}
+	cudaMemset(a, 1, bytes);
+	cudaEvent_t e0, e1;
+	cudaEventCreate(&e0);
+	cudaEventCreate(&e1);
+	double best = 0.0;
+	const int sms = dev_sms(dev);
+	for (int r = 0; r < std::max(1, repeats) + 1; ++r) {
+		cudaEventRecord(e0);
+		qp_probe_copy_kernel<<<sms * 16, 512>>>(a, b, bytes / 16);
+		cudaEventRecord(e1);
+		cudaEventSynchronize(e1);
+		float ms = 0;
+		cudaEventElapsedTime(&ms, e0, e1);
+		if (r > 0 && ms > 0)
+			best = std::max(best, 2.0 * double(bytes) / (ms * 1e-3) / 1e9);
+	}
+	cudaEventDestroy(e0);
+	cudaEventDestroy(e1);
+	cudaFree(a);
+	cudaFree(b);
+	return best;
+}

@@ -1,0 +1,112 @@
+// qp_common.cuh -- shared device-side definitions for the batched box-QP kernels.
+//
+// Target: sm_100a only (B200).  FP32 CUDA cores; bulk asynchronous copies
+// (cp.async.bulk + mbarrier) move problem data between HBM and shared memory.
+#pragma once
+
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "../../include/qp_batch.h"
+
+namespace qpb {
+
+// Kernel arguments: one packed batch resident in device memory.
+// Mirrors qp_batch / qp_batch_solution / qp_options (include/qp_batch.h).
+struct KernelArgs {
+	const float *P, *q, *lb, *ub, *z0, *u0;
+	float *x, *z, *lam;
+	int32_t *status, *iters;
+	unsigned long long count;
+	int n;
+	float lb_s, ub_s;      // scalar box when lb/ub are null
+	float rho, alpha;
+	float eps_abs;         // sqrt(n) * abstol   (qp_solvers.c:242, :252)
+	float reltol;
+	unsigned max_iter;
+};
+
+// ---- PTX wrappers ---------------------------------------------------------
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
+{
+	return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t arrivals)
+{
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(arrivals)
+		     : "memory");
+}
+
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+		     "r"(bytes)
+		     : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+	asm volatile(
+		"{\n"
+		".reg .pred p;\n"
+		"QPB_WAIT:\n"
+		"mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+		"@p bra QPB_DONE;\n"
+		"bra QPB_WAIT;\n"
+		"QPB_DONE:\n"
+		"}\n" ::"r"(smem_u32(bar)),
+		"r"(parity)
+		: "memory");
+}
+
+// global -> shared bulk copy (TMA engine, 1-D), completion on an mbarrier.
+// dst/src 16-byte aligned, bytes a multiple of 16.
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes,
+					 uint64_t *bar)
+{
+	asm volatile(
+		"cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+			"r"(smem_u32(dst)),
+		"l"(src), "r"(bytes), "r"(smem_u32(bar))
+		: "memory");
+}
+
+// shared -> global bulk store, tracked by the per-thread bulk async-group.
+__device__ __forceinline__ void bulk_s2g(void *dst, const void *src, uint32_t bytes)
+{
+	asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst),
+		     "r"(smem_u32(src)), "r"(bytes)
+		     : "memory");
+}
+__device__ __forceinline__ void bulk_commit()
+{
+	asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+// wait until the sources of all committed bulk stores have been read
+__device__ __forceinline__ void bulk_wait_read()
+{
+	asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+// make generic-proxy shared-memory accesses visible to / ordered with the
+// async proxy (bulk copies)
+__device__ __forceinline__ void fence_async_smem()
+{
+	asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+__device__ __forceinline__ float warp_sum(float v)
+{
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1)
+		v += __shfl_xor_sync(0xffffffffu, v, o);
+	return v;
+}
+
+__device__ __forceinline__ bool finite_f(float v)
+{
+	return (v - v) == 0.0f;
+}
+
+} // namespace qpb

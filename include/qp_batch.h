@@ -1,0 +1,194 @@
+/*
+ * qp_batch.h -- C ABI of the B200-native batched box-QP engine (libqpb200.so).
+ *
+ *   minimize   (1/2) x'Px + q'x      subject to   lb <= x <= ub
+ *
+ * solved for `count` independent problems at once with the reference's ADMM
+ * iteration.  Every entry point below names the reference interface it
+ * replaces; paths are relative to the reference repository
+ * (YangLingyuan/Embedded-qp-solver).
+ *
+ *   reference, one problem per call          this library, a batch per call
+ *   ---------------------------------        ------------------------------
+ *   struct _matrix *admm(x0, iterations, qf) qp_solve_batch(), qp_admm_qf(),
+ *     qp_solvers/qp_solvers.h:14-16            qp_admm_qf_batch()
+ *     qp_solvers/qp_solvers.c:255-319
+ *   quadratic_form_eval()  qp.h:20-21        qp_eval_batch()
+ *   kmalloc_init()/static pools              qp_workspace_create()/destroy()
+ *     kmalloc/kmalloc.h:16-18
+ *
+ * Plain C: pointers and sizes only.  All arrays are caller-owned; the library
+ * never allocates or frees memory that the caller sees.  Element order of
+ * every matrix is the reference's row-major `elements[row * ncols + col]`
+ * (matrix/matrix_ops/matrix_ops.c:68-78).  P must be symmetric with
+ * P + rho*I positive definite (a convex QP, ReadMe.txt:1-3); the upper
+ * triangle is what the kernels read.
+ *
+ * The arithmetic type of the batch entry points is binary32 (`float`); the
+ * reference computes in binary64.  The qf entry points take the reference's
+ * own `double` structs and convert.
+ */
+#ifndef QP_BATCH_H
+#define QP_BATCH_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QP_B200_ABI_VERSION 1
+
+/* largest problem dimension the kernels accept */
+#define QP_MAX_DIM 64
+
+/* Per-problem outcome, written to qp_batch_solution.status.  The reference
+ * returns no status; these are defined on its state:        */
+#define QP_STATUS_CONVERGED 0 /* stop test passed, qp_solvers.c:308-309          */
+#define QP_STATUS_MAX_ITER  1 /* loop ran out of `iterations`, qp_solvers.c:284   */
+#define QP_STATUS_SINGULAR  2 /* factorisation of P + rho*I hit a pivot <= 0; the
+                                 reference prints "singular matrix" at
+                                 matrix_ops.c:511-515 and carries on           */
+#define QP_STATUS_NONFINITE 3 /* x contains Inf/NaN                               */
+
+/* Return codes of the API calls (0 = success). */
+#define QP_OK                 0
+#define QP_ERR_INVALID       -1 /* null pointer, n == 0, bad option            */
+#define QP_ERR_UNSUPPORTED   -2 /* n > QP_MAX_DIM                              */
+#define QP_ERR_CUDA          -3 /* a CUDA call failed; see qp_last_error()     */
+#define QP_ERR_NO_DEVICE     -4 /* no usable GPU / device id out of range      */
+
+/* Where the arrays of a batch live. */
+#define QP_MEM_HOST   0 /* host pointers: the call copies in and out, sharding
+                           the batch over the GPUs in device_mask             */
+#define QP_MEM_DEVICE 1 /* device pointers on qp_options.device: the kernel is
+                           launched on qp_options.stream and the call returns
+                           without synchronising                              */
+
+/*
+ * A batch of `count` problems of dimension n, packed back to back.
+ * Replaces one `struct _quadratic_form {p, q, r}` (qp_solvers/qp.h:8-13) per
+ * problem plus the compile-time box ADMM_BOX_CONSTRAINT_{MAX,MIN}
+ * (config.h:29-30, broadcast at qp_solvers.c:277-280).
+ */
+typedef struct qp_batch {
+	uint32_t n;          /* problem dimension (the reference's N_DIM)          */
+	uint32_t mem;        /* QP_MEM_HOST or QP_MEM_DEVICE, for every pointer    */
+	size_t count;        /* number of problems                                 */
+	const float *P;      /* [count][n][n] row-major                            */
+	const float *q;      /* [count][n]                                         */
+	const float *lb;     /* [count][n], or NULL: lb_scalar for every entry     */
+	const float *ub;     /* [count][n], or NULL: ub_scalar for every entry     */
+	float lb_scalar;     /* used when lb == NULL (the reference's only mode)   */
+	float ub_scalar;     /* used when ub == NULL                               */
+	const float *z0;     /* [count][n] warm start of z, or NULL = 0            */
+	const float *u0;     /* [count][n] warm start of u, or NULL = 0
+	                        (the reference zeroes both, qp_solvers.c:263-264)  */
+} qp_batch;
+
+/* Caller-owned outputs; any pointer may be NULL to skip that output. */
+typedef struct qp_batch_solution {
+	float *x;        /* [count][n] what admm() returns: the x-update iterate     */
+	float *z;        /* [count][n] the clipped iterate (always inside the box)   */
+	float *lambda;   /* [count][n] rho*u; >0 upper bound active, <0 lower        */
+	int32_t *status; /* [count]    QP_STATUS_*                                   */
+	int32_t *iters;  /* [count]    iterations executed (i+1 at the break)        */
+} qp_batch_solution;
+
+/* Solver knobs; qp_options_default() installs the reference's constants. */
+typedef struct qp_options {
+	float rho;            /* 1      qp_solvers.c:281                            */
+	float alpha;          /* 1      over-relaxation, qp_solvers.c:282           */
+	float abstol;         /* 1e-4   qp_solvers.c:17                             */
+	float reltol;         /* 1e-2   qp_solvers.c:18                             */
+	uint32_t max_iter;    /* 10000  the `iterations` argument, config.h:38      */
+	uint32_t device_mask; /* QP_MEM_HOST: bit i = use GPU i; 0 = GPU `device`   */
+	int32_t device;       /* CUDA device ordinal, -1 = the current device       */
+	void *stream;         /* QP_MEM_DEVICE: cudaStream_t to launch on (NULL =
+	                         the legacy default stream)                         */
+	uint32_t chunk;       /* QP_MEM_HOST: problems per pipelined copy/solve
+	                         chunk, 0 = choose                                  */
+	uint32_t reserved;
+} qp_options;
+
+void qp_options_default(qp_options *opt);
+
+/*
+ * Solve a batch.  Replaces a loop of
+ *     x = admm(x0, iterations, qf)          qp_solvers/qp_solvers.c:255-319
+ * (as called through the solver function pointer at test/test.c:97).
+ * opt == NULL means qp_options_default().  Never exits the process: API
+ * misuse returns QP_ERR_*, per-problem trouble goes to sol->status[].
+ */
+int qp_solve_batch(const qp_batch *prob, const qp_batch_solution *sol,
+		   const qp_options *opt);
+
+/* Opaque preallocated device workspace: streams, device staging buffers and
+ * pinned host buffers for the QP_MEM_HOST path.  Replaces the reference's
+ * static slab pools (kmalloc/kmalloc.c:37-66).  qp_solve_batch() keeps one
+ * per device internally; create one explicitly to control its lifetime and
+ * to keep the first call free of allocation. */
+typedef struct qp_workspace qp_workspace;
+int qp_workspace_create(uint32_t n, size_t max_count, uint32_t device_mask,
+			qp_workspace **out);
+void qp_workspace_destroy(qp_workspace *ws);
+int qp_solve_batch_ws(qp_workspace *ws, const qp_batch *prob,
+		      const qp_batch_solution *sol, const qp_options *opt);
+
+/*
+ * Objective values f(x) = (1/2) x'Px + q'x + r for a batch (host or device
+ * pointers as prob->mem says; `x`, `f` live where prob's arrays live).
+ * Replaces quadratic_form_eval(), qp_solvers/qp.c:9-27 -- the number the
+ * reference's tests print (test/test.c:100-102).
+ */
+int qp_eval_batch(const qp_batch *prob, const float *x, float r, float *f,
+		  const qp_options *opt);
+
+/*
+ * Entry points on the reference's own structs (binary64, pool-owned).  The
+ * two structs below are layout-identical to `struct _matrix`
+ * (matrix/matrix_type/matrix_type.h:20-23: rows in bits 31:16 and columns in
+ * bits 15:0 of `dimensions`) and `struct _quadratic_form`
+ * (qp_solvers/qp.h:8-13); a reference host passes its own pointers.
+ */
+struct qp_ref_matrix {
+	unsigned dimensions;
+	double *elements;
+};
+struct qp_ref_quadratic_form {
+	struct qp_ref_matrix *p;
+	struct qp_ref_matrix *q;
+	double r;
+};
+
+/* One problem: what the body of a drop-in `admm_b200(x0, iterations, qf)`
+ * calls.  lb/ub are the reference's scalar box.  Writes
+ * n doubles to x_out; status/iters may be NULL. */
+int qp_admm_qf(const struct qp_ref_quadratic_form *qf, unsigned iterations,
+	       double lb, double ub, double *x_out, int32_t *status,
+	       int32_t *iters);
+
+/* Many reference structs at once (array-of-structs host): gathers P and q
+ * from each qfs[i], solves them as one batch, scatters x into x_out[i]
+ * (n doubles each).  All problems must share one dimension. */
+int qp_admm_qf_batch(const struct qp_ref_quadratic_form *const *qfs,
+		     size_t count, unsigned iterations, double lb, double ub,
+		     double *const *x_out, int32_t *status, int32_t *iters,
+		     const qp_options *opt);
+
+/* Diagnostics. */
+const char *qp_last_error(void);      /* text of the last QP_ERR_CUDA, per thread */
+int qp_device_count(void);
+const char *qp_kernel_for(uint32_t n, int aligned16); /* "tpq<16>", "gpq<40>", ... */
+
+/* Measurement helpers used by bench.py for the roofline denominators:
+ * a register-resident FP32 FMA loop (returns TFLOP/s) and a device copy
+ * (returns GB/s, read+write bytes), both timed with CUDA events on `device`. */
+double qp_probe_fp32_tflops(int device, int repeats);
+double qp_probe_hbm_gbs(int device, size_t bytes, int repeats);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QP_BATCH_H */

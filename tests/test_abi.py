@@ -1,0 +1,85 @@
+"""CPU: the C-ABI shared library loads, exports every symbol the header declares,
+and rejects API misuse without touching a GPU."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_functions():
+    src = open(os.path.join(ROOT, "include", "qp_batch.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    names = re.findall(r"\b(qp_[a-z0-9_]+)\s*\(", src)
+    return sorted(set(names))
+
+
+def test_header_and_library_agree(qp):
+    lib = qp.load_library()
+    declared = header_functions()
+    assert declared, "no functions parsed from include/qp_batch.h"
+    missing = [f for f in declared if not hasattr(lib, f)]
+    assert not missing, f"declared in qp_batch.h but not exported: {missing}"
+    assert sorted(qp.ABI_SYMBOLS) == declared
+
+
+def test_default_options_are_the_reference_constants(qp):
+    from embedded_qp_solver_b200 import api
+    o = api.qp_options()
+    qp.load_library().qp_options_default(C.byref(o))
+    # rho, alpha: qp_solvers.c:281-282; ABSTOL, RELTOL: :17-18; ADMM_ITERATIONS: config.h:38
+    assert (o.rho, o.alpha, o.max_iter) == (1.0, 1.0, 10000)
+    assert o.abstol == np.float32(1e-4) and o.reltol == np.float32(1e-2)
+    assert o.device == -1 and o.device_mask == 0
+
+
+def test_struct_sizes_match_header(qp):
+    from embedded_qp_solver_b200 import api
+    assert C.sizeof(api.qp_batch) == 72
+    assert C.sizeof(api.qp_batch_solution) == 40
+    assert C.sizeof(api.qp_options) == 48
+
+
+def test_api_misuse_returns_error_codes(qp):
+    from embedded_qp_solver_b200 import api
+    lib = qp.load_library()
+    pb, sol = api.qp_batch(), api.qp_batch_solution()
+    assert lib.qp_solve_batch(None, C.byref(sol), None) == api.QP_ERR_INVALID
+    pb.n, pb.count = 0, 1
+    assert lib.qp_solve_batch(C.byref(pb), C.byref(sol), None) == api.QP_ERR_INVALID
+    pb.n = 65
+    assert lib.qp_solve_batch(C.byref(pb), C.byref(sol), None) == api.QP_ERR_UNSUPPORTED
+    pb.n = 16  # null P with count > 0
+    assert lib.qp_solve_batch(C.byref(pb), C.byref(sol), None) == api.QP_ERR_INVALID
+    pb.count = 0  # an empty batch is fine, even without a GPU
+    assert lib.qp_solve_batch(C.byref(pb), C.byref(sol), None) == api.QP_OK
+    P = np.zeros((1, 16, 16), np.float32)
+    q = np.zeros((1, 16), np.float32)
+    with pytest.raises(qp.QpError):
+        qp.solve_batch(P, q, options=qp.Options(rho=0.0))
+    with pytest.raises(qp.QpError):
+        qp.solve_batch(P, q, options=qp.Options(alpha=2.5))
+
+
+def test_kernel_selection(qp):
+    assert qp.kernel_for(4) == "tpq<4>" and qp.kernel_for(16) == "tpq<16>"
+    assert qp.kernel_for(16, aligned16=False) == "gpq<16>"
+    assert qp.kernel_for(40) == "gpq<40>" and qp.kernel_for(64) == "gpq<64>"
+    assert qp.kernel_for(13) == "gpq<16>" and qp.kernel_for(65) == "unsupported"
+
+
+def test_roofline_bookkeeping(qp):
+    # 152 / 1352 / 7208 / 17672 bytes without z; +4n with z
+    assert [qp.algorithmic_bytes(n, with_z=False) for n in (4, 16, 40, 64)] == \
+        [152, 1352, 7208, 17672]
+    assert qp.algorithmic_bytes(64, warm=True, with_z=False) == 18184
+    assert round(qp.algorithmic_flops(16, 12)) == 21675
+
+
+def test_missing_library_fails_loudly(qp, tmp_path):
+    from embedded_qp_solver_b200 import api
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        api.load_library(str(tmp_path / "nope.so"))

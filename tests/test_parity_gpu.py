@@ -1,0 +1,364 @@
+"""GPU: the CUDA path (through the C ABI, libqpb200.so) against the oracle and the
+golden vectors the unmodified reference produced.
+
+Bars (BASELINE.json north_star):
+  * status and iteration count identical on every non-degenerate problem
+    (stop-test margin > 1e-3, conftest.nondegenerate), active set identical;
+  * ||x - x_ref||_inf / (1 + ||x_ref||_inf) <= 1e-4 against the FP64 reference.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden_files, load_golden, nondegenerate
+from embedded_qp_solver_b200 import problems
+
+pytestmark = pytest.mark.gpu
+
+X_TOL = 1e-4          # north_star tolerance on x, FP32 kernel vs FP64 reference
+FIXED_K_TOL = 2e-5    # fixed-iteration-count runs: pure arithmetic difference
+
+
+def dev(*arrs):
+    return [torch.from_numpy(np.ascontiguousarray(a)).cuda() if a is not None else None
+            for a in arrs]
+
+
+def solve_dev(qp, P, q, lb, ub, **kw):
+    tP, tq, tlb, tub = dev(P, q, lb, ub)
+    z0, u0 = kw.pop("z0", None), kw.pop("u0", None)
+    tz0, tu0 = dev(z0, u0)
+    r = qp.solve_batch(tP, tq, tlb, tub, z0=tz0, u0=tu0, **kw)
+    torch.cuda.synchronize()
+    return {k: v.cpu().numpy() for k, v in r.items()}
+
+
+def rel_err(x, x_ref):
+    return np.max(np.abs(x - x_ref), axis=1) / (1 + np.max(np.abs(x_ref), axis=1))
+
+
+def active_set(z, lb, ub):
+    return (z == lb).astype(np.int8) - (z == ub).astype(np.int8)
+
+
+def check_against(res, g, lb, ub, what):
+    ok = nondegenerate(g["margins"]) & (g["status"] == 0)
+    assert ok.sum() >= 0.5 * len(ok), f"{what}: too few non-degenerate problems"
+    assert np.array_equal(res["status"][ok], g["status"][ok]), what
+    assert np.array_equal(res["iters"][ok], g["iters"][ok]), what
+    assert np.array_equal(active_set(res["z"][ok], lb[ok], ub[ok]),
+                          active_set(g["z"][ok].astype(np.float32), lb[ok], ub[ok])), what
+    e = rel_err(res["x"][ok].astype(np.float64), g["x_ref"][ok])
+    assert e.max() <= X_TOL, f"{what}: max rel err {e.max():.3e}"
+    ez = rel_err(res["z"][ok].astype(np.float64), g["z"][ok])
+    assert ez.max() <= X_TOL
+    lam_ref = g["u"][ok]  # rho = 1
+    el = np.max(np.abs(res["lam"][ok] - lam_ref), axis=1) / (1 + np.max(np.abs(lam_ref), axis=1))
+    assert el.max() <= 10 * X_TOL
+
+
+WELL = [p for p in golden_files() if "refdist" not in os.path.basename(p)]
+
+
+@pytest.mark.parametrize("path", WELL, ids=os.path.basename)
+def test_golden_reference_vectors(qp, path):
+    """Golden x/iters/status from the UNMODIFIED reference (well-conditioned sets
+    and the MPC shape): exact iteration counts, x within 1e-4."""
+    g = load_golden(path)
+    res = solve_dev(qp, g["P"], g["q"], g["lb"], g["ub"])
+    check_against(res, g, g["lb"], g["ub"], os.path.basename(path))
+
+
+@pytest.mark.parametrize("path", [p for p in golden_files() if "refdist" in p],
+                         ids=os.path.basename)
+def test_golden_reference_distribution_fixed_k(qp, orc, path):
+    """The reference's own (ill-conditioned) test distribution: FP32 cannot follow
+    the FP64 stop test there, so compare the arithmetic at
+    a fixed iteration count K, where both sides run exactly K steps."""
+    g = load_golden(path)
+    P64, q64 = g["P"].astype(np.float64), g["q"].astype(np.float64)
+    for K in (1, 5):
+        o = orc.admm(P64, q64, g["lb"].astype(np.float64), g["ub"].astype(np.float64),
+                     max_iter=K, abstol=0.0, reltol=0.0)
+        res = solve_dev(qp, g["P"], g["q"], g["lb"], g["ub"],
+                        options=qp.Options(max_iter=K, abstol=0.0, reltol=0.0))
+        assert np.all(res["iters"] == K) and np.all(res["status"] == 1)
+        cond = np.linalg.cond(P64 + np.eye(P64.shape[1]))
+        easy = cond < 1e3
+        e = rel_err(res["x"].astype(np.float64), o["x"])
+        assert e[easy].max() <= 50 * FIXED_K_TOL, (K, e[easy].max())
+        # everything, including cond ~1e4 problems, stays within cond * eps_f32
+        assert np.all(e <= 4 * cond * 6e-8 + 1e-6)
+
+
+@pytest.mark.parametrize("n", [4, 8, 12, 16, 5, 13, 24, 32, 40, 48, 64])
+def test_random_batches_against_oracle(qp, orc, n):
+    """Fresh seeded problems at every kernel shape (tpq: 4/8/12/16, gpq: the rest),
+    batch sizes that are not multiples of the warp batch."""
+    count = 1000 + 37 if n <= 16 else 131
+    P, q, lb, ub = problems.wellcond(count, n, seed=100 + n, beta=0.5)
+    o = orc.admm(P.astype(np.float64), q.astype(np.float64), lb, ub)
+    res = solve_dev(qp, P, q, lb, ub)
+    g = dict(x_ref=o["x"], z=o["z"], u=o["u"], iters=o["iters"], status=o["status"],
+             margins=o["margins"])
+    check_against(res, g, lb, ub, f"n={n}")
+
+
+@pytest.mark.parametrize("n", [4, 16, 40, 64])
+def test_fixed_k_matches_oracle_arithmetic(qp, orc, n):
+    count = 256 if n <= 16 else 32
+    P, q, lb, ub = problems.wellcond(count, n, seed=200 + n, beta=0.5)
+    for K in (1, 2, 7):
+        o = orc.admm(P.astype(np.float64), q.astype(np.float64), lb, ub, max_iter=K,
+                     abstol=0.0, reltol=0.0)
+        res = solve_dev(qp, P, q, lb, ub, options=qp.Options(max_iter=K, abstol=0.0, reltol=0.0))
+        assert np.all(res["iters"] == K) and np.all(res["status"] == qp.STATUS_MAX_ITER)
+        assert rel_err(res["x"].astype(np.float64), o["x"]).max() <= FIXED_K_TOL
+        assert np.max(np.abs(res["lam"] - o["u"])) <= 1e-4
+
+
+@pytest.mark.parametrize("n", [4, 16, 40])
+def test_scalar_box_equals_array_box(qp, n):
+    """lb/ub = NULL + scalars (the reference's only mode, qp_solvers.c:277-280) is
+    the same computation as uniform arrays."""
+    P, q, lb, ub = problems.wellcond(200, n, seed=300 + n, beta=0.5)
+    a = solve_dev(qp, P, q, lb, ub)
+    tP, tq = dev(P, q)
+    b = qp.solve_batch(tP, tq, -0.5, 0.5)
+    torch.cuda.synchronize()
+    for k in ("x", "z", "lam", "iters", "status"):
+        assert np.array_equal(a[k], b[k].cpu().numpy()), k
+
+
+@pytest.mark.parametrize("n", [8, 16, 40])
+def test_per_coordinate_bounds(qp, orc, n):
+    count = 300 if n <= 16 else 40
+    P, q, _, _ = problems.wellcond(count, n, seed=400 + n)
+    rng = np.random.default_rng(n)
+    lb = (-rng.uniform(0.05, 1.0, (count, n))).astype(np.float32)
+    ub = rng.uniform(0.05, 1.0, (count, n)).astype(np.float32)
+    o = orc.admm(P.astype(np.float64), q.astype(np.float64), lb.astype(np.float64),
+                 ub.astype(np.float64))
+    res = solve_dev(qp, P, q, lb, ub)
+    g = dict(x_ref=o["x"], z=o["z"], u=o["u"], iters=o["iters"], status=o["status"],
+             margins=o["margins"])
+    check_against(res, g, lb, ub, f"bounds n={n}")
+    assert np.all(res["z"] >= lb) and np.all(res["z"] <= ub)
+
+
+@pytest.mark.parametrize("n", [16, 64])
+def test_warm_start(qp, orc, n):
+    """BASELINE config 5: re-solve from the (z,u) of a previous solve after
+    perturbing q.  The reference ignores x0 (qp_solvers.c:256); the oracle
+    restates its loop started from (z0,u0)."""
+    count = 128 if n <= 16 else 16
+    P, q, lb, ub = problems.wellcond(count, n, seed=500 + n, beta=0.5)
+    first = solve_dev(qp, P, q, lb, ub)
+    q2 = problems.perturb_q(q, seed=9)
+    z0, u0 = first["z"], first["lam"]  # rho = 1: u = lambda
+    o = orc.admm(P.astype(np.float64), q2.astype(np.float64), lb, ub,
+                 z0=z0.astype(np.float64), u0=u0.astype(np.float64))
+    cold = orc.admm(P.astype(np.float64), q2.astype(np.float64), lb, ub)
+    res = solve_dev(qp, P, q2, lb, ub, z0=z0, u0=u0)
+    g = dict(x_ref=o["x"], z=o["z"], u=o["u"], iters=o["iters"], status=o["status"],
+             margins=o["margins"])
+    check_against(res, g, lb, ub, f"warm n={n}")
+    assert o["iters"].mean() < cold["iters"].mean()
+
+
+def test_resolving_from_the_solution_is_idempotent(qp):
+    """Size-independent property: started at a converged (z,u), ADMM stops at once
+    and returns the same point."""
+    P, q, lb, ub = problems.wellcond(500, 16, seed=600, beta=0.5)
+    tight = qp.Options(abstol=1e-6, reltol=1e-6, max_iter=2000)
+    a = solve_dev(qp, P, q, lb, ub, options=tight)
+    b = solve_dev(qp, P, q, lb, ub, z0=a["z"], u0=a["lam"], options=tight)
+    assert np.all(b["iters"] <= 2)
+    assert np.max(np.abs(a["z"] - b["z"])) <= 1e-5
+
+
+@pytest.mark.parametrize("n", [4, 16, 40, 64])
+def test_kkt_at_tight_tolerance(qp, n):
+    """north_star: KKT residual <= 1e-5 (relative).  With the reference's loose
+    reltol = 1e-2 the iterate is not yet a KKT point, so the KKT test runs the
+    same kernel to a tight tolerance: stationarity P z + q + lambda = 0, z in the
+    box, lambda's sign consistent with the active bound."""
+    count = 256 if n <= 16 else 32
+    P, q, lb, ub = problems.wellcond(count, n, seed=700 + n, beta=0.5)
+    res = solve_dev(qp, P, q, lb, ub, options=qp.Options(abstol=1e-7, reltol=1e-7, max_iter=5000))
+    P64, z, lam = P.astype(np.float64), res["z"].astype(np.float64), res["lam"].astype(np.float64)
+    grad = np.einsum("cij,cj->ci", P64, z) + q
+    stat = np.max(np.abs(grad + lam), axis=1) / (1 + np.max(np.abs(grad), axis=1))
+    assert stat.max() <= 1e-5, stat.max()
+    assert np.all(z >= lb) and np.all(z <= ub)
+    inside = (z > lb) & (z < ub)
+    assert np.max(np.abs(lam[inside])) <= 1e-4
+    assert np.all(lam[z == ub] >= -1e-5) and np.all(lam[z == lb] <= 1e-5)
+    assert np.max(np.abs(res["x"] - res["z"])) <= 1e-4
+
+
+def test_over_relaxation_and_rho(qp, orc):
+    P, q, lb, ub = problems.wellcond(300, 16, seed=800, beta=0.5)
+    for rho, alpha in ((1.0, 1.6), (2.5, 1.0), (0.5, 1.3)):
+        o = orc.admm(P.astype(np.float64), q.astype(np.float64), lb, ub, rho=rho, alpha=alpha)
+        res = solve_dev(qp, P, q, lb, ub, options=qp.Options(rho=rho, alpha=alpha))
+        ok = nondegenerate(o["margins"])
+        assert np.array_equal(res["iters"][ok], o["iters"][ok])
+        assert rel_err(res["x"][ok].astype(np.float64), o["x"][ok]).max() <= X_TOL
+        assert np.max(np.abs(res["lam"][ok] - rho * o["u"][ok])) <= 1e-3
+
+
+def test_edge_cases(qp, orc):
+    n = 16
+    P, q, lb, ub = problems.wellcond(33, n, seed=900, beta=0.5)
+    # empty batch
+    r = qp.solve_batch(torch.empty((0, n, n), device="cuda"), torch.empty((0, n), device="cuda"))
+    assert r["x"].shape == (0, n)
+    # one problem; 31, 32, 33 problems (ragged warp batches)
+    for c in (1, 31, 32, 33):
+        res = solve_dev(qp, P[:c], q[:c], lb[:c], ub[:c])
+        full = solve_dev(qp, P, q, lb, ub)
+        for k in ("x", "z", "lam", "iters", "status"):
+            assert np.array_equal(res[k], full[k][:c]), (c, k)
+    # iteration cap -> status 1, iters == cap
+    res = solve_dev(qp, P, q, lb, ub, options=qp.Options(max_iter=3))
+    assert np.all(res["status"] == qp.STATUS_MAX_ITER) and np.all(res["iters"] == 3)
+    # max_iter = 0: nothing runs, x = 0
+    res = solve_dev(qp, P, q, lb, ub, options=qp.Options(max_iter=0))
+    assert np.all(res["iters"] == 0) and np.all(res["x"] == 0)
+    # P + rho I singular / not positive definite -> status 2 (reference: "singular matrix")
+    Pb = P.copy()
+    Pb[5] = -np.eye(n, dtype=np.float32)
+    Pb[7] = -3 * np.eye(n, dtype=np.float32)
+    res = solve_dev(qp, Pb, q, lb, ub)
+    assert res["status"][5] == qp.STATUS_SINGULAR and res["status"][7] == qp.STATUS_SINGULAR
+    o = orc.admm(Pb[5:6].astype(np.float64), q[5:6].astype(np.float64), lb[5:6], ub[5:6])
+    assert o["status"][0] == qp.STATUS_SINGULAR
+    good = np.ones(33, bool)
+    good[[5, 7]] = False
+    ref = solve_dev(qp, P, q, lb, ub)
+    assert np.array_equal(res["x"][good], ref["x"][good])
+    # non-finite input -> status 3, neighbours unaffected
+    qn = q.copy()
+    qn[2, 3] = np.inf
+    res = solve_dev(qp, P, qn, lb, ub)
+    assert res["status"][2] == qp.STATUS_NONFINITE
+    assert np.array_equal(res["x"][3:], ref["x"][3:])
+    # the same on the warp-per-QP kernel
+    P40, q40, lb40, ub40 = problems.wellcond(9, 40, seed=901, beta=0.5)
+    P40[4] = -np.eye(40, dtype=np.float32)
+    q40[6, 0] = np.nan
+    res = solve_dev(qp, P40, q40, lb40, ub40, options=qp.Options(max_iter=50))
+    assert res["status"][4] == qp.STATUS_SINGULAR and res["status"][6] == qp.STATUS_NONFINITE
+    assert np.all(res["status"][[0, 1, 2, 3, 5, 7, 8]] == 0)
+
+
+def test_misaligned_pointers_take_the_generic_kernel(qp):
+    """tpq needs 16-byte aligned arrays (bulk copies); anything else must still
+    give the same answer through gpq."""
+    n, c = 16, 100
+    P, q, lb, ub = problems.wellcond(c, n, seed=1000, beta=0.5)
+    base = solve_dev(qp, P, q, lb, ub)
+    buf = torch.zeros(c * n * n + 1, device="cuda")
+    tP = buf[1:].view(c, n, n)
+    tP.copy_(torch.from_numpy(P))
+    assert tP.data_ptr() % 16 == 4
+    tq, = dev(q)
+    r = qp.solve_batch(tP, tq, -0.5, 0.5)
+    torch.cuda.synchronize()
+    assert np.array_equal(r["iters"].cpu().numpy(), base["iters"])
+    assert np.max(np.abs(r["x"].cpu().numpy() - base["x"])) <= 1e-5
+
+
+def test_host_path_equals_device_path(qp):
+    """QP_MEM_HOST (chunked copy/solve pipeline, pageable and pinned memory) returns
+    bit-identical results to QP_MEM_DEVICE."""
+    n, c = 16, 5000
+    P, q, lb, ub = problems.wellcond(c, n, seed=1100, beta=0.5)
+    d = solve_dev(qp, P, q, lb, ub)
+    h = qp.solve_batch(P, q, lb, ub, options=qp.Options(chunk=1024))       # pageable, 5 chunks
+    for k in d:
+        assert np.array_equal(d[k], h[k]), k
+    pin = [torch.from_numpy(a).pin_memory() for a in (P, q, lb, ub)]
+    out = {k: torch.empty((c, n), dtype=torch.float32).pin_memory() for k in ("x", "z", "lam")}
+    out.update({k: torch.empty(c, dtype=torch.int32).pin_memory() for k in ("status", "iters")})
+    qp.solve_batch(*pin, options=qp.Options(chunk=2048), out=out)            # pinned, in place
+    for k in d:
+        assert np.array_equal(d[k], out[k].numpy()), k
+    ws = qp.Workspace(n, c)
+    h2 = qp.solve_batch(P, q, lb, ub, workspace=ws)
+    ws.close()
+    for k in d:
+        assert np.array_equal(d[k], h2[k]), k
+    # n = 40 through the host path as well
+    P, q, lb, ub = problems.wellcond(300, 40, seed=1101, beta=0.5)
+    d = solve_dev(qp, P, q, lb, ub)
+    h = qp.solve_batch(P, q, lb, ub)
+    for k in d:
+        assert np.array_equal(d[k], h[k]), k
+
+
+def test_reference_operator_mirror(qp, orc):
+    """admm(x0, iterations, qf) on the reference's own structs (qp_admm_qf):
+    same call shape as test/test.c:97, double in / double out."""
+    g = load_golden(os.path.join(os.path.dirname(golden_files()[0]), "wellcond_free_n16.npz"))
+    for c in range(4):
+        qf = qp.QuadraticForm(g["P"][c].astype(np.float64), g["q"][c].astype(np.float64), 0.0)
+        info = {}
+        x = qp.admm(np.zeros((16, 1)), 10000, qf, info=info)
+        assert x.shape == (16, 1) and x.dtype == np.float64
+        assert info["status"] == 0 and info["iters"] == g["iters"][c]
+        assert rel_err(x.T, g["x_ref"][c:c + 1]).max() <= X_TOL
+        # the objective the reference's tests print (test/test.c:100-102)
+        f = orc.eval(g["P"][c].astype(np.float64), g["q"][c].astype(np.float64), 0.0, x[:, 0])
+        assert abs(f - g["f_ref"][c]) <= 1e-4 * (1 + abs(g["f_ref"][c]))
+    qfs = [qp.QuadraticForm(g["P"][c].astype(np.float64), g["q"][c].astype(np.float64))
+           for c in range(20)]
+    xs, st, it = qp.admm_many(qfs, 10000)
+    assert np.array_equal(it, g["iters"][:20]) and np.all(st == 0)
+    assert rel_err(xs, g["x_ref"][:20]).max() <= X_TOL
+
+
+def test_eval_batch(qp, orc):
+    P, q, _, _ = problems.wellcond(64, 16, seed=1200)
+    x = np.random.default_rng(0).standard_normal((64, 16)).astype(np.float32)
+    f_dev = qp.eval_batch(*dev(P, q, x), r=0.25).cpu().numpy()
+    f_host = qp.eval_batch(P, q, x, r=0.25)
+    f_ref = np.array([orc.eval(P[c].astype(np.float64), q[c].astype(np.float64), 0.25,
+                               x[c].astype(np.float64)) for c in range(64)])
+    assert np.max(np.abs(f_dev - f_ref)) <= 1e-4 * (1 + np.abs(f_ref).max())
+    assert np.array_equal(f_dev, f_host)
+
+
+def test_full_size_headline_properties(qp, orc):
+    """BASELINE headline size (2^20 problems, n = 16): checks that do not need the
+    oracle on every problem -- feasibility of z, status/iteration statistics,
+    a deterministic checksum across two runs, and oracle agreement on a sample."""
+    n, count = 16, 1 << 20
+    gen = torch.Generator(device="cuda").manual_seed(2026)
+    G = torch.randn((count, n, n), generator=gen, device="cuda")
+    P = torch.baddbmm(torch.eye(n, device="cuda").expand(count, n, n), G.transpose(1, 2), G,
+                      alpha=1.0 / n)
+    P = (0.5 * (P + P.transpose(1, 2))).contiguous()
+    q = torch.randn((count, n), generator=gen, device="cuda")
+    del G
+    r1 = qp.solve_batch(P, q, -0.5, 0.5)
+    torch.cuda.synchronize()
+    r2 = qp.solve_batch(P, q, -0.5, 0.5)
+    torch.cuda.synchronize()
+    for k in r1:
+        assert torch.equal(r1[k], r2[k]), k            # deterministic
+    assert int((r1["status"] != 0).sum()) == 0
+    assert float(r1["z"].abs().max()) <= 0.5
+    it = r1["iters"].float()
+    assert 8.0 < float(it.mean()) < 12.5 and int(r1["iters"].max()) < 40
+    idx = torch.randint(0, count, (2000,), generator=torch.Generator().manual_seed(1))
+    Ps, qs = P[idx.cuda()].cpu().numpy(), q[idx.cuda()].cpu().numpy()
+    o = orc.admm(Ps.astype(np.float64), qs.astype(np.float64), -0.5, 0.5)
+    ok = nondegenerate(o["margins"])
+    assert ok.mean() > 0.9
+    assert np.array_equal(r1["iters"][idx.cuda()].cpu().numpy()[ok], o["iters"][ok])
+    e = rel_err(r1["x"][idx.cuda()].cpu().numpy()[ok].astype(np.float64), o["x"][ok])
+    assert e.max() <= X_TOL
