@@ -88,7 +88,8 @@ def test_golden_reference_distribution_fixed_k(qp, orc, path):
         cond = np.linalg.cond(P64 + np.eye(P64.shape[1]))
         easy = cond < 1e3
         e = rel_err(res["x"].astype(np.float64), o["x"])
-        assert e[easy].max() <= 50 * FIXED_K_TOL, (K, e[easy].max())
+        if easy.any():
+            assert e[easy].max() <= 50 * FIXED_K_TOL, (K, e[easy].max())
         # everything, including cond ~1e4 problems, stays within cond * eps_f32
         assert np.all(e <= 4 * cond * 6e-8 + 1e-6)
 
