@@ -324,7 +324,8 @@ def run_ours(args, rank, local_rank, world):
         hbm_src = "MEASURED_PEAKS.json (burst copy)"
     fp32_peak = qp.probe_fp32_tflops(local_rank, 5)
     kernel_s = ms_per_step * 1e-3  # one launch per step: the step IS the kernel
-    bytes_per = qp.algorithmic_bytes(n, warm=False, with_z=True)
+    # this launch: scalar box (no lb/ub arrays), cold start, x/z/lambda/status/iters written
+    bytes_per = qp.algorithmic_bytes(n, warm=False, with_z=True, bound_arrays=False)
     flops_per = qp.algorithmic_flops(n, mean_iters)
     hbm = {"bound": "hbm", "achieved": bytes_per * count / kernel_s / 1e9, "peak": hbm_peak,
            "unit": "GB/s", "peak_source": hbm_src, "bytes_per_problem": bytes_per}
@@ -336,7 +337,15 @@ def run_ours(args, rank, local_rank, world):
     fp["frac"] = fp["achieved"] / fp["peak"] if fp32_peak > 0 else None
     binding = fp if (fp["frac"] or 0) >= hbm["frac"] else hbm
     roofline = dict(binding)
+    # DRAM bytes per launch of this kernel from the committed `ncu --set full` capture
+    # (profiles/traffic.json, keyed by kernel and batch size); null when not captured
     roofline["traffic"] = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        rec = json.load(open(tpath)).get(f"{qp.kernel_for(n)}@{count}")
+        if rec:
+            roofline["traffic"] = rec["dram_bytes_per_launch"]
+            roofline["traffic_source"] = rec["source"]
     roofline["kernel"] = qp.kernel_for(n)
     roofline["hbm"] = hbm
     roofline["fp32"] = fp

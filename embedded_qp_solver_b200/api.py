@@ -381,10 +381,15 @@ def probe_hbm_gbs(device: int = -1, nbytes: int = 1 << 30, repeats: int = 5) -> 
 
 # ---- roofline bookkeeping --------------------------------------------------
 
-def algorithmic_bytes(n: int, warm: bool = False, with_z: bool = True) -> int:
-    """HBM bytes one problem must move: in (n^2+3n) floats [+2n warm start],
-    out x,lambda (+z) and status,iters."""
-    b = (n * n + 3 * n) * 4 + (2 * n * 4 if warm else 0) + 2 * n * 4 + 8
+def algorithmic_bytes(n: int, warm: bool = False, with_z: bool = True,
+                      bound_arrays: bool = True) -> int:
+    """HBM bytes one problem must move: in P, q (+ lb, ub when they
+    are arrays; the reference's scalar box moves nothing) [+ z0, u0 warm start],
+    out x, lambda (+ z) and status, iters.
+    n=16: 1352 with bound arrays and no z (the SURVEY figure); 1288 for the
+    benchmark configuration (scalar box, z written)."""
+    b = (n * n + n) * 4 + (2 * n * 4 if bound_arrays else 0) + (2 * n * 4 if warm else 0)
+    b += 2 * n * 4 + 8
     return b + (4 * n if with_z else 0)
 
 

@@ -1,0 +1,48 @@
+/*
+ * admm_b200.c -- drop-in replacement for the reference's admm() with the
+ * reference's exact solver signature (qp_solvers/qp_solvers.h:14-16):
+ *
+ *     struct _matrix *admm_b200(struct _matrix *x0, unsigned iterations,
+ *                               struct _quadratic_form *qf);
+ *
+ * This file is compiled INSIDE the reference's build (it includes the
+ * reference's headers and uses its pool allocator for the returned vector, so
+ * that the caller's matrix_free(x) at test/test.c:105 keeps working) and is
+ * linked against libqpb200.so.  It can be handed to the reference's solver
+ * function pointer unchanged:
+ *
+ *     test_optimizer(qf, ADMM_ITERATIONS, x0, "admm_b200", admm_b200);
+ *
+ * Like the reference, x0 is accepted and ignored (qp_solvers.c:256), the box
+ * is the compile-time scalar pair ADMM_BOX_CONSTRAINT_{MIN,MAX}
+ * (config.h:29-30) and the result is a freshly pool-allocated N x 1 matrix.
+ * On failure it returns 0 like the reference's allocators do; it never exits.
+ */
+#include <stdio.h>
+
+#include "matrix_ops.h"
+#include "qp.h"
+#include "qp_solvers.h"
+
+#include "qp_batch.h"
+
+struct _matrix *admm_b200(struct _matrix *x0, unsigned iterations,
+			  struct _quadratic_form *qf)
+{
+	(void)x0;
+	struct _matrix *x = matrix_alloc(Nx1);
+	if (!x)
+		return 0;
+	/* struct qp_ref_quadratic_form / qp_ref_matrix are layout-identical to
+	 * the reference structs (checked by tests/test_oracle_vs_ref.py) */
+	int rc = qp_admm_qf((const struct qp_ref_quadratic_form *)qf, iterations,
+			    ADMM_BOX_CONSTRAINT_MIN, ADMM_BOX_CONSTRAINT_MAX,
+			    x->elements, 0, 0);
+	if (rc != QP_OK) {
+		fprintf(stderr, "admm_b200: qp_admm_qf failed (%d) %s\n", rc,
+			qp_last_error());
+		matrix_free(x);
+		return 0;
+	}
+	return x;
+}

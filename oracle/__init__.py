@@ -41,6 +41,9 @@ def build(ref: bool | None = None) -> None:
         ref = os.path.isdir(REFERENCE_ROOT)
     if ref:
         subprocess.run(["make", "-s", "-C", HERE, "ref"], check=True)
+        if os.path.exists(os.path.join(HERE, "..", "embedded_qp_solver_b200", "lib",
+                                       "libqpb200.so")):
+            subprocess.run(["make", "-s", "-C", HERE, "compat"], check=True)
 
 
 def _ptr(a, ctype):

@@ -76,6 +76,8 @@ def test_roofline_bookkeeping(qp):
     assert [qp.algorithmic_bytes(n, with_z=False) for n in (4, 16, 40, 64)] == \
         [152, 1352, 7208, 17672]
     assert qp.algorithmic_bytes(64, warm=True, with_z=False) == 18184
+    # benchmark configuration: scalar box (nothing to load), z written
+    assert qp.algorithmic_bytes(16, bound_arrays=False) == 1288
     assert round(qp.algorithmic_flops(16, 12)) == 21675
 
 

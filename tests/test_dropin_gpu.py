@@ -1,0 +1,47 @@
+"""GPU: the reference's own program structure with the drop-in solver swapped in.
+
+oracle/_ref/libqpcompat.so is the UNMODIFIED reference built with ITS OWN config.h
+(N_DIM = 48, box +-1e12) plus embedded_qp_solver_b200/csrc/compat/admm_b200.c, linked
+against libqpb200.so (oracle/Makefile target `compat`).  compat_run() draws a problem
+with the reference's generators (matirx_random_pos_def, matrix_random; main.c:36-40),
+calls the reference's test_optimizer() through the solver function pointer
+(test/test.c:89-106) with `admm` and with `admm_b200`, and returns both solutions.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB = os.path.join(ROOT, "oracle", "_ref", "libqpcompat.so")
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(not os.path.exists(LIB), reason="libqpcompat.so not built")]
+
+
+def test_reference_harness_runs_with_admm_b200(qp, orc, capfd):
+    qp.load_library()
+    lib = C.CDLL(LIB)
+    lib.compat_dim.restype = C.c_uint
+    n = lib.compat_dim()
+    assert n == 48  # the reference's own config.h:5
+    d = C.POINTER(C.c_double)
+    lib.compat_run.restype = C.c_int
+    lib.compat_run.argtypes = [C.c_uint, d, d, d, d, d]
+    for seed in (1, 2, 3):
+        x_ref, x_gpu = np.zeros(n), np.zeros(n)
+        f = np.zeros(2)
+        P, q = np.zeros((n, n)), np.zeros(n)
+        rc = lib.compat_run(seed, x_ref.ctypes.data_as(d), x_gpu.ctypes.data_as(d),
+                            f.ctypes.data_as(d), P.ctypes.data_as(d), q.ctypes.data_as(d))
+        assert rc == 0
+        # the comparison the reference makes by eye: printed objectives agree
+        # (test/test.c:100-102 prints %e, 7 significant digits)
+        assert abs(f[1] - f[0]) <= 1e-3 * abs(f[0]), (seed, f)
+        # and the restatement agrees with what the reference's admm returned here
+        o = orc.admm(P[None], q[None], -1e12, 1e12)
+        assert np.array_equal(o["x"][0], x_ref)
+        assert np.all(np.isfinite(x_gpu))
+    out = capfd.readouterr().out
+    assert out.count("admm_b200 gave:") == 3 and out.count("admm gave:") == 3
