@@ -118,11 +118,12 @@ bool tpq_eligible(const KernelArgs &a)
 	return true;
 }
 
-template <int N, bool B, bool W> int launch_tpq(const KernelArgs &a, int dev, cudaStream_t st)
+template <int N, bool B, bool W, bool R>
+int launch_tpq(const KernelArgs &a, int dev, cudaStream_t st)
 {
 	using L = TpqLayout<N, B, W>;
 	using Cfg = TpqCfg<N>;
-	auto kern = qp_tpq_kernel<N, B, W>;
+	auto kern = qp_tpq_kernel<N, B, W, R>;
 	static bool attr_done[64] = {};
 	if (!attr_done[dev]) {
 		QP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -142,13 +143,22 @@ template <int N, bool B, bool W> int launch_tpq(const KernelArgs &a, int dev, cu
 template <int N> int launch_tpq_n(const KernelArgs &a, int dev, cudaStream_t st)
 {
 	const bool b = a.lb != nullptr, w = a.z0 != nullptr;
+	if (a.alpha != 1.0f) { // over-relaxation: separate instantiation, not a branch in the loop
+		if (b && w)
+			return launch_tpq<N, true, true, true>(a, dev, st);
+		if (b)
+			return launch_tpq<N, true, false, true>(a, dev, st);
+		if (w)
+			return launch_tpq<N, false, true, true>(a, dev, st);
+		return launch_tpq<N, false, false, true>(a, dev, st);
+	}
 	if (b && w)
-		return launch_tpq<N, true, true>(a, dev, st);
+		return launch_tpq<N, true, true, false>(a, dev, st);
 	if (b)
-		return launch_tpq<N, true, false>(a, dev, st);
+		return launch_tpq<N, true, false, false>(a, dev, st);
 	if (w)
-		return launch_tpq<N, false, true>(a, dev, st);
-	return launch_tpq<N, false, false>(a, dev, st);
+		return launch_tpq<N, false, true, false>(a, dev, st);
+	return launch_tpq<N, false, false, false>(a, dev, st);
 }
 
 template <int NP> int launch_gpq(const KernelArgs &a, int dev, cudaStream_t st)

@@ -96,6 +96,25 @@ __device__ __forceinline__ void fence_async_smem()
 	asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
+// MUFU.SQRT: one instruction, no special-case branches (relative error ~2^-22,
+// far inside the 1e-3 stop-test margin that defines a non-degenerate problem)
+__device__ __forceinline__ float sqrt_approx(float v)
+{
+	float r;
+	asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+	return r;
+}
+
+// shared-memory 128-bit load the compiler may not hoist or merge
+__device__ __forceinline__ float4 lds128(const float4 *p)
+{
+	float4 v;
+	asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+		     : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+		     : "r"(smem_u32(p)));
+	return v;
+}
+
 __device__ __forceinline__ float warp_sum(float v)
 {
 #pragma unroll

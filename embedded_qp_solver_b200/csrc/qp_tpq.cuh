@@ -115,7 +115,7 @@ __device__ __forceinline__ void ldlt_solve(const float (&a)[N * (N + 1) / 2], fl
 
 // ---- the kernel -----------------------------------------------------------------
 
-template <int N, bool BOUNDS, bool WARM>
+template <int N, bool BOUNDS, bool WARM, bool RELAX>
 __global__ void __launch_bounds__(TpqCfg<N>::WARPS * 32, TpqCfg<N>::MINB)
 qp_tpq_kernel(const KernelArgs p)
 {
@@ -290,14 +290,21 @@ qp_tpq_kernel(const KernelArgs p)
 		unsigned it = 0;
 		bool active = valid && !bad && p.max_iter > 0;
 		const float rho = p.rho, alpha = p.alpha;
-		const bool relax = (alpha != 1.0f);
+		const float rho2 = rho * rho, relrho = p.reltol * rho;
+
+		// q lives in shared memory; it is fetched one iteration ahead (at the end of the
+		// body) so that the first FMAs of an iteration do not wait on the load
+		float4 qn[NQ];
+#pragma unroll
+		for (int k = 0; k < NQ; ++k)
+			qn[k] = lds128(&priv_vec4[k * 32 + lane]);
 
 		while (__any_sync(FULL, active)) {
 			if (active) {
 				// admm_update_x (:146-159): y = rho (z - u) - q ; x = (P + rho I)^-1 y
 #pragma unroll
 				for (int k = 0; k < NQ; ++k) {
-					const float4 qv = priv_vec4[k * 32 + lane];
+					const float4 qv = qn[k];
 					w[4 * k + 0] = fmaf(rho, z[4 * k + 0] - u[4 * k + 0], -qv.x);
 					w[4 * k + 1] = fmaf(rho, z[4 * k + 1] - u[4 * k + 1], -qv.y);
 					w[4 * k + 2] = fmaf(rho, z[4 * k + 2] - u[4 * k + 2], -qv.z);
@@ -325,7 +332,7 @@ qp_tpq_kernel(const KernelArgs p)
 						const float xj = w[j];
 						// admm_update_x_hat (:161-174)
 						const float xh =
-							relax ? fmaf(alpha, xj, (1.0f - alpha) * z[j]) : xj;
+							RELAX ? fmaf(alpha, xj, (1.0f - alpha) * z[j]) : xj;
 						// admm_update_z (:176-190): clip(x_hat + u)
 						const float zn = fminf(fmaxf(xh + u[j], lo[e]), hi[e]);
 						// admm_s_norm (:218-231) uses z - z_old
@@ -343,12 +350,17 @@ qp_tpq_kernel(const KernelArgs p)
 					}
 				}
 				++it;
-				// admm_eps_pri (:233-243), admm_eps_dual (:245-253), stop test (:308)
-				const float r_norm = __fsqrt_rn(rr);
-				const float s_norm = fabsf(rho) * __fsqrt_rn(ss);
-				const float eps_pri = fmaf(p.reltol, __fsqrt_rn(fmaxf(nx, nz)), p.eps_abs);
-				const float eps_dual = fmaf(p.reltol * rho, __fsqrt_rn(nu), p.eps_abs);
-				if (r_norm < eps_pri && s_norm < eps_dual) {
+#pragma unroll
+				for (int k = 0; k < NQ; ++k)
+					qn[k] = lds128(&priv_vec4[k * 32 + lane]);
+				// admm_eps_pri (:233-243), admm_eps_dual (:245-253), stop test (:308):
+				//   ||x-z|| < eps_pri  and  rho ||z-z_old|| < eps_dual,
+				// compared as squares so that only the two norms inside the thresholds
+				// need a square root (MUFU.SQRT, no branches)
+				const float eps_pri = fmaf(p.reltol, sqrt_approx(fmaxf(nx, nz)), p.eps_abs);
+				const float eps_dual = fmaf(relrho, sqrt_approx(nu), p.eps_abs);
+				const bool conv = (rr < eps_pri * eps_pri) && (rho2 * ss < eps_dual * eps_dual);
+				if (conv) {
 					my_status = QP_STATUS_CONVERGED;
 					my_iters = int(it);
 					active = false;
