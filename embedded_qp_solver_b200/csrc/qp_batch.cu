@@ -122,7 +122,7 @@ template <int N, bool B, bool W, bool R>
 int launch_tpq(const KernelArgs &a, int dev, cudaStream_t st)
 {
 	using L = TpqLayout<N, B, W>;
-	using Cfg = TpqCfg<N>;
+	using Cfg = TpqCfg<N, B, W>;
 	auto kern = qp_tpq_kernel<N, B, W, R>;
 	static bool attr_done[64] = {};
 	if (!attr_done[dev]) {

@@ -32,13 +32,21 @@
 
 #include "qp_common.cuh"
 
+#ifndef QPB_TPQ16_WARPS
+#define QPB_TPQ16_WARPS 8
+#endif
+
 namespace qpb {
 
-template <int N> struct TpqCfg;
-template <> struct TpqCfg<16> { static constexpr int WARPS = 8, STAGES = 3, MINB = 1; };
-template <> struct TpqCfg<12> { static constexpr int WARPS = 8, STAGES = 3, MINB = 1; };
-template <> struct TpqCfg<8>  { static constexpr int WARPS = 8, STAGES = 4, MINB = 2; };
-template <> struct TpqCfg<4>  { static constexpr int WARPS = 8, STAGES = 4, MINB = 4; };
+// warps per CTA, ring stages and CTAs per SM, chosen so that registers and the
+// 227 KB of shared memory are both filled
+template <int N, bool BOUNDS, bool WARM> struct TpqCfg;
+template <bool B, bool W> struct TpqCfg<16, B, W> {
+	static constexpr int WARPS = (B ? 8 : QPB_TPQ16_WARPS), STAGES = 3, MINB = 1;
+};
+template <bool B, bool W> struct TpqCfg<12, B, W> { static constexpr int WARPS = 12, STAGES = 3, MINB = 1; };
+template <bool B, bool W> struct TpqCfg<8, B, W>  { static constexpr int WARPS = 8, STAGES = 4, MINB = 2; };
+template <bool B, bool W> struct TpqCfg<4, B, W>  { static constexpr int WARPS = 8, STAGES = 4, MINB = 4; };
 
 // packed upper-triangle index, i <= j
 template <int N> __host__ __device__ constexpr int sidx(int i, int j)
@@ -47,7 +55,7 @@ template <int N> __host__ __device__ constexpr int sidx(int i, int j)
 }
 
 template <int N, bool BOUNDS, bool WARM> struct TpqLayout {
-	using Cfg = TpqCfg<N>;
+	using Cfg = TpqCfg<N, BOUNDS, WARM>;
 	static constexpr int PAD = (N >= 8) ? 4 : 0;          // floats of padding per P slot
 	static constexpr int PSLOT = N * N + PAD;             // floats per P slot
 	static constexpr int NVEC_STAGE = 1 + (BOUNDS ? 2 : 0) + (WARM ? 2 : 0);
@@ -59,6 +67,7 @@ template <int N, bool BOUNDS, bool WARM> struct TpqLayout {
 	static constexpr int FLOATS = Cfg::STAGES * STAGE + Cfg::WARPS * PRIV;
 	static constexpr size_t BYTES = size_t(FLOATS) * 4 + Cfg::STAGES * 8 /*mbarriers*/
 					+ (1 + Cfg::STAGES) * 4 /*ticket, rounds*/ + 16;
+	static_assert(BYTES * Cfg::MINB <= 232448, "shared memory budget of one SM exceeded");
 };
 
 // ---- register-resident dense routines (all indices compile-time) ------------
@@ -116,11 +125,12 @@ __device__ __forceinline__ void ldlt_solve(const float (&a)[N * (N + 1) / 2], fl
 // ---- the kernel -----------------------------------------------------------------
 
 template <int N, bool BOUNDS, bool WARM, bool RELAX>
-__global__ void __launch_bounds__(TpqCfg<N>::WARPS * 32, TpqCfg<N>::MINB)
+__global__ void
+__launch_bounds__(TpqCfg<N, BOUNDS, WARM>::WARPS * 32, TpqCfg<N, BOUNDS, WARM>::MINB)
 qp_tpq_kernel(const KernelArgs p)
 {
 	using L = TpqLayout<N, BOUNDS, WARM>;
-	using Cfg = TpqCfg<N>;
+	using Cfg = TpqCfg<N, BOUNDS, WARM>;
 	constexpr int STAGES = Cfg::STAGES;
 	constexpr int NQ = N / 4; // float4 per vector
 	constexpr unsigned FULL = 0xffffffffu;

@@ -1,0 +1,75 @@
+#!/usr/bin/env python
+"""Device-resident throughput of every BASELINE.json shape (one JSON line each).
+
+    python tools/bench_shapes.py [--steps K] [--shapes 4,16,40,64]
+
+configs: 1M n=4 | 1M n=16 (headline, also bench.py) | 256K n=40 (condensed-MPC-like
+dense box QPs) | 64K n=64 warm-started from a perturbed previous solve.
+Same timing rules as bench.py (CUDA events on the launching stream, >= 3 warm-ups,
+inputs larger than L2 or noted).
+"""
+import argparse
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import embedded_qp_solver_b200 as qp  # noqa: E402
+from bench import make_batch  # noqa: E402
+
+SHAPES = {4: 1 << 20, 16: 1 << 20, 40: 1 << 18, 64: 1 << 16}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--shapes", default="4,16,40,64")
+    ap.add_argument("--beta", type=float, default=0.5)
+    args = ap.parse_args()
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    fp32_peak = qp.probe_fp32_tflops(0, 5)
+    peaks = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    hbm_peak = float(json.load(open(peaks))["hbm_gbs"]) if os.path.exists(peaks) else 6650.0
+    for n in [int(s) for s in args.shapes.split(",")]:
+        count = SHAPES[n]
+        P, q = make_batch(count, n, 2026, dev)
+        warm = n == 64
+        kw = {}
+        if warm:
+            first = qp.solve_batch(P, q, -args.beta, args.beta)
+            q = q + 0.01 * torch.randn_like(q)
+            kw = dict(z0=first["z"].clone(), u0=first["lam"].clone())
+        out = None
+        for _ in range(3):
+            out = qp.solve_batch(P, q, -args.beta, args.beta, out=out, **kw)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            qp.solve_batch(P, q, -args.beta, args.beta, out=out, **kw)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / args.steps
+        k = float(out["iters"].float().mean())
+        bytes_per = qp.algorithmic_bytes(n, warm=warm, with_z=True, bound_arrays=False)
+        flops_per = qp.algorithmic_flops(n, k)
+        rate = count / (ms * 1e-3)
+        line = {"shape": f"n={n},m={2 * n}", "count": count, "kernel": qp.kernel_for(n),
+                "warm_start": warm, "qp_per_s": rate, "ms_per_step": ms, "mean_iters": k,
+                "not_converged": int((out["status"] != 0).sum()),
+                "hbm": {"achieved_gbs": bytes_per * rate / 1e9, "peak": hbm_peak,
+                        "frac": bytes_per * rate / 1e9 / hbm_peak, "bytes_per_problem": bytes_per},
+                "fp32": {"achieved_tflops": flops_per * rate / 1e12, "peak": fp32_peak,
+                         "frac": flops_per * rate / 1e12 / fp32_peak,
+                         "flops_per_problem": flops_per},
+                "input_mb": (n * n + n) * 4 * count / 1e6}
+        print(json.dumps(line), flush=True)
+        del P, q, out
+
+
+if __name__ == "__main__":
+    main()
