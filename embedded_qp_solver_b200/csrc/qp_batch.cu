@@ -163,14 +163,16 @@ template <int N> int launch_tpq_n(const KernelArgs &a, int dev, cudaStream_t st)
 
 template <int NP> int launch_gpq(const KernelArgs &a, int dev, cudaStream_t st)
 {
-	auto kern = qp_gpq_kernel<NP>;
+	constexpr int T = GpqLanes<NP>::T; // lanes per QP; 32 / T problems per warp
+	auto kern = qp_gpq_kernel<NP, T>;
 	static int per_sm[64] = {};
 	if (!per_sm[dev]) {
 		int b = 0;
 		QP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, kern, GPQ_WARPS * 32, 0));
 		per_sm[dev] = std::max(1, b);
 	}
-	const unsigned long long need = (a.count + GPQ_WARPS - 1) / GPQ_WARPS;
+	constexpr unsigned long long per_cta = GPQ_WARPS * (32 / T);
+	const unsigned long long need = (a.count + per_cta - 1) / per_cta;
 	unsigned long long grid = (unsigned long long)dev_sms(dev) * per_sm[dev];
 	grid = std::max(1ull, std::min(grid, need));
 	kern<<<dim3((unsigned)grid), dim3(GPQ_WARPS * 32), 0, st>>>(a);
