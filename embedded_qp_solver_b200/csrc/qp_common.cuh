@@ -105,6 +105,14 @@ __device__ __forceinline__ float sqrt_approx(float v)
 	return r;
 }
 
+// MUFU.RCP: one instruction (1 ulp), for the reciprocals of the block pivots
+__device__ __forceinline__ float rcp_approx(float v)
+{
+	float r;
+	asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+	return r;
+}
+
 // shared-memory 128-bit load the compiler may not hoist or merge
 __device__ __forceinline__ float4 lds128(const float4 *p)
 {

@@ -43,9 +43,11 @@ template <int NP> struct GpqLanes {
 
 template <int NP, int T> struct GpqSmem {
 	static constexpr int G = 32 / T; // QPs per warp
-	// two buffers of four pivot rows per group, +4 floats so that the groups of a
-	// warp start in different 16-byte bank groups
-	static constexpr int GROUP = 2 * 4 * NP + 4;
+	// pivot rows are NP + 4 floats apart so that the four owners' 128-bit stores of
+	// one column chunk fall into different bank groups; two buffers of four rows per
+	// group, +4 floats so that the groups of a warp are staggered as well
+	static constexpr int ROW = NP + 4;
+	static constexpr int GROUP = 2 * 4 * ROW + 4;
 	static constexpr int WARP = G * GROUP;
 };
 
@@ -58,7 +60,7 @@ __device__ __forceinline__ bool inv4(float (&B)[4][4])
 	for (int k = 0; k < 4; ++k) {
 		const float piv = B[k][k];
 		bad |= !(piv > 0.0f);
-		const float d = __frcp_rn(piv);
+		const float d = rcp_approx(piv);
 #pragma unroll
 		for (int j = 0; j < 4; ++j)
 			if (j != k)
@@ -79,13 +81,21 @@ __device__ __forceinline__ bool inv4(float (&B)[4][4])
 	return bad;
 }
 
+// CTAs per SM the register budget is capped for (rows in registers: NP * RPL floats)
+template <int NP, int T> struct GpqOcc {
+	static constexpr int ROWREGS = NP * ((NP + T - 1) / T);
+	static constexpr int MINB = ROWREGS <= 64 ? 6 : (ROWREGS <= 96 ? 4 : 3);
+};
+
 template <int NP, int T>
-__global__ void __launch_bounds__(GPQ_WARPS * 32) qp_gpq_kernel(const KernelArgs p)
+__global__ void __launch_bounds__(GPQ_WARPS * 32, GpqOcc<NP, T>::MINB)
+qp_gpq_kernel(const KernelArgs p)
 {
 	using SM = GpqSmem<NP, T>;
 	constexpr int G = SM::G;
 	constexpr int RPL = (NP + T - 1) / T; // rows per lane
 	constexpr int NC = NP / 4;            // 4-column chunks per row
+	constexpr int ROW = SM::ROW;          // floats between published pivot rows
 	constexpr unsigned FULL = 0xffffffffu;
 	__shared__ __align__(16) float sm[GPQ_WARPS * SM::WARP];
 
@@ -94,7 +104,7 @@ __global__ void __launch_bounds__(GPQ_WARPS * 32) qp_gpq_kernel(const KernelArgs
 	const int g = lane & (T - 1); // lane inside its group
 	const int grp = lane / T;     // group inside the warp
 	const int n = p.n;
-	float *bc = sm + warp * SM::WARP + grp * SM::GROUP; // bc[(buf*4+m)*NP + j]
+	float *bc = sm + warp * SM::WARP + grp * SM::GROUP; // bc[(buf*4+m)*ROW + j]
 	const float rho = p.rho, alpha = p.alpha;
 	const bool relax = (alpha != 1.0f);
 	const float rho2 = rho * rho, relrho = p.reltol * rho;
@@ -129,14 +139,14 @@ __global__ void __launch_bounds__(GPQ_WARPS * 32) qp_gpq_kernel(const KernelArgs
 			const int ks = r0 / T, kl = r0 & (T - 1); // slot and first lane of the pivot rows
 			const int m0 = g - kl;
 			const bool owner = (m0 >= 0) && (m0 < 4);
-			float *pb = bc + (K & 1) * 4 * NP;
+			float *pb = bc + (K & 1) * 4 * ROW;
 			// the four owners publish their (pre-update) rows
 #pragma unroll
 			for (int s = 0; s < RPL; ++s) {
 				if (s == ks && owner) {
 #pragma unroll
 					for (int c = 0; c < NC; ++c)
-						*reinterpret_cast<float4 *>(pb + m0 * NP + 4 * c) =
+						*reinterpret_cast<float4 *>(pb + m0 * ROW + 4 * c) =
 							make_float4(S[s][4 * c], S[s][4 * c + 1],
 								    S[s][4 * c + 2], S[s][4 * c + 3]);
 				}
@@ -146,7 +156,7 @@ __global__ void __launch_bounds__(GPQ_WARPS * 32) qp_gpq_kernel(const KernelArgs
 			float B[4][4];
 #pragma unroll
 			for (int m = 0; m < 4; ++m) {
-				const float4 v = *reinterpret_cast<const float4 *>(pb + m * NP);
+				const float4 v = *reinterpret_cast<const float4 *>(pb + m * ROW);
 				B[m][0] = v.x, B[m][1] = v.y, B[m][2] = v.z, B[m][3] = v.w;
 			}
 			bad |= inv4(B);
@@ -182,7 +192,7 @@ __global__ void __launch_bounds__(GPQ_WARPS * 32) qp_gpq_kernel(const KernelArgs
 #pragma unroll
 				for (int m = 0; m < 4; ++m) {
 					const float4 v =
-						*reinterpret_cast<const float4 *>(pb + m * NP + 4 * c);
+						*reinterpret_cast<const float4 *>(pb + m * ROW + 4 * c);
 					pr[m][0] = v.x, pr[m][1] = v.y, pr[m][2] = v.z, pr[m][3] = v.w;
 				}
 #pragma unroll
