@@ -32,9 +32,6 @@
 
 #include "qp_common.cuh"
 
-#ifndef QPB_TPQ16_WARPS
-#define QPB_TPQ16_WARPS 8
-#endif
 
 namespace qpb {
 
@@ -42,7 +39,7 @@ namespace qpb {
 // 227 KB of shared memory are both filled
 template <int N, bool BOUNDS, bool WARM> struct TpqCfg;
 template <bool B, bool W> struct TpqCfg<16, B, W> {
-	static constexpr int WARPS = (B ? 8 : QPB_TPQ16_WARPS), STAGES = 3, MINB = 1;
+	static constexpr int WARPS = 8, STAGES = (B ? 3 : 4), MINB = 1;
 };
 template <bool B, bool W> struct TpqCfg<12, B, W> { static constexpr int WARPS = 12, STAGES = 3, MINB = 1; };
 template <bool B, bool W> struct TpqCfg<8, B, W>  { static constexpr int WARPS = 8, STAGES = 4, MINB = 2; };
