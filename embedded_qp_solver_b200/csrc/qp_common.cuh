@@ -123,6 +123,17 @@ __device__ __forceinline__ float4 lds128(const float4 *p)
 	return v;
 }
 
+// the same with ld.volatile: ptxas will neither merge two of them nor replace one
+// by register moves (used to fill registers with constants four at a time)
+__device__ __forceinline__ float4 lds128_volatile(const float4 *p)
+{
+	float4 v;
+	asm volatile("ld.volatile.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+		     : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+		     : "r"(smem_u32(p)));
+	return v;
+}
+
 __device__ __forceinline__ float warp_sum(float v)
 {
 #pragma unroll

@@ -28,12 +28,21 @@
 //     updates on the owned coordinates, one butterfly all-reduce (inside the
 //     group) of the five sums of squares, and a group-uniform stop test.
 //   * x, z, lambda are written with lane = coordinate: coalesced per group.
+//   * Arithmetic is issued as packed FP32 pairs (fma.rn.f32x2, SASS FFMA2): a row
+//     lives in registers as NP/2 float2, the elimination multiplier is the scalar
+//     broadcast operand of FFMA2 and the pivot rows arrive from shared memory as
+//     128-bit loads that are already two aligned pairs.  FFMA2 does not raise the
+//     FP32 peak, it halves the issue slots the FMAs need -- this kernel is
+//     issue-bound, not pipe-bound (profiles/README.md).
 #pragma once
 
 #include "qp_common.cuh"
 
 namespace qpb {
 
+#ifndef QPB_GPQ_MINB_BIG
+#define QPB_GPQ_MINB_BIG 2
+#endif
 constexpr int GPQ_WARPS = 4; // warps per CTA
 
 // lanes per QP for a padded dimension
@@ -84,8 +93,48 @@ __device__ __forceinline__ bool inv4(float (&B)[4][4])
 // CTAs per SM the register budget is capped for (rows in registers: NP * RPL floats)
 template <int NP, int T> struct GpqOcc {
 	static constexpr int ROWREGS = NP * ((NP + T - 1) / T);
-	static constexpr int MINB = ROWREGS <= 64 ? 6 : (ROWREGS <= 96 ? 4 : 3);
+	static constexpr int MINB = ROWREGS <= 64 ? 6 : (ROWREGS <= 96 ? 4 : QPB_GPQ_MINB_BIG);
 };
+
+// packed-pair helpers: d = a * (s, s) + c and friends (SASS FFMA2 with a scalar
+// broadcast operand; no instruction is spent on building the (s, s) pair)
+__device__ __forceinline__ float2 fma2_bc(float2 a, float s, float2 c)
+{
+	return __ffma2_rn(a, make_float2(s, s), c);
+}
+
+// one row (NH pairs) to shared memory as 128-bit stores
+template <int NH> __device__ __forceinline__ void publish_row(const float2 (&row)[NH], float *dst)
+{
+#pragma unroll
+	for (int c = 0; c < NH / 2; ++c)
+		*reinterpret_cast<float4 *>(dst + 4 * c) =
+			make_float4(row[2 * c].x, row[2 * c].y, row[2 * c + 1].x, row[2 * c + 1].y);
+}
+
+// row <- -e_m0.  The constants come from shared memory (ctab[0..3] = rows of -I_4,
+// ctab[4] = 0): one 128-bit load fills four registers, a register move fills one
+// (measured: 142 vs 138 M QP/s at n = 40; -DQPB_GPQ_MOV_FILL selects the moves)
+template <int NH>
+__device__ __forceinline__ void pivot_row_reset(float2 (&row)[NH], const float4 *ctab, int m0)
+{
+#ifndef QPB_GPQ_MOV_FILL
+	const float4 e = lds128_volatile(&ctab[m0]);
+	row[0] = make_float2(e.x, e.y), row[1] = make_float2(e.z, e.w);
+#pragma unroll
+	for (int h = 2; h < NH; h += 2) {
+		const float4 zz = lds128_volatile(&ctab[4]);
+		row[h] = make_float2(zz.x, zz.y), row[h + 1] = make_float2(zz.z, zz.w);
+	}
+#else
+	(void)ctab;
+	row[0] = make_float2(m0 == 0 ? -1.0f : 0.0f, m0 == 1 ? -1.0f : 0.0f);
+	row[1] = make_float2(m0 == 2 ? -1.0f : 0.0f, m0 == 3 ? -1.0f : 0.0f);
+#pragma unroll
+	for (int h = 2; h < NH; ++h)
+		row[h] = make_float2(0.0f, 0.0f);
+#endif
+}
 
 template <int NP, int T>
 __global__ void __launch_bounds__(GPQ_WARPS * 32, GpqOcc<NP, T>::MINB)
@@ -95,9 +144,18 @@ qp_gpq_kernel(const KernelArgs p)
 	constexpr int G = SM::G;
 	constexpr int RPL = (NP + T - 1) / T; // rows per lane
 	constexpr int NC = NP / 4;            // 4-column chunks per row
+	constexpr int NH = NP / 2;            // float2 pairs per row
 	constexpr int ROW = SM::ROW;          // floats between published pivot rows
 	constexpr unsigned FULL = 0xffffffffu;
 	__shared__ __align__(16) float sm[GPQ_WARPS * SM::WARP];
+	__shared__ float4 ctab[5]; // rows of -I_4, then a zero vector
+
+	if (threadIdx.x < 5) {
+		const int t = threadIdx.x;
+		ctab[t] = make_float4(t == 0 ? -1.0f : 0.0f, t == 1 ? -1.0f : 0.0f, t == 2 ? -1.0f : 0.0f,
+				      t == 3 ? -1.0f : 0.0f);
+	}
+	__syncthreads();
 
 	const int lane = threadIdx.x & 31;
 	const int warp = threadIdx.x >> 5;
@@ -116,103 +174,157 @@ qp_gpq_kernel(const KernelArgs p)
 		const bool valid = prob < p.count;
 
 		// ---- load: the owner of row r takes column r of the symmetric P ------------------
-		float S[RPL][NP];
+		// S[s][h] = (row element 2h, row element 2h+1) of row g + T*s
+		float2 S[RPL][NH];
 		const float *Pp = p.P + (valid ? prob : 0ull) * (unsigned long long)n * n;
+		if (n == NP) {
+			// no padding: offsets are compile-time, no per-element bounds tests
 #pragma unroll
-		for (int s = 0; s < RPL; ++s) {
-			const int r = g + T * s;
+			for (int s = 0; s < RPL; ++s) {
+				const int r = g + T * s;
+				const bool in = valid && r < NP;
+				const float *col = Pp + (in ? r : 0);
 #pragma unroll
-			for (int j = 0; j < NP; ++j) {
-				float v = 0.0f;
-				if (valid && r < n && j < n)
-					v = __ldg(Pp + (unsigned long long)j * n + r);
-				if (r == j)
-					v = (valid && r < n) ? v + rho : 1.0f; // padding: identity block
-				S[s][j] = v;
+				for (int j = 0; j < NP; ++j) {
+					float v = in ? __ldg(col + j * NP) : 0.0f;
+					if (r == j)
+						v = in ? v + rho : 1.0f;
+					if (j & 1)
+						S[s][j / 2].y = v;
+					else
+						S[s][j / 2].x = v;
+				}
+			}
+		} else {
+#pragma unroll
+			for (int s = 0; s < RPL; ++s) {
+				const int r = g + T * s;
+#pragma unroll
+				for (int j = 0; j < NP; ++j) {
+					float v = 0.0f;
+					if (valid && r < n && j < n)
+						v = __ldg(Pp + (unsigned long long)j * n + r);
+					if (r == j)
+						v = (valid && r < n) ? v + rho : 1.0f; // padding: identity block
+					if (j & 1)
+						S[s][j / 2].y = v;
+					else
+						S[s][j / 2].x = v;
+				}
 			}
 		}
 
 		// ---- R = (P + rho I)^-1: block Gauss-Jordan, four pivots per step -----------------
+		// The block loop is split by the register slot ks that holds the pivot rows, so
+		// that "is this my pivot row" touches one slot's registers, not all of them.
+		//
+		// Look-ahead: the latency chain of a step -- publish the pivot rows, wait, load the
+		// 4x4 pivot block, invert it (four dependent reciprocals) -- is taken off the
+		// critical path.  Step K updates the chunk that holds the NEXT pivot columns first,
+		// the next owners publish just their 4x4 block, and its inverse is computed while
+		// the remaining chunks of step K are being updated.  At the end of step K the next
+		// owners publish their complete rows, so step K+1 starts with everything it needs.
 		bool bad = false;
-		for (int K = 0; K < NC; ++K) {
-			const int r0 = 4 * K;
-			const int ks = r0 / T, kl = r0 & (T - 1); // slot and first lane of the pivot rows
-			const int m0 = g - kl;
-			const bool owner = (m0 >= 0) && (m0 < 4);
-			float *pb = bc + (K & 1) * 4 * ROW;
-			// the four owners publish their (pre-update) rows
-#pragma unroll
-			for (int s = 0; s < RPL; ++s) {
-				if (s == ks && owner) {
-#pragma unroll
-					for (int c = 0; c < NC; ++c)
-						*reinterpret_cast<float4 *>(pb + m0 * ROW + 4 * c) =
-							make_float4(S[s][4 * c], S[s][4 * c + 1],
-								    S[s][4 * c + 2], S[s][4 * c + 3]);
-				}
-			}
+		float Bi[4][4]; // inverse of the current pivot block
+		{
+			if (g < 4)
+				publish_row<NH>(S[0], bc + g * ROW);
 			__syncwarp();
-			// pivot block and its inverse (every lane, redundantly)
-			float B[4][4];
 #pragma unroll
 			for (int m = 0; m < 4; ++m) {
-				const float4 v = *reinterpret_cast<const float4 *>(pb + m * ROW);
-				B[m][0] = v.x, B[m][1] = v.y, B[m][2] = v.z, B[m][3] = v.w;
+				const float4 v = *reinterpret_cast<const float4 *>(bc + m * ROW);
+				Bi[m][0] = v.x, Bi[m][1] = v.y, Bi[m][2] = v.z, Bi[m][3] = v.w;
 			}
-			bad |= inv4(B);
-			// an owner's new row is (row m0 of B^-1) x (pivot rows): expressed through the
-			// common update by replacing its row with -e_m0
+			bad |= inv4(Bi);
+		}
 #pragma unroll
-			for (int s = 0; s < RPL; ++s) {
-				if (s == ks && owner) {
-#pragma unroll
-					for (int j = 0; j < NP; ++j)
-						S[s][j] = 0.0f;
-#pragma unroll
-					for (int m = 0; m < 4; ++m)
-						S[s][m] = (m == m0) ? -1.0f : 0.0f;
-				}
-			}
-			float H[RPL][4];
-#pragma unroll
-			for (int s = 0; s < RPL; ++s) {
-#pragma unroll
-				for (int m = 0; m < 4; ++m) {
-					float h = S[s][0] * B[0][m];
-					h = fmaf(S[s][1], B[1][m], h);
-					h = fmaf(S[s][2], B[2][m], h);
-					h = fmaf(S[s][3], B[3][m], h);
-					H[s][m] = -h;
-				}
-			}
-			// S(:, j-4) <- S(:, j) + H * pivot_rows(:, j)
-#pragma unroll
-			for (int c = 1; c < NC; ++c) {
-				float pr[4][4];
-#pragma unroll
-				for (int m = 0; m < 4; ++m) {
-					const float4 v =
-						*reinterpret_cast<const float4 *>(pb + m * ROW + 4 * c);
-					pr[m][0] = v.x, pr[m][1] = v.y, pr[m][2] = v.z, pr[m][3] = v.w;
-				}
+		for (int ks = 0; ks < RPL; ++ks) {
+			constexpr int KPS = T / 4; // block steps per slot
+			const int ns = (ks + 1 < RPL) ? ks + 1 : ks; // slot after this one
+			const int Kend = (ks + 1) * KPS < NC ? (ks + 1) * KPS : NC;
+			for (int K = ks * KPS; K < Kend; ++K) {
+				const int m0 = g - (4 * K - ks * T); // my pivot row inside the block, if any
+				const bool owner = (m0 >= 0) && (m0 < 4);
+				const float *pb = bc + (K & 1) * 4 * ROW;
+				float *pn = bc + ((K + 1) & 1) * 4 * ROW;
+				// next step: same slot, or the first four lanes of the next slot
+				const bool same_slot = K + 1 < Kend;
+				const bool more = K + 1 < NC;
+				const int m1 = same_slot ? m0 - 4 : g;
+				const bool nowner = more && (m1 >= 0) && (m1 < 4);
+				// my row was published at the end of the previous step: turn it into -e_m0,
+				// which makes the common update below produce (row m0 of B^-1) x (pivot rows)
+				if (owner)
+					pivot_row_reset<NH>(S[ks], ctab, m0);
+				// H = -(first four columns) x B^-1, as two pairs per row
+				float2 H[RPL][2];
 #pragma unroll
 				for (int s = 0; s < RPL; ++s) {
 #pragma unroll
-					for (int e = 0; e < 4; ++e) {
-						float a = S[s][4 * c + e];
-						a = fmaf(H[s][0], pr[0][e], a);
-						a = fmaf(H[s][1], pr[1][e], a);
-						a = fmaf(H[s][2], pr[2][e], a);
-						a = fmaf(H[s][3], pr[3][e], a);
-						S[s][4 * (c - 1) + e] = a;
+					for (int mp = 0; mp < 2; ++mp) {
+						float2 h = __fmul2_rn(make_float2(Bi[0][2 * mp], Bi[0][2 * mp + 1]),
+								      make_float2(S[s][0].x, S[s][0].x));
+						h = fma2_bc(make_float2(Bi[1][2 * mp], Bi[1][2 * mp + 1]), S[s][0].y, h);
+						h = fma2_bc(make_float2(Bi[2][2 * mp], Bi[2][2 * mp + 1]), S[s][1].x, h);
+						h = fma2_bc(make_float2(Bi[3][2 * mp], Bi[3][2 * mp + 1]), S[s][1].y, h);
+						H[s][mp] = make_float2(-h.x, -h.y);
 					}
 				}
+				// S(:, j-4) <- S(:, j) + H * pivot_rows(:, j), one 4-column chunk at a time
+				auto update_chunk = [&](int c) {
+					float2 lo[4], hi[4];
+#pragma unroll
+					for (int m = 0; m < 4; ++m) {
+						const float4 v =
+							*reinterpret_cast<const float4 *>(pb + m * ROW + 4 * c);
+						lo[m] = make_float2(v.x, v.y), hi[m] = make_float2(v.z, v.w);
+					}
+#pragma unroll
+					for (int s = 0; s < RPL; ++s) {
+						float2 a = S[s][2 * c], b = S[s][2 * c + 1];
+						a = fma2_bc(lo[0], H[s][0].x, a), b = fma2_bc(hi[0], H[s][0].x, b);
+						a = fma2_bc(lo[1], H[s][0].y, a), b = fma2_bc(hi[1], H[s][0].y, b);
+						a = fma2_bc(lo[2], H[s][1].x, a), b = fma2_bc(hi[2], H[s][1].x, b);
+						a = fma2_bc(lo[3], H[s][1].y, a), b = fma2_bc(hi[3], H[s][1].y, b);
+						S[s][2 * c - 2] = a, S[s][2 * c - 1] = b;
+					}
+				};
+				update_chunk(1);
+				// the next pivot block is complete: publish it and start on its inverse
+				if (nowner) {
+					const float2 a = same_slot ? S[ks][0] : S[ns][0];
+					const float2 b = same_slot ? S[ks][1] : S[ns][1];
+					*reinterpret_cast<float4 *>(pn + m1 * ROW) = make_float4(a.x, a.y, b.x, b.y);
+				}
+				__syncwarp();
+				float Bn[4][4];
+#pragma unroll
+				for (int m = 0; m < 4; ++m) {
+					const float4 v = *reinterpret_cast<const float4 *>(pn + m * ROW);
+					Bn[m][0] = v.x, Bn[m][1] = v.y, Bn[m][2] = v.z, Bn[m][3] = v.w;
+				}
+				const bool badn = inv4(Bn);
+#pragma unroll
+				for (int c = 2; c < NC; ++c)
+					update_chunk(c);
+#pragma unroll
+				for (int s = 0; s < RPL; ++s)
+					S[s][NH - 2] = H[s][0], S[s][NH - 1] = H[s][1];
+				// the next owners publish their complete rows
+				if (nowner) {
+					if (same_slot)
+						publish_row<NH>(S[ks], pn + m1 * ROW);
+					else
+						publish_row<NH>(S[ns], pn + m1 * ROW);
+				}
+				__syncwarp();
+				bad |= more && badn;
+#pragma unroll
+				for (int i = 0; i < 4; ++i)
+#pragma unroll
+					for (int j = 0; j < 4; ++j)
+						Bi[i][j] = Bn[i][j];
 			}
-#pragma unroll
-			for (int s = 0; s < RPL; ++s)
-#pragma unroll
-				for (int m = 0; m < 4; ++m)
-					S[s][NP - 4 + m] = H[s][m];
 		}
 		__syncwarp();
 
@@ -250,26 +362,25 @@ qp_gpq_kernel(const KernelArgs p)
 						ybuf[r] = fmaf(rho, z[s] - u[s], -q[s]);
 				}
 				__syncwarp(am);
-				float acc[RPL][4];
+				float2 acc[RPL][2];
 #pragma unroll
 				for (int s = 0; s < RPL; ++s)
-					acc[s][0] = acc[s][1] = acc[s][2] = acc[s][3] = 0.0f;
+					acc[s][0] = acc[s][1] = make_float2(0.0f, 0.0f);
 #pragma unroll
 				for (int j = 0; j < NP; j += 4) {
 					const float4 y = *reinterpret_cast<const float4 *>(ybuf + j);
+					const float2 ylo = make_float2(y.x, y.y), yhi = make_float2(y.z, y.w);
 #pragma unroll
 					for (int s = 0; s < RPL; ++s) {
-						acc[s][0] = fmaf(S[s][j], y.x, acc[s][0]);
-						acc[s][1] = fmaf(S[s][j + 1], y.y, acc[s][1]);
-						acc[s][2] = fmaf(S[s][j + 2], y.z, acc[s][2]);
-						acc[s][3] = fmaf(S[s][j + 3], y.w, acc[s][3]);
+						acc[s][0] = __ffma2_rn(S[s][j / 2], ylo, acc[s][0]);
+						acc[s][1] = __ffma2_rn(S[s][j / 2 + 1], yhi, acc[s][1]);
 					}
 				}
 				__syncwarp(am);
 				float rr = 0.f, ss = 0.f, nx = 0.f, nz = 0.f, nu = 0.f;
 #pragma unroll
 				for (int s = 0; s < RPL; ++s) {
-					const float xs = (acc[s][0] + acc[s][1]) + (acc[s][2] + acc[s][3]);
+					const float xs = (acc[s][0].x + acc[s][0].y) + (acc[s][1].x + acc[s][1].y);
 					x[s] = xs;
 					// admm_update_x_hat (:161-174), _z (:176-190), _u (:192-203)
 					const float xh = relax ? fmaf(alpha, xs, (1.0f - alpha) * z[s]) : xs;
