@@ -8,14 +8,14 @@ hand-written sm_100a kernels behind a C ABI (``include/qp_batch.h``,
 The CUDA library is loaded on first use; if it is missing the call raises --
 there is no CPU path in this package.
 """
-from .api import (ABI_SYMBOLS, LIB_PATH, QP_MAX_DIM, STATUS_CONVERGED, STATUS_MAX_ITER,
+from .api import (ABI_SYMBOLS, KERNEL_AUTO, KERNEL_BPQ, KERNEL_GPQ, KERNEL_TPQ, LIB_PATH, QP_MAX_DIM, STATUS_CONVERGED, STATUS_MAX_ITER,
                   STATUS_NONFINITE, STATUS_SINGULAR, Matrix, Options, QpError, QuadraticForm,
                   Workspace, admm, admm_many, algorithmic_bytes, algorithmic_flops, eval_batch,
                   kernel_for, load_library, probe_fp32_tflops, probe_hbm_gbs, solve_batch)
 from . import problems  # noqa: F401
 
 __all__ = [
-    "ABI_SYMBOLS", "LIB_PATH", "QP_MAX_DIM", "STATUS_CONVERGED", "STATUS_MAX_ITER",
+    "ABI_SYMBOLS", "KERNEL_AUTO", "KERNEL_BPQ", "KERNEL_GPQ", "KERNEL_TPQ", "LIB_PATH", "QP_MAX_DIM", "STATUS_CONVERGED", "STATUS_MAX_ITER",
     "STATUS_NONFINITE", "STATUS_SINGULAR", "Matrix", "Options", "QpError", "QuadraticForm",
     "Workspace", "admm", "admm_many", "algorithmic_bytes", "algorithmic_flops", "eval_batch",
     "kernel_for", "load_library", "probe_fp32_tflops", "probe_hbm_gbs", "solve_batch",

@@ -24,6 +24,7 @@ QP_MAX_DIM = 64
 STATUS_CONVERGED, STATUS_MAX_ITER, STATUS_SINGULAR, STATUS_NONFINITE = 0, 1, 2, 3
 QP_OK, QP_ERR_INVALID, QP_ERR_UNSUPPORTED, QP_ERR_CUDA, QP_ERR_NO_DEVICE = 0, -1, -2, -3, -4
 MEM_HOST, MEM_DEVICE = 0, 1
+KERNEL_AUTO, KERNEL_TPQ, KERNEL_GPQ, KERNEL_BPQ = 0, 1, 2, 3
 
 _fp = C.POINTER(C.c_float)
 _ip = C.POINTER(C.c_int32)
@@ -45,7 +46,7 @@ class qp_options(C.Structure):
     _fields_ = [("rho", C.c_float), ("alpha", C.c_float), ("abstol", C.c_float),
                 ("reltol", C.c_float), ("max_iter", C.c_uint32), ("device_mask", C.c_uint32),
                 ("device", C.c_int32), ("stream", C.c_void_p), ("chunk", C.c_uint32),
-                ("reserved", C.c_uint32)]
+                ("kernel", C.c_uint32)]
 
 
 class qp_ref_matrix(C.Structure):
@@ -143,11 +144,12 @@ class Options:
     device: int = -1
     stream: int = 0
     chunk: int = 0
+    kernel: int = 0   # KERNEL_AUTO / KERNEL_TPQ / KERNEL_GPQ / KERNEL_BPQ
 
     def to_c(self) -> qp_options:
         return qp_options(self.rho, self.alpha, self.abstol, self.reltol, int(self.max_iter),
                           int(self.device_mask), int(self.device), C.c_void_p(self.stream or None),
-                          int(self.chunk), 0)
+                          int(self.chunk), int(self.kernel))
 
 
 def _is_torch(t) -> bool:

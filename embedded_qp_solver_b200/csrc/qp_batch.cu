@@ -24,6 +24,7 @@
 #include <thread>
 #include <vector>
 
+#include "qp_bpq.cuh"
 #include "qp_gpq.cuh"
 #include "qp_tpq.cuh"
 
@@ -70,6 +71,7 @@ extern "C" void qp_options_default(qp_options *o)
 	o->device = -1;
 	o->stream = nullptr;
 	o->chunk = 0;
+	o->kernel = QP_KERNEL_AUTO;
 }
 
 // ----------------------------------------------------------------------------------------
@@ -180,28 +182,86 @@ template <int NP> int launch_gpq(const KernelArgs &a, int dev, cudaStream_t st)
 	return QP_OK;
 }
 
-int launch_solver(const KernelArgs &a, int dev, cudaStream_t st)
+bool bpq_eligible(const KernelArgs &a)
+{
+	const int n = a.n;
+	if (n % 8 != 0 || n > 40)
+		return false;
+	const void *ptrs[] = { a.P, a.q, a.lb, a.ub, a.z0, a.u0, a.x, a.z, a.lam };
+	for (const void *p : ptrs)
+		if (p && !aligned16(p))
+			return false;
+	return true;
+}
+
+template <int NP> int launch_bpq(const KernelArgs &a, int dev, cudaStream_t st)
+{
+	auto kern = qp_bpq_kernel<NP>;
+	static int per_sm[64] = {};
+	if (!per_sm[dev]) {
+		int b = 0;
+		QP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, kern, BPQ_WARPS * 32, 0));
+		per_sm[dev] = std::max(1, b);
+	}
+	constexpr unsigned long long per_cta = BPQ_WARPS * BpqCfg<NP>::G;
+	const unsigned long long need = (a.count + per_cta - 1) / per_cta;
+	unsigned long long grid = (unsigned long long)dev_sms(dev) * per_sm[dev];
+	grid = std::max(1ull, std::min(grid, need));
+	kern<<<dim3((unsigned)grid), dim3(BPQ_WARPS * 32), 0, st>>>(a);
+	QP_CUDA(cudaGetLastError());
+	return QP_OK;
+}
+
+// which kernel family solves this batch (QP_KERNEL_*), 0 = none
+int pick_kernel(const KernelArgs &a, uint32_t forced)
+{
+	const bool t = tpq_eligible(a), b = bpq_eligible(a), g = a.n >= 1 && a.n <= QP_MAX_DIM;
+	switch (forced) {
+	case QP_KERNEL_TPQ: return t ? QP_KERNEL_TPQ : 0;
+	case QP_KERNEL_BPQ: return b ? QP_KERNEL_BPQ : 0;
+	case QP_KERNEL_GPQ: return g ? QP_KERNEL_GPQ : 0;
+	}
+	if (t)
+		return QP_KERNEL_TPQ;
+	if (b && a.n >= 24) // measured at n = 24, 32, 40: bpq ahead of gpq by 12, 11 and 27 % (profiles/README.md)
+		return QP_KERNEL_BPQ;
+	return g ? QP_KERNEL_GPQ : 0;
+}
+
+int launch_solver(const KernelArgs &a, int dev, cudaStream_t st, uint32_t forced = QP_KERNEL_AUTO)
 {
 	if (a.count == 0)
 		return QP_OK;
-	if (tpq_eligible(a)) {
+	switch (pick_kernel(a, forced)) {
+	case QP_KERNEL_TPQ:
 		switch (a.n) {
 		case 4:  return launch_tpq_n<4>(a, dev, st);
 		case 8:  return launch_tpq_n<8>(a, dev, st);
 		case 12: return launch_tpq_n<12>(a, dev, st);
 		case 16: return launch_tpq_n<16>(a, dev, st);
 		}
-	}
-	const int np = (a.n + 7) / 8 * 8;
-	switch (np) {
-	case 8:  return launch_gpq<8>(a, dev, st);
-	case 16: return launch_gpq<16>(a, dev, st);
-	case 24: return launch_gpq<24>(a, dev, st);
-	case 32: return launch_gpq<32>(a, dev, st);
-	case 40: return launch_gpq<40>(a, dev, st);
-	case 48: return launch_gpq<48>(a, dev, st);
-	case 56: return launch_gpq<56>(a, dev, st);
-	case 64: return launch_gpq<64>(a, dev, st);
+		break;
+	case QP_KERNEL_BPQ:
+		switch (a.n) {
+		case 8:  return launch_bpq<8>(a, dev, st);
+		case 16: return launch_bpq<16>(a, dev, st);
+		case 24: return launch_bpq<24>(a, dev, st);
+		case 32: return launch_bpq<32>(a, dev, st);
+		case 40: return launch_bpq<40>(a, dev, st);
+		}
+		break;
+	case QP_KERNEL_GPQ:
+		switch ((a.n + 7) / 8 * 8) {
+		case 8:  return launch_gpq<8>(a, dev, st);
+		case 16: return launch_gpq<16>(a, dev, st);
+		case 24: return launch_gpq<24>(a, dev, st);
+		case 32: return launch_gpq<32>(a, dev, st);
+		case 40: return launch_gpq<40>(a, dev, st);
+		case 48: return launch_gpq<48>(a, dev, st);
+		case 56: return launch_gpq<56>(a, dev, st);
+		case 64: return launch_gpq<64>(a, dev, st);
+		}
+		break;
 	}
 	return QP_ERR_UNSUPPORTED;
 }
@@ -496,7 +556,7 @@ int run_shard(qp_workspace *ws, DeviceCtx &ctx, const qp_batch &pb, const qp_bat
 		dsol.lambda = sol.lambda ? s.dlam : nullptr;
 		dsol.status = sol.status ? s.dstatus : nullptr;
 		dsol.iters = sol.iters ? s.diters : nullptr;
-		rc = launch_solver(make_args(dpb, dsol, opt), ctx.dev, st);
+		rc = launch_solver(make_args(dpb, dsol, opt), ctx.dev, st, opt.kernel);
 		if (rc != QP_OK)
 			return rc;
 
@@ -614,7 +674,7 @@ extern "C" int qp_solve_batch_ws(qp_workspace *ws, const qp_batch *pb,
 		if (g.enter(dev) != QP_OK)
 			return QP_ERR_NO_DEVICE;
 		return launch_solver(make_args(*pb, *sol, opt), dev,
-				     static_cast<cudaStream_t>(opt.stream));
+				     static_cast<cudaStream_t>(opt.stream), opt.kernel);
 	}
 
 	if (!ws || ws->n != pb->n)
@@ -874,10 +934,15 @@ extern "C" const char *qp_kernel_for(uint32_t n, int al16)
 	static thread_local char buf[32];
 	if (n == 0 || n > QP_MAX_DIM)
 		return "unsupported";
-	if (al16 && (n == 4 || n == 8 || n == 12 || n == 16))
-		std::snprintf(buf, sizeof buf, "tpq<%u>", n);
-	else
-		std::snprintf(buf, sizeof buf, "gpq<%u>", (n + 7) / 8 * 8);
+	KernelArgs a = {};
+	a.n = int(n);
+	if (!al16)
+		a.P = reinterpret_cast<const float *>(uintptr_t(4)); // a pointer that is not 16-byte aligned
+	switch (pick_kernel(a, QP_KERNEL_AUTO)) {
+	case QP_KERNEL_TPQ: std::snprintf(buf, sizeof buf, "tpq<%u>", n); break;
+	case QP_KERNEL_BPQ: std::snprintf(buf, sizeof buf, "bpq<%u>", n); break;
+	default: std::snprintf(buf, sizeof buf, "gpq<%u>", (n + 7) / 8 * 8); break;
+	}
 	return buf;
 }
 

@@ -1,0 +1,360 @@
+// qp_bpq.cuh -- "four rows per lane" kernel for n = 8, 16, 24, 32, 40 (n = 40 in BASELINE.json).
+//
+// What it replaces: the same reference path as qp_gpq.cuh -- admm()
+// (/root/reference/qp_solvers/qp_solvers.c:255-319) with matrix_invert()
+// (/root/reference/matrix/matrix_ops/matrix_ops.c:551-630) and matrix_mult()
+// (:235-271) underneath.
+//
+// Why a second lane-group kernel: qp_gpq.cuh spreads rows cyclically over a power-of-two
+// group (16 lanes at n = 40, three row slots of which the third is half empty: 40/48 of
+// the FMAs are useful) and every shared-memory pivot value feeds RPL = 3 FMAs.  Here
+//   * lane g of a group of T = n/4 lanes owns the four CONSECUTIVE rows 4g..4g+3.  At
+//     n = 40 that is 10 lanes per QP and three QPs per warp (lanes 30, 31 idle): 30/32 of
+//     the FMAs are useful, and every pivot value loaded from shared memory feeds four FMAs;
+//   * registers hold ROW PAIRS: S[rp][j] = (row 4g+2rp, row 4g+2rp+1) at column j.  One
+//     128-bit load of P[j][4g..4g+3] is then exactly the two pairs of column j, one
+//     128-bit shared-memory store publishes the four pivot rows at column j, and the
+//     elimination is FFMA2 with the pair of multipliers (H) in registers and the pivot
+//     value as the scalar broadcast operand;
+//   * a 4x4 pivot block lies in ONE lane, all four register slots, so the block loop needs
+//     no per-slot split.  The pivot rows are published by ALL lanes at once, each writing
+//     the 4x4 block it knows by the (signed) symmetry of the Gauss-Jordan intermediate;
+//     the owner then turns its rows into -I_4 so that the common update produces
+//     B^-1 x (pivot rows) for it;
+//   * loads, stores and the per-coordinate vectors are 128-bit per lane: lane g reads
+//     P[j][4g..4g+3] (column block of the symmetric P = row block), q/lb/ub/z0/u0[4g..4g+3],
+//     and writes x/z/lambda[4g..4g+3];
+//   * groups of 10 or 6 lanes are not a power of two: the five sums of squares are
+//     all-reduced with a fold by T/2 followed by a doubling ring over the odd remainder,
+//     and the stop decision is taken by lane 0 of the group and broadcast, so a group can
+//     never disagree with itself.
+// Same block Gauss-Jordan in shifting form and the same packed FP32 pairs (FFMA2) as
+// qp_gpq.cuh.  Requires n == NP (a multiple of 8) and 16-byte aligned arrays; everything
+// else goes to qp_gpq.cuh.
+#pragma once
+
+#include "qp_common.cuh"
+#include "qp_gpq.cuh"
+
+namespace qpb {
+
+#ifndef QPB_BPQ_WARPS
+#define QPB_BPQ_WARPS 4
+#endif
+constexpr int BPQ_WARPS = QPB_BPQ_WARPS; // warps per CTA
+
+template <int NP> struct BpqCfg {
+	static constexpr int T = NP / 4;           // lanes per QP
+	static constexpr int G = 32 / T;           // QPs per warp
+	static constexpr int GG = G + ((32 % T) ? 1 : 0); // + a scratch region for the idle lanes
+	static constexpr int ROW = NP + 4;         // floats between published pivot rows
+	static constexpr int BUF = 4 * ROW;        // one buffer: four pivot rows
+	static constexpr int GROUP = 2 * BUF + 4;  // two buffers, groups staggered by 16 bytes
+	static constexpr int MINB = NP <= 8 ? 6 : (NP <= 16 ? 4 : (NP <= 24 ? 3 : 2));
+};
+
+// all-reduce over the T lanes of a group (lanes base .. base+T-1, this lane is base + g).
+// Power-of-two groups: xor butterfly.  T = 2 * odd: fold the two halves, then a doubling
+// ring over the odd remainder.  The source lanes are computed once per kernel.  Lanes of
+// one group may round differently in the ring; callers take decisions from lane 0 only.
+template <int T> struct GroupRing {
+	int fold, n1, n2, n4; // source lanes
+	__device__ __forceinline__ GroupRing(int base, int g)
+	{
+		constexpr int Hh = T / 2;
+		const int gh = g >= Hh ? g - Hh : g;      // position inside the half
+		const int hb = base + (g >= Hh ? Hh : 0); // first lane of my half
+		fold = base + (g >= Hh ? g - Hh : g + Hh);
+		n1 = hb + (gh + 1) % Hh;
+		n2 = hb + (gh + 2) % Hh;
+		n4 = hb + (gh + 4) % Hh;
+	}
+	__device__ __forceinline__ float sum(float v, unsigned mask) const
+	{
+		if constexpr ((T & (T - 1)) == 0) {
+#pragma unroll
+			for (int o = T / 2; o > 0; o >>= 1)
+				v += __shfl_xor_sync(mask, v, o);
+			return v;
+		} else {
+			constexpr int Hh = T / 2; // 5 (T = 10) or 3 (T = 6)
+			static_assert(T == 2 * Hh && (Hh == 3 || Hh == 5), "unsupported group size");
+			// ring over Hh values w_0..w_{Hh-1} (after the fold both halves hold the same ones)
+			const float w = v + __shfl_sync(mask, v, fold);
+			float a = w + __shfl_sync(mask, w, n1); // w_j + w_{j+1}
+			if constexpr (Hh == 3) {
+				a += __shfl_sync(mask, w, n2);
+			} else {
+				a += __shfl_sync(mask, a, n2); // four consecutive
+				a += __shfl_sync(mask, w, n4); // the fifth
+			}
+			return a;
+		}
+	}
+};
+
+template <int NP>
+__global__ void __launch_bounds__(BPQ_WARPS * 32, BpqCfg<NP>::MINB)
+qp_bpq_kernel(const KernelArgs p)
+{
+	using C = BpqCfg<NP>;
+	constexpr int T = C::T, G = C::G, ROW = C::ROW;
+	constexpr unsigned FULL = 0xffffffffu;
+	__shared__ __align__(16) float sm[BPQ_WARPS * C::GG * C::GROUP];
+	__shared__ float4 ctab[5]; // columns of -I_4, then a zero vector
+
+	if (threadIdx.x < 5) {
+		const int t = threadIdx.x;
+		ctab[t] = make_float4(t == 0 ? -1.0f : 0.0f, t == 1 ? -1.0f : 0.0f, t == 2 ? -1.0f : 0.0f,
+				      t == 3 ? -1.0f : 0.0f);
+	}
+	__syncthreads();
+
+	const int lane = threadIdx.x & 31;
+	const int warp = threadIdx.x >> 5;
+	const int grp = lane / T;     // group inside the warp (== G for the idle lanes)
+	const int g = lane - grp * T; // lane inside its group
+	const int gbase = grp * T;
+	// the idle lanes (grp == G) fold into the last T lanes so that their shuffles stay in range
+	const GroupRing<T> ring(grp < G ? gbase : 32 - T, grp < G ? g : lane - (32 - T));
+	float *bc = sm + (warp * C::GG + grp) * C::GROUP; // bc[buf * BUF + 4 * j + m]
+	const float rho = p.rho, alpha = p.alpha;
+	const bool relax = (alpha != 1.0f);
+	const float rho2 = rho * rho, relrho = p.reltol * rho;
+
+	const unsigned long long stride = (unsigned long long)gridDim.x * BPQ_WARPS * G;
+	for (unsigned long long base = ((unsigned long long)blockIdx.x * BPQ_WARPS + warp) * G;
+	     base < p.count; base += stride) {
+		const unsigned long long prob = base + grp;
+		const bool valid = (grp < G) && (prob < p.count);
+
+		// ---- load: rows 4g..4g+3 of P + rho I, read as column blocks of the symmetric P ------
+		float2 S[2][NP]; // S[rp][j] = (row 4g+2rp, row 4g+2rp+1) at column j
+		{
+			const float4 *Pp = reinterpret_cast<const float4 *>(
+				p.P + (valid ? prob : 0ull) * (unsigned long long)(NP * NP)) + g;
+#pragma unroll
+			for (int j = 0; j < NP; ++j) {
+				float4 v = valid ? __ldg(Pp + j * (NP / 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+				if (j / 4 == g) { // the diagonal element of row 4g + (j % 4)
+					const float d = valid ? rho : 1.0f; // idle lanes / tail: identity
+					if (j % 4 == 0) v.x += d;
+					if (j % 4 == 1) v.y += d;
+					if (j % 4 == 2) v.z += d;
+					if (j % 4 == 3) v.w += d;
+				}
+				S[0][j] = make_float2(v.x, v.y), S[1][j] = make_float2(v.z, v.w);
+			}
+		}
+
+		// ---- R = (P + rho I)^-1: block Gauss-Jordan, four pivots per step, shifting form ----
+		bool bad = false;
+		for (int K = 0; K < NP / 4; ++K) {
+			float *pb = bc + (K & 1) * C::BUF; // pb[m * ROW + position]: pivot row m
+			// Publish the four pivot rows WITHOUT their owner writing forty stores: the
+			// intermediate matrix of Gauss-Jordan is symmetric up to sign (rows already
+			// pivoted: M[m][c] = -M[c][m]; the others: M[m][c] = M[c][m]), so the entries of
+			// the pivot rows at the columns of MY rows are my own first four columns.  Every
+			// lane writes its 4x4 block (four 128-bit stores, all lanes in parallel).
+			// Column c sits at shifted position (c - 4K) mod n.
+			{
+				const float sg = g < K ? -1.0f : 1.0f;
+				const int p0 = 4 * (g >= K ? g - K : g - K + NP / 4);
+#pragma unroll
+				for (int m = 0; m < 4; ++m) {
+					const float2 a = __fmul2_rn(S[0][m], make_float2(sg, sg));
+					const float2 b = __fmul2_rn(S[1][m], make_float2(sg, sg));
+					*reinterpret_cast<float4 *>(pb + m * ROW + p0) = make_float4(a.x, a.y, b.x, b.y);
+				}
+			}
+			if (g == K) {
+				// my four rows become -I_4, so that the common update below produces
+				// B^-1 x (pivot rows) for them (constants from shared memory: one 128-bit
+				// load per column)
+#pragma unroll
+				for (int j = 0; j < NP; ++j) {
+					const float4 c = lds128_volatile(&ctab[j < 4 ? j : 4]);
+					S[0][j] = make_float2(c.x, c.y), S[1][j] = make_float2(c.z, c.w);
+				}
+			}
+			__syncwarp();
+			// pivot block (B[m][j] = pivot row m at column j), replaced by minus its inverse
+			float B[4][4];
+#pragma unroll
+			for (int m = 0; m < 4; ++m) {
+				const float4 v = *reinterpret_cast<const float4 *>(pb + m * ROW);
+				B[m][0] = v.x, B[m][1] = v.y, B[m][2] = v.z, B[m][3] = v.w;
+			}
+			bad |= neg_inv4(B);
+			// H = -(first four columns) x B^-1 = (first four columns) x B; H[m][rp] is the pair of multipliers of pivot
+			// row m for my row pair rp
+			float2 H[4][2];
+#pragma unroll
+			for (int m = 0; m < 4; ++m) {
+#pragma unroll
+				for (int rp = 0; rp < 2; ++rp) {
+					float2 h = __fmul2_rn(S[rp][0], make_float2(B[0][m], B[0][m]));
+					h = fma2_bc(S[rp][1], B[1][m], h);
+					h = fma2_bc(S[rp][2], B[2][m], h);
+					h = fma2_bc(S[rp][3], B[3][m], h);
+					H[m][rp] = h;
+				}
+			}
+			// S(:, j-4) <- S(:, j) + H * pivot_rows(:, j)
+#pragma unroll
+			for (int c = 1; c < NP / 4; ++c) {
+				float4 pr[4];
+#pragma unroll
+				for (int m = 0; m < 4; ++m)
+					pr[m] = *reinterpret_cast<const float4 *>(pb + m * ROW + 4 * c);
+#pragma unroll
+				for (int rp = 0; rp < 2; ++rp) {
+					float2 a0 = S[rp][4 * c], a1 = S[rp][4 * c + 1], a2 = S[rp][4 * c + 2],
+					       a3 = S[rp][4 * c + 3];
+#pragma unroll
+					for (int m = 0; m < 4; ++m) {
+						a0 = fma2_bc(H[m][rp], pr[m].x, a0);
+						a1 = fma2_bc(H[m][rp], pr[m].y, a1);
+						a2 = fma2_bc(H[m][rp], pr[m].z, a2);
+						a3 = fma2_bc(H[m][rp], pr[m].w, a3);
+					}
+					S[rp][4 * c - 4] = a0, S[rp][4 * c - 3] = a1, S[rp][4 * c - 2] = a2,
+						      S[rp][4 * c - 1] = a3;
+				}
+			}
+#pragma unroll
+			for (int m = 0; m < 4; ++m)
+				S[0][NP - 4 + m] = H[m][0], S[1][NP - 4 + m] = H[m][1];
+		}
+		__syncwarp();
+
+		// ---- per-coordinate state: coordinates 4g..4g+3 ---------------------------------------
+		float q[4], lo[4], hi[4], z[4], u[4], x[4];
+		{
+			const unsigned long long o4 = (valid ? prob : 0ull) * (unsigned long long)(NP / 4) + g;
+			const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+			const float4 vq = valid ? __ldg(reinterpret_cast<const float4 *>(p.q) + o4) : zero4;
+			const float4 vl = (valid && p.lb) ? __ldg(reinterpret_cast<const float4 *>(p.lb) + o4)
+							  : make_float4(p.lb_s, p.lb_s, p.lb_s, p.lb_s);
+			const float4 vh = (valid && p.ub) ? __ldg(reinterpret_cast<const float4 *>(p.ub) + o4)
+							  : make_float4(p.ub_s, p.ub_s, p.ub_s, p.ub_s);
+			const float4 vz = (valid && p.z0) ? __ldg(reinterpret_cast<const float4 *>(p.z0) + o4) : zero4;
+			const float4 vu = (valid && p.u0) ? __ldg(reinterpret_cast<const float4 *>(p.u0) + o4) : zero4;
+			q[0] = vq.x, q[1] = vq.y, q[2] = vq.z, q[3] = vq.w;
+			lo[0] = vl.x, lo[1] = vl.y, lo[2] = vl.z, lo[3] = vl.w;
+			hi[0] = vh.x, hi[1] = vh.y, hi[2] = vh.z, hi[3] = vh.w;
+			z[0] = vz.x, z[1] = vz.y, z[2] = vz.z, z[3] = vz.w;
+			u[0] = vu.x, u[1] = vu.y, u[2] = vu.z, u[3] = vu.w;
+			x[0] = x[1] = x[2] = x[3] = 0.0f;
+		}
+
+		// ---- ADMM iterations (qp_solvers.c:284-310) -----------------------------------------
+		int status = QP_STATUS_MAX_ITER;
+		unsigned it = 0;
+		bool active = valid && !bad && p.max_iter > 0; // uniform inside a group
+		float *ybuf = bc;
+		for (;;) {
+			const unsigned am = __ballot_sync(FULL, active);
+			if (am == 0u)
+				break;
+			if (active) {
+				// admm_update_x (:146-159): y = rho (z - u) - q ; x = R y
+				*reinterpret_cast<float4 *>(ybuf + 4 * g) =
+					make_float4(fmaf(rho, z[0] - u[0], -q[0]), fmaf(rho, z[1] - u[1], -q[1]),
+						    fmaf(rho, z[2] - u[2], -q[2]), fmaf(rho, z[3] - u[3], -q[3]));
+				__syncwarp(am);
+				// four partial sums per row pair keep the FFMA2 chains short
+				float2 acc[2][4];
+#pragma unroll
+				for (int rp = 0; rp < 2; ++rp)
+					acc[rp][0] = acc[rp][1] = acc[rp][2] = acc[rp][3] = make_float2(0.0f, 0.0f);
+#pragma unroll
+				for (int j = 0; j < NP; j += 4) {
+					const float4 y = *reinterpret_cast<const float4 *>(ybuf + j);
+#pragma unroll
+					for (int rp = 0; rp < 2; ++rp) {
+						acc[rp][0] = fma2_bc(S[rp][j], y.x, acc[rp][0]);
+						acc[rp][1] = fma2_bc(S[rp][j + 1], y.y, acc[rp][1]);
+						acc[rp][2] = fma2_bc(S[rp][j + 2], y.z, acc[rp][2]);
+						acc[rp][3] = fma2_bc(S[rp][j + 3], y.w, acc[rp][3]);
+					}
+				}
+				__syncwarp(am);
+				float xr[4];
+#pragma unroll
+				for (int rp = 0; rp < 2; ++rp) {
+					const float2 t = __fadd2_rn(__fadd2_rn(acc[rp][0], acc[rp][1]),
+								    __fadd2_rn(acc[rp][2], acc[rp][3]));
+					xr[2 * rp] = t.x, xr[2 * rp + 1] = t.y;
+				}
+				float rr = 0.f, ss = 0.f, nx = 0.f, nz = 0.f, nu = 0.f;
+#pragma unroll
+				for (int s = 0; s < 4; ++s) {
+					const float xs = xr[s];
+					x[s] = xs;
+					// admm_update_x_hat (:161-174), _z (:176-190), _u (:192-203)
+					const float xh = relax ? fmaf(alpha, xs, (1.0f - alpha) * z[s]) : xs;
+					const float zn = fminf(fmaxf(xh + u[s], lo[s]), hi[s]);
+					const float dz = zn - z[s];
+					ss = fmaf(dz, dz, ss);
+					u[s] += xh - zn;
+					const float dr = xs - zn;
+					rr = fmaf(dr, dr, rr);
+					nx = fmaf(xs, xs, nx);
+					nz = fmaf(zn, zn, nz);
+					nu = fmaf(u[s], u[s], nu);
+					z[s] = zn;
+				}
+				rr = ring.sum(rr, am);
+				ss = ring.sum(ss, am);
+				nx = ring.sum(nx, am);
+				nz = ring.sum(nz, am);
+				nu = ring.sum(nu, am);
+				++it;
+				// stop test (:233-253, :308), squared form as in qp_tpq.cuh; lane 0 of the
+				// group decides for everybody
+				const float eps_pri = fmaf(p.reltol, sqrt_approx(fmaxf(nx, nz)), p.eps_abs);
+				const float eps_dual = fmaf(relrho, sqrt_approx(nu), p.eps_abs);
+				int conv = (rr < eps_pri * eps_pri) && (rho2 * ss < eps_dual * eps_dual);
+				if constexpr ((T & (T - 1)) != 0)
+					conv = __shfl_sync(am, conv, gbase);
+				if (conv) {
+					status = QP_STATUS_CONVERGED;
+					active = false;
+				} else if (it >= p.max_iter) {
+					active = false;
+				}
+			}
+		}
+		__syncwarp();
+
+		// ---- results ---------------------------------------------------------------------------
+		float nf = fmaf(x[0], 0.0f, fmaf(x[1], 0.0f, fmaf(x[2], 0.0f, x[3] * 0.0f)));
+		nf = ring.sum(nf, FULL);
+		int iters = int(it);
+		if (bad) {
+			status = QP_STATUS_SINGULAR;
+			iters = 0;
+		} else if (!(nf == 0.0f)) {
+			status = QP_STATUS_NONFINITE;
+		}
+		if (valid) {
+			const unsigned long long o4 = prob * (unsigned long long)(NP / 4) + g;
+			if (p.x)
+				reinterpret_cast<float4 *>(p.x)[o4] = make_float4(x[0], x[1], x[2], x[3]);
+			if (p.z)
+				reinterpret_cast<float4 *>(p.z)[o4] = make_float4(z[0], z[1], z[2], z[3]);
+			if (p.lam)
+				reinterpret_cast<float4 *>(p.lam)[o4] =
+					make_float4(rho * u[0], rho * u[1], rho * u[2], rho * u[3]);
+			if (g == 0) {
+				if (p.status)
+					p.status[prob] = status;
+				if (p.iters)
+					p.iters[prob] = iters;
+			}
+		}
+	}
+}
+
+} // namespace qpb

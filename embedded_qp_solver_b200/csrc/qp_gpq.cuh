@@ -60,9 +60,11 @@ template <int NP, int T> struct GpqSmem {
 	static constexpr int WARP = G * GROUP;
 };
 
-// In-place inverse of a symmetric positive definite 4x4 block (Gauss-Jordan, no
-// pivoting).  Returns true when a pivot is not strictly positive.
-__device__ __forceinline__ bool inv4(float (&B)[4][4])
+// B <- -B^-1 for a symmetric positive definite 4x4 block: four symmetric sweeps on the
+// upper triangle (36 multiply-adds and four MUFU reciprocals; a Gauss-Jordan on the full
+// block needs 60).  Only the upper triangle of B is read; the full (symmetric) result is
+// written.  Returns true when a pivot is not strictly positive.
+__device__ __forceinline__ bool neg_inv4(float (&B)[4][4])
 {
 	bool bad = false;
 #pragma unroll
@@ -70,23 +72,34 @@ __device__ __forceinline__ bool inv4(float (&B)[4][4])
 		const float piv = B[k][k];
 		bad |= !(piv > 0.0f);
 		const float d = rcp_approx(piv);
+		float t[4];
 #pragma unroll
 		for (int j = 0; j < 4; ++j)
-			if (j != k)
-				B[k][j] *= d;
-		B[k][k] = d;
+			t[j] = (j < k ? B[j][k] : B[k][j]) * d;
 #pragma unroll
 		for (int i = 0; i < 4; ++i) {
 			if (i == k)
 				continue;
-			const float f = B[i][k];
+			const float aik = i < k ? B[i][k] : B[k][i];
 #pragma unroll
-			for (int j = 0; j < 4; ++j)
+			for (int j = i; j < 4; ++j)
 				if (j != k)
-					B[i][j] = fmaf(-f, B[k][j], B[i][j]);
-			B[i][k] = -f * d;
+					B[i][j] = fmaf(-aik, t[j], B[i][j]);
 		}
+#pragma unroll
+		for (int j = 0; j < 4; ++j) {
+			if (j < k)
+				B[j][k] = t[j];
+			else if (j > k)
+				B[k][j] = t[j];
+		}
+		B[k][k] = -d;
 	}
+#pragma unroll
+	for (int i = 1; i < 4; ++i)
+#pragma unroll
+		for (int j = 0; j < i; ++j)
+			B[i][j] = B[j][i];
 	return bad;
 }
 
@@ -225,7 +238,7 @@ qp_gpq_kernel(const KernelArgs p)
 		// the remaining chunks of step K are being updated.  At the end of step K the next
 		// owners publish their complete rows, so step K+1 starts with everything it needs.
 		bool bad = false;
-		float Bi[4][4]; // inverse of the current pivot block
+		float Bi[4][4]; // minus the inverse of the current pivot block
 		{
 			if (g < 4)
 				publish_row<NH>(S[0], bc + g * ROW);
@@ -235,7 +248,7 @@ qp_gpq_kernel(const KernelArgs p)
 				const float4 v = *reinterpret_cast<const float4 *>(bc + m * ROW);
 				Bi[m][0] = v.x, Bi[m][1] = v.y, Bi[m][2] = v.z, Bi[m][3] = v.w;
 			}
-			bad |= inv4(Bi);
+			bad |= neg_inv4(Bi);
 		}
 #pragma unroll
 		for (int ks = 0; ks < RPL; ++ks) {
@@ -256,7 +269,7 @@ qp_gpq_kernel(const KernelArgs p)
 				// which makes the common update below produce (row m0 of B^-1) x (pivot rows)
 				if (owner)
 					pivot_row_reset<NH>(S[ks], ctab, m0);
-				// H = -(first four columns) x B^-1, as two pairs per row
+				// H = -(first four columns) x B^-1 = (first four columns) x Bi, two pairs per row
 				float2 H[RPL][2];
 #pragma unroll
 				for (int s = 0; s < RPL; ++s) {
@@ -267,7 +280,7 @@ qp_gpq_kernel(const KernelArgs p)
 						h = fma2_bc(make_float2(Bi[1][2 * mp], Bi[1][2 * mp + 1]), S[s][0].y, h);
 						h = fma2_bc(make_float2(Bi[2][2 * mp], Bi[2][2 * mp + 1]), S[s][1].x, h);
 						h = fma2_bc(make_float2(Bi[3][2 * mp], Bi[3][2 * mp + 1]), S[s][1].y, h);
-						H[s][mp] = make_float2(-h.x, -h.y);
+						H[s][mp] = h;
 					}
 				}
 				// S(:, j-4) <- S(:, j) + H * pivot_rows(:, j), one 4-column chunk at a time
@@ -303,7 +316,7 @@ qp_gpq_kernel(const KernelArgs p)
 					const float4 v = *reinterpret_cast<const float4 *>(pn + m * ROW);
 					Bn[m][0] = v.x, Bn[m][1] = v.y, Bn[m][2] = v.z, Bn[m][3] = v.w;
 				}
-				const bool badn = inv4(Bn);
+				const bool badn = neg_inv4(Bn);
 #pragma unroll
 				for (int c = 2; c < NC; ++c)
 					update_chunk(c);

@@ -109,8 +109,15 @@ typedef struct qp_options {
 	                         the legacy default stream)                         */
 	uint32_t chunk;       /* QP_MEM_HOST: problems per pipelined copy/solve
 	                         chunk, 0 = choose                                  */
-	uint32_t reserved;
+	uint32_t kernel;      /* QP_KERNEL_AUTO, or force one kernel family (tests,
+	                         measurements); a family that cannot take the
+	                         batch returns QP_ERR_UNSUPPORTED                   */
 } qp_options;
+
+#define QP_KERNEL_AUTO 0
+#define QP_KERNEL_TPQ  1 /* one QP per thread:       n = 4, 8, 12, 16              */
+#define QP_KERNEL_GPQ  2 /* cyclic rows per lane:    any n <= 64                   */
+#define QP_KERNEL_BPQ  3 /* four rows per lane:      n = 8, 16, 24, 32, 40         */
 
 void qp_options_default(qp_options *opt);
 

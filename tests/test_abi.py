@@ -67,7 +67,9 @@ def test_api_misuse_returns_error_codes(qp):
 def test_kernel_selection(qp):
     assert qp.kernel_for(4) == "tpq<4>" and qp.kernel_for(16) == "tpq<16>"
     assert qp.kernel_for(16, aligned16=False) == "gpq<16>"
-    assert qp.kernel_for(40) == "gpq<40>" and qp.kernel_for(64) == "gpq<64>"
+    assert qp.kernel_for(40) == "bpq<40>" and qp.kernel_for(64) == "gpq<64>"
+    assert qp.kernel_for(40, aligned16=False) == "gpq<40>" and qp.kernel_for(33) == "gpq<40>"
+    assert qp.kernel_for(24) == "bpq<24>" and qp.kernel_for(32) == "bpq<32>" and qp.kernel_for(48) == "gpq<48>"
     assert qp.kernel_for(13) == "gpq<16>" and qp.kernel_for(65) == "unsupported"
 
 

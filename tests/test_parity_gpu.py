@@ -363,3 +363,67 @@ def test_full_size_headline_properties(qp, orc):
     assert np.array_equal(r1["iters"][idx.cuda()].cpu().numpy()[ok], o["iters"][ok])
     e = rel_err(r1["x"][idx.cuda()].cpu().numpy()[ok].astype(np.float64), o["x"][ok])
     assert e.max() <= X_TOL
+
+
+# every kernel family at every shape it accepts (qp_options.kernel forces the family)
+FAMILIES = ([("tpq", n) for n in (4, 8, 12, 16)] + [("bpq", n) for n in (8, 16, 24, 32, 40)] +
+            [("gpq", n) for n in (4, 8, 13, 16, 24, 32, 40, 56, 64)])
+
+
+@pytest.mark.parametrize("family,n", FAMILIES, ids=[f"{f}{n}" for f, n in FAMILIES])
+def test_every_kernel_family_against_oracle(qp, orc, family, n):
+    """Cold start with the scalar box, then warm start with per-coordinate bounds and
+    over-relaxation, each family forced; batch sizes that leave ragged warps/groups."""
+    kern = {"tpq": qp.KERNEL_TPQ, "bpq": qp.KERNEL_BPQ, "gpq": qp.KERNEL_GPQ}[family]
+    count = 333 if n <= 24 else 77
+    P, q, lb, ub = problems.wellcond(count, n, seed=900 + n, beta=0.5)
+    P64, q64 = P.astype(np.float64), q.astype(np.float64)
+    o = orc.admm(P64, q64, lb, ub)
+    tP, tq = dev(P, q)
+    r = qp.solve_batch(tP, tq, -0.5, 0.5, options=qp.Options(kernel=kern))
+    torch.cuda.synchronize()
+    res = {k: v.cpu().numpy() for k, v in r.items()}
+    g = dict(x_ref=o["x"], z=o["z"], u=o["u"], iters=o["iters"], status=o["status"],
+             margins=o["margins"])
+    check_against(res, g, lb, ub, f"{family} n={n} cold")
+
+    rng = np.random.default_rng(n)
+    lb2 = (-rng.uniform(0.05, 1.0, (count, n))).astype(np.float32)
+    ub2 = rng.uniform(0.05, 1.0, (count, n)).astype(np.float32)
+    q2 = problems.perturb_q(q, seed=n)
+    z0 = np.clip(res["z"], lb2, ub2)
+    u0 = res["lam"]
+    o2 = orc.admm(P64, q2.astype(np.float64), lb2.astype(np.float64), ub2.astype(np.float64),
+                  z0=z0.astype(np.float64), u0=u0.astype(np.float64), alpha=1.5)
+    res2 = solve_dev(qp, P, q2, lb2, ub2, z0=z0, u0=u0,
+                     options=qp.Options(kernel=kern, alpha=1.5))
+    g2 = dict(x_ref=o2["x"], z=o2["z"], u=o2["u"], iters=o2["iters"], status=o2["status"],
+              margins=o2["margins"])
+    check_against(res2, g2, lb2, ub2, f"{family} n={n} warm+bounds+relax")
+
+
+def test_forced_family_that_cannot_take_the_batch_is_refused(qp):
+    P, q, _, _ = problems.wellcond(8, 24, seed=1)
+    tP, tq = dev(P, q)
+    with pytest.raises(qp.QpError) as e:
+        qp.solve_batch(tP, tq, -1.0, 1.0, options=qp.Options(kernel=qp.KERNEL_TPQ))
+    assert e.value.code == -2  # QP_ERR_UNSUPPORTED
+    P, q, _, _ = problems.wellcond(8, 48, seed=1)
+    tP, tq = dev(P, q)
+    with pytest.raises(qp.QpError):
+        qp.solve_batch(tP, tq, -1.0, 1.0, options=qp.Options(kernel=qp.KERNEL_BPQ))
+
+
+def test_status_codes_every_family(qp):
+    """A pivot <= 0 is status 2 (the reference prints "singular matrix",
+    matrix_ops.c:511-515), a NaN in q is status 3; neighbours are unaffected."""
+    for kern, n in ((qp.KERNEL_TPQ, 8), (qp.KERNEL_BPQ, 40), (qp.KERNEL_GPQ, 40)):
+        P, q, lb, ub = problems.wellcond(70, n, seed=77, beta=0.5)
+        P[3] = -P[3] - 3 * np.eye(n, dtype=np.float32)  # P + I negative definite
+        q[5, 1] = np.nan
+        res = solve_dev(qp, P, q, lb, ub, options=qp.Options(kernel=kern))
+        assert res["status"][3] == qp.STATUS_SINGULAR and res["iters"][3] == 0
+        assert res["status"][5] == qp.STATUS_NONFINITE
+        rest = np.ones(70, bool)
+        rest[[3, 5]] = False
+        assert np.all(res["status"][rest] == 0)

@@ -28,29 +28,37 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--shapes", default="4,16,40,64")
     ap.add_argument("--beta", type=float, default=0.5)
+    ap.add_argument("--kernel", default="auto", choices=["auto", "tpq", "gpq", "bpq"])
+    ap.add_argument("--counts", default="", help="override batch sizes, e.g. 24:262144,32:262144")
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(dev)
     fp32_peak = qp.probe_fp32_tflops(0, 5)
     peaks = os.path.join(ROOT, "MEASURED_PEAKS.json")
     hbm_peak = float(json.load(open(peaks))["hbm_gbs"]) if os.path.exists(peaks) else 6650.0
+    kern = {"auto": qp.KERNEL_AUTO, "tpq": qp.KERNEL_TPQ, "gpq": qp.KERNEL_GPQ, "bpq": qp.KERNEL_BPQ}[args.kernel]
+    opts = qp.Options(kernel=kern)
+    counts = dict(SHAPES)
+    for item in filter(None, args.counts.split(",")):
+        k, v = item.split(":")
+        counts[int(k)] = int(v)
     for n in [int(s) for s in args.shapes.split(",")]:
-        count = SHAPES[n]
+        count = counts[n]
         P, q = make_batch(count, n, 2026, dev)
         warm = n == 64
         kw = {}
         if warm:
-            first = qp.solve_batch(P, q, -args.beta, args.beta)
+            first = qp.solve_batch(P, q, -args.beta, args.beta, options=opts)
             q = q + 0.01 * torch.randn_like(q)
             kw = dict(z0=first["z"].clone(), u0=first["lam"].clone())
         out = None
         for _ in range(3):
-            out = qp.solve_batch(P, q, -args.beta, args.beta, out=out, **kw)
+            out = qp.solve_batch(P, q, -args.beta, args.beta, out=out, options=opts, **kw)
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(args.steps):
-            qp.solve_batch(P, q, -args.beta, args.beta, out=out, **kw)
+            qp.solve_batch(P, q, -args.beta, args.beta, out=out, options=opts, **kw)
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / args.steps
@@ -58,7 +66,7 @@ def main():
         bytes_per = qp.algorithmic_bytes(n, warm=warm, with_z=True, bound_arrays=False)
         flops_per = qp.algorithmic_flops(n, k)
         rate = count / (ms * 1e-3)
-        line = {"shape": f"n={n},m={2 * n}", "count": count, "kernel": qp.kernel_for(n),
+        line = {"shape": f"n={n},m={2 * n}", "count": count, "kernel": qp.kernel_for(n) if args.kernel == "auto" else f"{args.kernel}<{n}>",
                 "warm_start": warm, "qp_per_s": rate, "ms_per_step": ms, "mean_iters": k,
                 "not_converged": int((out["status"] != 0).sum()),
                 "hbm": {"achieved_gbs": bytes_per * rate / 1e9, "peak": hbm_peak,
