@@ -65,6 +65,7 @@ ABI_SYMBOLS = [
     "qp_options_default", "qp_solve_batch", "qp_workspace_create", "qp_workspace_destroy",
     "qp_solve_batch_ws", "qp_eval_batch", "qp_admm_qf", "qp_admm_qf_batch", "qp_last_error",
     "qp_device_count", "qp_kernel_for", "qp_probe_fp32_tflops", "qp_probe_hbm_gbs",
+    "qp_newton_batch", "qp_newton_qf",
 ]
 
 _lib = None
@@ -119,6 +120,13 @@ def load_library(path: Optional[str] = None):
                                      C.POINTER(C.POINTER(C.c_double)), _ip, _ip,
                                      C.POINTER(qp_options)]
     lib.qp_admm_qf_batch.restype = C.c_int
+    lib.qp_newton_batch.argtypes = [C.POINTER(qp_batch), C.c_void_p, C.c_uint, C.c_void_p,
+                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_float,
+                                    C.POINTER(qp_options)]
+    lib.qp_newton_batch.restype = C.c_int
+    lib.qp_newton_qf.argtypes = [C.POINTER(qp_ref_quadratic_form), C.POINTER(C.c_double), C.c_uint,
+                                 C.POINTER(C.c_double), _ip, _ip]
+    lib.qp_newton_qf.restype = C.c_int
     lib.qp_last_error.restype = C.c_char_p
     lib.qp_device_count.restype = C.c_int
     lib.qp_kernel_for.argtypes = [C.c_uint32, C.c_int]
@@ -306,6 +314,42 @@ def eval_batch(P, q, x, r: float = 0.0):
     return f
 
 
+def newton_batch(P, q, x0=None, iterations: int = 10, r: float = 0.0, want_f: bool = False):
+    """Batched ``newton_method_with_line_search`` (qp_solvers.c:103-144): returns a
+    dict(x, status, steps[, f]).  Device tensors in, device tensors out; numpy in,
+    numpy out.  ``iterations`` defaults to the reference's HESS_ITERATIONS."""
+    lib = load_library()
+    count, n = int(P.shape[0]), int(P.shape[1])
+    hP, aP, dev = _as_f32(P, (count, n, n), "P")
+    hq, aq, _ = _as_f32(q, (count, n), "q")
+    hx0, ax0, _ = _as_f32(x0, (count, n), "x0")
+    pb = qp_batch()
+    pb.n, pb.count, pb.mem, pb.P, pb.q = n, count, (MEM_DEVICE if dev else MEM_HOST), aP, aq
+    copt = Options().to_c()
+    if dev:
+        import torch
+        d = hP.device
+        out = {"x": torch.empty((count, n), dtype=torch.float32, device=d),
+               "status": torch.empty(count, dtype=torch.int32, device=d),
+               "steps": torch.empty(count, dtype=torch.int32, device=d)}
+        if want_f:
+            out["f"] = torch.empty(count, dtype=torch.float32, device=d)
+        copt.device = d.index
+        copt.stream = C.c_void_p(torch.cuda.current_stream(d).cuda_stream or None)
+        addr = {k: v.data_ptr() for k, v in out.items()}
+    else:
+        out = {"x": np.empty((count, n), np.float32), "status": np.empty(count, np.int32),
+               "steps": np.empty(count, np.int32)}
+        if want_f:
+            out["f"] = np.empty(count, np.float32)
+        addr = {k: v.ctypes.data for k, v in out.items()}
+    rc = lib.qp_newton_batch(C.byref(pb), ax0, int(iterations), addr["x"], addr["status"],
+                             addr["steps"], addr.get("f"), float(r), C.byref(copt))
+    if rc != QP_OK:
+        raise QpError(rc, "qp_newton_batch")
+    return out
+
+
 # ---- the reference's own operator ------------------------------------------------------
 
 class Matrix:
@@ -347,6 +391,28 @@ def admm(x0, iterations: int, qf: QuadraticForm, lb: float = -1e12, ub: float = 
         raise QpError(rc, "qp_admm_qf")
     if info is not None:
         info["status"], info["iters"] = st.value, it.value
+    return x
+
+
+def newton_method_with_line_search(x0, iterations: int, qf: QuadraticForm,
+                                   info: Optional[dict] = None) -> np.ndarray:
+    """``struct _matrix *newton_method_with_line_search(x0, iterations, qf)``
+    (qp_solvers.c:103-144) on the GPU; x returned as an n x 1 float64 array."""
+    lib = load_library()
+    n = qf.p.array.shape[0]
+    x = np.zeros((n, 1))
+    st, it = C.c_int32(), C.c_int32()
+    x0a = None
+    if x0 is not None:
+        x0a = np.ascontiguousarray(x0.array if isinstance(x0, Matrix) else x0, np.float64).reshape(-1)
+    rc = lib.qp_newton_qf(C.byref(qf.c),
+                          x0a.ctypes.data_as(C.POINTER(C.c_double)) if x0a is not None else None,
+                          int(iterations), x.ctypes.data_as(C.POINTER(C.c_double)),
+                          C.byref(st), C.byref(it))
+    if rc != QP_OK:
+        raise QpError(rc, "qp_newton_qf")
+    if info is not None:
+        info["status"], info["steps"] = st.value, it.value
     return x
 
 

@@ -46,3 +46,26 @@ struct _matrix *admm_b200(struct _matrix *x0, unsigned iterations,
 	}
 	return x;
 }
+
+/*
+ * Drop-in for newton_method_with_line_search() (qp_solvers/qp_solvers.h:9-12,
+ * qp_solvers.c:103-144), same signature, same ownership of the result:
+ *
+ *     test_optimizer(qf, HESS_ITERATIONS, x0, "newton_b200", newton_b200);
+ */
+struct _matrix *newton_b200(struct _matrix *x0, unsigned iterations,
+			    struct _quadratic_form *qf)
+{
+	struct _matrix *x = matrix_alloc(Nx1);
+	if (!x)
+		return 0;
+	int rc = qp_newton_qf((const struct qp_ref_quadratic_form *)qf,
+			      x0 ? x0->elements : 0, iterations, x->elements, 0, 0);
+	if (rc != QP_OK) {
+		fprintf(stderr, "newton_b200: qp_newton_qf failed (%d) %s\n", rc,
+			qp_last_error());
+		matrix_free(x);
+		return 0;
+	}
+	return x;
+}

@@ -26,6 +26,7 @@
 
 #include "qp_bpq.cuh"
 #include "qp_gpq.cuh"
+#include "qp_newton.cuh"
 #include "qp_tpq.cuh"
 
 using namespace qpb;
@@ -851,6 +852,98 @@ extern "C" int qp_eval_batch(const qp_batch *pb, const float *x, float r, float 
 }
 
 // ----------------------------------------------------------------------------------------
+// batched Newton (newton_method_with_line_search, /root/reference/qp_solvers/qp_solvers.c:103-144)
+// ----------------------------------------------------------------------------------------
+static int launch_newton(const NewtonArgs &a, int dev, cudaStream_t st)
+{
+	const size_t smem = NEWTON_WARPS * newton_smem_floats_per_warp(a.n) * sizeof(float);
+	static size_t attr_done[64] = {};
+	if (attr_done[dev] < smem) {
+		QP_CUDA(cudaFuncSetAttribute(qp_newton_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+					     int(NEWTON_WARPS * newton_smem_floats_per_warp(QP_MAX_DIM) *
+						 sizeof(float))));
+		attr_done[dev] = NEWTON_WARPS * newton_smem_floats_per_warp(QP_MAX_DIM) * sizeof(float);
+	}
+	int per_sm = 1;
+	QP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, qp_newton_kernel,
+							      NEWTON_WARPS * 32, smem));
+	per_sm = std::max(1, per_sm);
+	const unsigned long long need = (a.count + NEWTON_WARPS - 1) / NEWTON_WARPS;
+	const unsigned long long grid =
+		std::max(1ull, std::min((unsigned long long)dev_sms(dev) * per_sm, need));
+	qp_newton_kernel<<<dim3((unsigned)grid), dim3(NEWTON_WARPS * 32), smem, st>>>(a);
+	QP_CUDA(cudaGetLastError());
+	return QP_OK;
+}
+
+extern "C" int qp_newton_batch(const qp_batch *pb, const float *x0, unsigned iterations, float *x,
+			       int32_t *status, int32_t *steps, float *f, float r,
+			       const qp_options *opt_in)
+{
+	if (!pb || !x || pb->n == 0)
+		return QP_ERR_INVALID;
+	if (pb->n > QP_MAX_DIM)
+		return QP_ERR_UNSUPPORTED;
+	if (pb->mem != QP_MEM_HOST && pb->mem != QP_MEM_DEVICE)
+		return QP_ERR_INVALID;
+	if (pb->count == 0)
+		return QP_OK;
+	if (!pb->P || !pb->q)
+		return QP_ERR_INVALID;
+	qp_options opt;
+	if (opt_in)
+		opt = *opt_in;
+	else
+		qp_options_default(&opt);
+	const int dev = resolve_device(opt.device);
+	if (dev < 0)
+		return QP_ERR_NO_DEVICE;
+	DeviceGuard g;
+	if (g.enter(dev) != QP_OK)
+		return QP_ERR_NO_DEVICE;
+	const size_t n = pb->n, c = pb->count;
+	NewtonArgs a = {};
+	a.count = c, a.n = int(n), a.iterations = iterations, a.r = r;
+	if (pb->mem == QP_MEM_DEVICE) {
+		a.P = pb->P, a.q = pb->q, a.x0 = x0, a.x = x, a.fval = f, a.status = status, a.steps = steps;
+		return launch_newton(a, dev, static_cast<cudaStream_t>(opt.stream));
+	}
+	// host pointers: one staging allocation, synchronous (this is the cross-check path)
+	float *d = nullptr;
+	const size_t fl = c * n * n + 3 * c * n + 3 * c;
+	QP_CUDA(cudaMalloc(&d, fl * 4));
+	float *dP = d, *dq = dP + c * n * n, *dx0 = dq + c * n, *dx = dx0 + c * n, *df = dx + c * n;
+	int32_t *dst = reinterpret_cast<int32_t *>(df + c), *dsp = dst + c;
+	cudaError_t e = cudaMemcpy(dP, pb->P, c * n * n * 4, cudaMemcpyHostToDevice);
+	if (e == cudaSuccess)
+		e = cudaMemcpy(dq, pb->q, c * n * 4, cudaMemcpyHostToDevice);
+	if (e == cudaSuccess && x0)
+		e = cudaMemcpy(dx0, x0, c * n * 4, cudaMemcpyHostToDevice);
+	int rc = QP_OK;
+	if (e == cudaSuccess) {
+		a.P = dP, a.q = dq, a.x0 = x0 ? dx0 : nullptr, a.x = dx, a.fval = f ? df : nullptr;
+		a.status = dst, a.steps = dsp;
+		rc = launch_newton(a, dev, nullptr);
+		if (rc == QP_OK)
+			e = cudaMemcpy(x, dx, c * n * 4, cudaMemcpyDeviceToHost);
+		if (rc == QP_OK && e == cudaSuccess && f)
+			e = cudaMemcpy(f, df, c * 4, cudaMemcpyDeviceToHost);
+		if (rc == QP_OK && e == cudaSuccess && status)
+			e = cudaMemcpy(status, dst, c * 4, cudaMemcpyDeviceToHost);
+		if (rc == QP_OK && e == cudaSuccess && steps)
+			e = cudaMemcpy(steps, dsp, c * 4, cudaMemcpyDeviceToHost);
+	}
+	cudaFree(d);
+	if (rc != QP_OK)
+		return rc;
+	if (e != cudaSuccess) {
+		g_err = std::string("qp_newton_batch: ") + cudaGetErrorString(e);
+		return QP_ERR_CUDA;
+	}
+	return QP_OK;
+}
+
+// ----------------------------------------------------------------------------------------
 // entry points on the reference's structs
 // ----------------------------------------------------------------------------------------
 static inline unsigned ref_rows(const qp_ref_matrix *m)
@@ -927,6 +1020,36 @@ extern "C" int qp_admm_qf(const struct qp_ref_quadratic_form *qf, unsigned itera
 	const struct qp_ref_quadratic_form *one[1] = { qf };
 	double *xo[1] = { x_out };
 	return qp_admm_qf_batch(one, 1, iterations, lb, ub, xo, status, iters, nullptr);
+}
+
+extern "C" int qp_newton_qf(const struct qp_ref_quadratic_form *qf, const double *x0,
+			    unsigned iterations, double *x_out, int32_t *status, int32_t *steps)
+{
+	if (!qf || !qf->p || !qf->q || !qf->p->elements || !qf->q->elements || !x_out)
+		return QP_ERR_INVALID;
+	const unsigned n = ref_rows(qf->p);
+	if (n == 0 || ref_cols(qf->p) != n || ref_rows(qf->q) * ref_cols(qf->q) != n)
+		return QP_ERR_INVALID;
+	if (n > QP_MAX_DIM)
+		return QP_ERR_UNSUPPORTED;
+	std::vector<float> P(size_t(n) * n), q(n), x0f(n, 0.0f), x(n);
+	for (size_t k = 0; k < size_t(n) * n; ++k)
+		P[k] = float(qf->p->elements[k]);
+	for (size_t k = 0; k < n; ++k) {
+		q[k] = float(qf->q->elements[k]);
+		if (x0)
+			x0f[k] = float(x0[k]);
+	}
+	qp_batch pb;
+	std::memset(&pb, 0, sizeof(pb));
+	pb.n = n, pb.mem = QP_MEM_HOST, pb.count = 1, pb.P = P.data(), pb.q = q.data();
+	const int rc = qp_newton_batch(&pb, x0f.data(), iterations, x.data(), status, steps, nullptr,
+				       0.0f, nullptr);
+	if (rc != QP_OK)
+		return rc;
+	for (size_t k = 0; k < n; ++k)
+		x_out[k] = double(x[k]);
+	return QP_OK;
 }
 
 extern "C" const char *qp_kernel_for(uint32_t n, int al16)

@@ -153,6 +153,25 @@ int qp_eval_batch(const qp_batch *prob, const float *x, float r, float *f,
 		  const qp_options *opt);
 
 /*
+ * Batched unconstrained minimiser.  Replaces a loop of
+ *     x = newton_method_with_line_search(x0, iterations, qf)
+ *                                         qp_solvers/qp_solvers.c:103-144
+ * (the second solver the reference's tests run through the same function
+ * pointer, main.c:46-48): hessian_inv = P^-1 once, then Newton steps with
+ * the reference's Armijo backtracking (alpha0 = 1, shrink 0.9, c2 = 1e-4,
+ * :37-63) until ||P x + q|| < 0.1 (:125) or `iterations` steps.  With the
+ * box inactive its answer is the ADMM answer -- the reference's own
+ * cross-check (test/test.c:89-106 prints both objectives).
+ * prob->lb/ub/z0/u0 are ignored.  x0 == NULL starts from 0.  x [count][n] is
+ * required; status (0 gradient test passed, 1 step cap, 2 a pivot of P <= 0,
+ * 3 non-finite), steps (Newton steps taken) and f (objective at x, with
+ * constant term r) may be NULL.  Pointers live where prob->mem says.
+ */
+int qp_newton_batch(const qp_batch *prob, const float *x0, unsigned iterations,
+		    float *x, int32_t *status, int32_t *steps, float *f, float r,
+		    const qp_options *opt);
+
+/*
  * Entry points on the reference's own structs (binary64, pool-owned).  The
  * two structs below are layout-identical to `struct _matrix`
  * (matrix/matrix_type/matrix_type.h:20-23: rows in bits 31:16 and columns in
@@ -183,6 +202,12 @@ int qp_admm_qf_batch(const struct qp_ref_quadratic_form *const *qfs,
 		     size_t count, unsigned iterations, double lb, double ub,
 		     double *const *x_out, int32_t *status, int32_t *iters,
 		     const qp_options *opt);
+
+/* One problem on the reference's structs: the body of a drop-in
+ * `newton_b200(x0, iterations, qf)`.  x0 may be NULL (= 0). */
+int qp_newton_qf(const struct qp_ref_quadratic_form *qf, const double *x0,
+		 unsigned iterations, double *x_out, int32_t *status,
+		 int32_t *steps);
 
 /* Diagnostics. */
 const char *qp_last_error(void);      /* text of the last QP_ERR_CUDA, per thread */

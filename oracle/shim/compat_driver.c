@@ -17,6 +17,9 @@
 struct _matrix *admm_b200(struct _matrix *x0, unsigned iterations,
 			  struct _quadratic_form *qf);
 
+struct _matrix *newton_b200(struct _matrix *x0, unsigned iterations,
+			    struct _quadratic_form *qf);
+
 static int ready = 0;
 
 unsigned compat_dim(void)
@@ -60,6 +63,50 @@ int compat_run(unsigned seed, double *x_ref, double *x_gpu, double *f_out,
 		f_out[1] = quadratic_form_eval(qf, b);
 		memcpy(P_out, p->elements, sizeof(double) * N_DIM * N_DIM);
 		memcpy(q_out, q->elements, sizeof(double) * N_DIM);
+	}
+	if (a)
+		matrix_free(a);
+	if (b)
+		matrix_free(b);
+	quadratic_form_free(qf);
+	matrix_free(x0);
+	matrix_free(q);
+	matrix_free(p);
+	return rc;
+}
+
+/* the same for the Newton solver (main.c:46-48): test_optimizer() through the function
+ * pointer with newton_method_with_line_search and with the drop-in newton_b200 */
+int compat_run_newton(unsigned seed, double *x_ref, double *x_gpu, double *f_out)
+{
+	if (!ready) {
+		kmalloc_init();
+		ready = 1;
+	}
+	srand(seed);
+	struct _matrix *p = matrix_alloc(NxN);
+	struct _matrix *q = matrix_alloc(Nx1);
+	struct _matrix *x0 = matrix_alloc(Nx1);
+	struct _quadratic_form *qf = quadratic_form_alloc(p, q, 0);
+	if (!p || !q || !x0 || !qf)
+		return -1;
+	matirx_random_pos_def(p, P_RAND_ENTRY_MIN, P_RAND_ENTRY_MAX);
+	matrix_random(q, Q_RAND_ENTRY_MIN, Q_RAND_ENTRY_MAX);
+	matrix_random(x0, X_RAND_ENTRY_MIN, X_RAND_ENTRY_MAX);
+
+	test_optimizer(qf, HESS_ITERATIONS, x0, "newton", newton_method_with_line_search);
+	test_optimizer(qf, HESS_ITERATIONS, x0, "newton_b200", newton_b200);
+
+	struct _matrix *a = newton_method_with_line_search(x0, HESS_ITERATIONS, qf);
+	struct _matrix *b = newton_b200(x0, HESS_ITERATIONS, qf);
+	int rc = 0;
+	if (!a || !b) {
+		rc = -2;
+	} else {
+		memcpy(x_ref, a->elements, sizeof(double) * N_DIM);
+		memcpy(x_gpu, b->elements, sizeof(double) * N_DIM);
+		f_out[0] = quadratic_form_eval(qf, a);
+		f_out[1] = quadratic_form_eval(qf, b);
 	}
 	if (a)
 		matrix_free(a);

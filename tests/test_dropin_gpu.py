@@ -45,3 +45,24 @@ def test_reference_harness_runs_with_admm_b200(qp, orc, capfd):
         assert np.all(np.isfinite(x_gpu))
     out = capfd.readouterr().out
     assert out.count("admm_b200 gave:") == 3 and out.count("admm gave:") == 3
+
+
+def test_reference_harness_runs_with_newton_b200(qp, capfd):
+    """The reference's second solver through the same function pointer
+    (main.c:46-48): newton_method_with_line_search vs the drop-in newton_b200."""
+    qp.load_library()
+    lib = C.CDLL(LIB)
+    lib.compat_dim.restype = C.c_uint
+    n = lib.compat_dim()
+    d = C.POINTER(C.c_double)
+    lib.compat_run_newton.restype = C.c_int
+    lib.compat_run_newton.argtypes = [C.c_uint, d, d, d]
+    for seed in (4, 5, 6):
+        x_ref, x_gpu, f = np.zeros(n), np.zeros(n), np.zeros(2)
+        rc = lib.compat_run_newton(seed, x_ref.ctypes.data_as(d), x_gpu.ctypes.data_as(d),
+                                   f.ctypes.data_as(d))
+        assert rc == 0
+        assert abs(f[1] - f[0]) <= 1e-3 * abs(f[0]), (seed, f)
+        assert np.all(np.isfinite(x_gpu))
+    out = capfd.readouterr().out
+    assert out.count("newton_b200 gave:") == 3 and out.count("newton gave:") == 3
