@@ -23,6 +23,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libqpb200.so")
 QP_MAX_DIM = 64
 STATUS_CONVERGED, STATUS_MAX_ITER, STATUS_SINGULAR, STATUS_NONFINITE = 0, 1, 2, 3
 QP_OK, QP_ERR_INVALID, QP_ERR_UNSUPPORTED, QP_ERR_CUDA, QP_ERR_NO_DEVICE = 0, -1, -2, -3, -4
+QP_ERR_IO = -5
 MEM_HOST, MEM_DEVICE = 0, 1
 KERNEL_AUTO, KERNEL_TPQ, KERNEL_GPQ, KERNEL_BPQ = 0, 1, 2, 3
 
@@ -66,6 +67,7 @@ ABI_SYMBOLS = [
     "qp_solve_batch_ws", "qp_eval_batch", "qp_admm_qf", "qp_admm_qf_batch", "qp_last_error",
     "qp_device_count", "qp_kernel_for", "qp_probe_fp32_tflops", "qp_probe_hbm_gbs",
     "qp_newton_batch", "qp_newton_qf",
+    "qp_problem_file_write", "qp_problem_file_count", "qp_problem_file_read",
 ]
 
 _lib = None
@@ -79,7 +81,8 @@ class QpError(RuntimeError):
 
 def _describe(code: int) -> str:
     names = {QP_ERR_INVALID: "invalid argument", QP_ERR_UNSUPPORTED: "unsupported dimension",
-             QP_ERR_CUDA: "CUDA error", QP_ERR_NO_DEVICE: "no usable GPU"}
+             QP_ERR_CUDA: "CUDA error", QP_ERR_NO_DEVICE: "no usable GPU",
+             QP_ERR_IO: "problem file I/O"}
     s = names.get(code, "?")
     if code == QP_ERR_CUDA and _lib is not None:
         s += " (" + _lib.qp_last_error().decode() + ")"
@@ -127,6 +130,13 @@ def load_library(path: Optional[str] = None):
     lib.qp_newton_qf.argtypes = [C.POINTER(qp_ref_quadratic_form), C.POINTER(C.c_double), C.c_uint,
                                  C.POINTER(C.c_double), _ip, _ip]
     lib.qp_newton_qf.restype = C.c_int
+    _dp = C.POINTER(C.c_double)
+    lib.qp_problem_file_write.argtypes = [C.c_char_p, C.c_uint32, C.c_size_t, _dp, _dp, C.c_int]
+    lib.qp_problem_file_write.restype = C.c_int
+    lib.qp_problem_file_count.argtypes = [C.c_char_p, C.POINTER(C.c_uint32)]
+    lib.qp_problem_file_count.restype = C.c_longlong
+    lib.qp_problem_file_read.argtypes = [C.c_char_p, C.c_size_t, C.c_size_t, C.c_uint32, _dp, _dp]
+    lib.qp_problem_file_read.restype = C.c_int
     lib.qp_last_error.restype = C.c_char_p
     lib.qp_device_count.restype = C.c_int
     lib.qp_kernel_for.argtypes = [C.c_uint32, C.c_int]
@@ -348,6 +358,41 @@ def newton_batch(P, q, x0=None, iterations: int = 10, r: float = 0.0, want_f: bo
     if rc != QP_OK:
         raise QpError(rc, "qp_newton_batch")
     return out
+
+
+# ---- the reference's problem file (test/test.c:108-126, test/qp_ref.py:8-30) --------------
+
+def write_problem_file(path, P, q, append: bool = False) -> None:
+    """[double n][P][q] per problem; one problem gives the reference's exact bytes."""
+    lib = load_library()
+    P = np.ascontiguousarray(P, np.float64)
+    if P.ndim == 2:
+        P = P[None]
+    count, n = P.shape[0], P.shape[1]
+    q = np.ascontiguousarray(q, np.float64).reshape(count, n)
+    dp = C.POINTER(C.c_double)
+    rc = lib.qp_problem_file_write(os.fsencode(path), n, count, P.ctypes.data_as(dp),
+                                   q.ctypes.data_as(dp), int(append))
+    if rc != QP_OK:
+        raise QpError(rc, "qp_problem_file_write")
+
+
+def read_problem_file(path, first: int = 0, count: Optional[int] = None):
+    """Returns (P [count,n,n], q [count,n]) as float64."""
+    lib = load_library()
+    n = C.c_uint32()
+    total = lib.qp_problem_file_count(os.fsencode(path), C.byref(n))
+    if total < 0:
+        raise QpError(int(total), "qp_problem_file_count")
+    count = total - first if count is None else count
+    P = np.empty((count, n.value, n.value))
+    q = np.empty((count, n.value))
+    dp = C.POINTER(C.c_double)
+    rc = lib.qp_problem_file_read(os.fsencode(path), first, count, n.value,
+                                  P.ctypes.data_as(dp), q.ctypes.data_as(dp))
+    if rc != QP_OK:
+        raise QpError(rc, "qp_problem_file_read")
+    return P, q
 
 
 # ---- the reference's own operator ------------------------------------------------------

@@ -113,6 +113,14 @@ __device__ __forceinline__ float rcp_approx(float v)
 	return r;
 }
 
+// reciprocal to ~1 ulp without the range checks and slow path of __frcp_rn: MUFU.RCP and
+// one Newton step (pivots of P + rho I are far from the denormal range)
+__device__ __forceinline__ float rcp_newton(float v)
+{
+	const float r = rcp_approx(v);
+	return fmaf(r, fmaf(-v, r, 1.0f), r);
+}
+
 // shared-memory 128-bit load the compiler may not hoist or merge
 __device__ __forceinline__ float4 lds128(const float4 *p)
 {

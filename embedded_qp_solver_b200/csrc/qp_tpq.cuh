@@ -79,7 +79,7 @@ template <int N> __device__ __forceinline__ bool ldlt_factor(float (&a)[N * (N +
 	for (int k = 0; k < N; ++k) {
 		const float piv = a[sidx<N>(k, k)];
 		bad |= !(piv > 0.0f);
-		const float dinv = __frcp_rn(piv);
+		const float dinv = rcp_newton(piv);
 		a[sidx<N>(k, k)] = dinv;
 		float l[N];
 #pragma unroll

@@ -1,0 +1,46 @@
+"""Drop-in for the reference's ``python test/qp_ref.py FILE`` (test/test.c:10, :128).
+
+    python -m embedded_qp_solver_b200.qp_ref tmp_test_file
+
+The reference's script parses ``[n][P][q]`` (test/qp_ref.py:8-30), minimises the
+quadratic with a third-party solver under ``G = 0, h = 0`` -- i.e. unconstrained
+(:35) -- and prints the objective (:36-37).  This module does the same on the GPU
+through the C ABI: the file is read with ``qp_problem_file_read``, every record is
+solved by the box-ADMM kernel with the box inactive and a tight tolerance, and the
+same two lines are printed per record.  No CPU solve happens here.
+"""
+from __future__ import annotations
+
+import sys
+
+import numpy as np
+
+from . import api
+
+BOX = 1e12  # the reference's own "inactive" box, config.h:29-30
+
+
+def solve_file(path: str):
+    """Returns (P, q, x, f) for every record of the file; f = x'Px/2 + q'x in float64."""
+    P, q = api.read_problem_file(path)
+    res = api.solve_batch(P.astype(np.float32), q.astype(np.float32), -BOX, BOX,
+                          options=api.Options(abstol=1e-7, reltol=1e-7, max_iter=20000))
+    x = res["x"].astype(np.float64)
+    f = 0.5 * np.einsum("ci,cij,cj->c", x, P, x) + np.einsum("ci,ci->c", q, x)
+    return P, q, x, f
+
+
+def main(argv=None) -> int:
+    argv = sys.argv if argv is None else argv
+    if len(argv) != 2:
+        print("usage: python -m embedded_qp_solver_b200.qp_ref FILE", file=sys.stderr)
+        return 2
+    _, _, _, f = solve_file(argv[1])
+    for v in f:
+        print("reference implementation gave:")
+        print("f(x_min) = %e" % v)
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

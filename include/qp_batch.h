@@ -58,6 +58,7 @@ extern "C" {
 #define QP_ERR_UNSUPPORTED   -2 /* n > QP_MAX_DIM                              */
 #define QP_ERR_CUDA          -3 /* a CUDA call failed; see qp_last_error()     */
 #define QP_ERR_NO_DEVICE     -4 /* no usable GPU / device id out of range      */
+#define QP_ERR_IO            -5 /* problem file: cannot open / short read/write */
 
 /* Where the arrays of a batch live. */
 #define QP_MEM_HOST   0 /* host pointers: the call copies in and out, sharding
@@ -208,6 +209,25 @@ int qp_admm_qf_batch(const struct qp_ref_quadratic_form *const *qfs,
 int qp_newton_qf(const struct qp_ref_quadratic_form *qf, const double *x0,
 		 unsigned iterations, double *x_out, int32_t *status,
 		 int32_t *steps);
+
+/*
+ * The reference's problem file: [double n][P, n*n doubles row-major][q, n doubles],
+ * written by test_reference() (test/test.c:108-126) for its Python cross-check
+ * (test/qp_ref.py:8-30 parses it).  Host-only calls, no GPU involved.  Files with
+ * several records back to back (one dimension) are accepted as a batch; a
+ * one-record file is byte-identical to what the reference writes.
+ *   write: `count` records from packed double arrays, truncating or appending;
+ *   count: number of records (negative = QP_ERR_*), n of the file in *n;
+ *   read:  records [first, first+count) into packed double arrays.
+ * `python -m embedded_qp_solver_b200.qp_ref FILE` is the drop-in for the
+ * reference's `python test/qp_ref.py FILE` (test/test.c:10): it solves every
+ * record on the GPU and prints the same two lines.
+ */
+int qp_problem_file_write(const char *path, uint32_t n, size_t count,
+			  const double *P, const double *q, int append);
+long long qp_problem_file_count(const char *path, uint32_t *n);
+int qp_problem_file_read(const char *path, size_t first, size_t count,
+			 uint32_t n, double *P, double *q);
 
 /* Diagnostics. */
 const char *qp_last_error(void);      /* text of the last QP_ERR_CUDA, per thread */

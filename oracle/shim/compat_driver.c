@@ -118,3 +118,30 @@ int compat_run_newton(unsigned seed, double *x_ref, double *x_gpu, double *f_out
 	matrix_free(p);
 	return rc;
 }
+
+/* The reference's own problem-file writer: draws a problem like main.c:36-40 and calls
+ * test_reference() (test/test.c:108-130), which writes "tmp_test_file" in the current
+ * directory, runs `python test/qp_ref.py tmp_test_file` and unlinks the file.  The caller
+ * chdir()s to a scratch directory whose test/qp_ref.py keeps a copy of the file. */
+int compat_write_reference_file(unsigned seed, double *P_out, double *q_out)
+{
+	if (!ready) {
+		kmalloc_init();
+		ready = 1;
+	}
+	srand(seed);
+	struct _matrix *p = matrix_alloc(NxN);
+	struct _matrix *q = matrix_alloc(Nx1);
+	struct _quadratic_form *qf = quadratic_form_alloc(p, q, 0);
+	if (!p || !q || !qf)
+		return -1;
+	matirx_random_pos_def(p, P_RAND_ENTRY_MIN, P_RAND_ENTRY_MAX);
+	matrix_random(q, Q_RAND_ENTRY_MIN, Q_RAND_ENTRY_MAX);
+	test_reference(qf);
+	memcpy(P_out, p->elements, sizeof(double) * N_DIM * N_DIM);
+	memcpy(q_out, q->elements, sizeof(double) * N_DIM);
+	quadratic_form_free(qf);
+	matrix_free(q);
+	matrix_free(p);
+	return 0;
+}
