@@ -979,13 +979,30 @@ extern "C" int qp_admm_qf_batch(const struct qp_ref_quadratic_form *const *qfs, 
 
 	std::vector<float> P(count * n * n), q(count * n), x(count * n);
 	std::vector<int32_t> st(count), it(count);
-	for (size_t i = 0; i < count; ++i) {
-		const double *pe = qfs[i]->p->elements, *qe = qfs[i]->q->elements;
-		for (size_t k = 0; k < size_t(n) * n; ++k)
-			P[i * n * n + k] = float(pe[k]);
-		for (size_t k = 0; k < n; ++k)
-			q[i * n + k] = float(qe[k]);
-	}
+	// gather + binary64 -> binary32, split over the host cores for large batches (the
+	// structs are scattered in the caller's pools, so this cannot be a device-side copy)
+	auto for_ranges = [&](auto &&body) {
+		const size_t hw = std::max(1u, std::thread::hardware_concurrency());
+		const size_t nt = std::min<size_t>(std::min<size_t>(hw, 32), std::max<size_t>(1, count / 4096));
+		if (nt <= 1) {
+			body(size_t(0), count);
+			return;
+		}
+		std::vector<std::thread> th;
+		for (size_t t = 0; t < nt; ++t)
+			th.emplace_back(body, count * t / nt, count * (t + 1) / nt);
+		for (std::thread &t : th)
+			t.join();
+	};
+	for_ranges([&](size_t lo, size_t hi) {
+		for (size_t i = lo; i < hi; ++i) {
+			const double *pe = qfs[i]->p->elements, *qe = qfs[i]->q->elements;
+			for (size_t k = 0; k < size_t(n) * n; ++k)
+				P[i * n * n + k] = float(pe[k]);
+			for (size_t k = 0; k < n; ++k)
+				q[i * n + k] = float(qe[k]);
+		}
+	});
 	qp_batch pb;
 	std::memset(&pb, 0, sizeof(pb));
 	pb.n = n, pb.mem = QP_MEM_HOST, pb.count = count;
@@ -1003,14 +1020,16 @@ extern "C" int qp_admm_qf_batch(const struct qp_ref_quadratic_form *const *qfs, 
 	const int rc = qp_solve_batch(&pb, &sol, &opt);
 	if (rc != QP_OK)
 		return rc;
-	for (size_t i = 0; i < count; ++i) {
-		for (size_t k = 0; k < n; ++k)
-			x_out[i][k] = double(x[i * n + k]);
-		if (status)
-			status[i] = st[i];
-		if (iters)
-			iters[i] = it[i];
-	}
+	for_ranges([&](size_t lo, size_t hi) {
+		for (size_t i = lo; i < hi; ++i) {
+			for (size_t k = 0; k < n; ++k)
+				x_out[i][k] = double(x[i * n + k]);
+			if (status)
+				status[i] = st[i];
+			if (iters)
+				iters[i] = it[i];
+		}
+	});
 	return QP_OK;
 }
 
