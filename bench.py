@@ -340,12 +340,25 @@ def run_ours(args, rank, local_rank, world):
     # DRAM bytes per launch of this kernel from the committed `ncu --set full` capture
     # (profiles/traffic.json, keyed by kernel and batch size); null when not captured
     roofline["traffic"] = None
+    rec = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
         rec = json.load(open(tpath)).get(f"{qp.kernel_for(n)}@{count}")
         if rec:
             roofline["traffic"] = rec["dram_bytes_per_launch"]
             roofline["traffic_source"] = rec["source"]
+    # instruction-issue view (the binding resource of this kernel): warp
+    # instructions per launch from the same ncu capture over this run's launch time, against
+    # one issue per cycle per SM sub-partition at the sampled SM clock
+    rec = rec if os.path.exists(tpath) else None
+    clk = (sampler.report().get("sm_mhz") or 0) * 1e6
+    if rec and rec.get("warp_instructions_per_launch") and clk > 0:
+        sms = torch.cuda.get_device_properties(device).multi_processor_count
+        peak_issue = sms * 4 * clk
+        ach = rec["warp_instructions_per_launch"] / kernel_s
+        roofline["issue"] = {"achieved": ach / 1e9, "peak": peak_issue / 1e9, "unit": "G warp-inst/s",
+                             "frac": ach / peak_issue,
+                             "warp_instructions_per_launch": rec["warp_instructions_per_launch"]}
     roofline["kernel"] = qp.kernel_for(n)
     roofline["hbm"] = hbm
     roofline["fp32"] = fp
