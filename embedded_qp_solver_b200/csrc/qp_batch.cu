@@ -29,6 +29,13 @@
 #include "qp_newton.cuh"
 #include "qp_tpq.cuh"
 
+#ifndef QPB_BPQ_PFI_FROM
+#define QPB_BPQ_PFI_FROM 24
+#endif
+#ifndef QPB_GPQ_PFI_FROM
+#define QPB_GPQ_PFI_FROM 48
+#endif
+
 using namespace qpb;
 
 // ----------------------------------------------------------------------------------------
@@ -167,7 +174,8 @@ template <int N> int launch_tpq_n(const KernelArgs &a, int dev, cudaStream_t st)
 template <int NP> int launch_gpq(const KernelArgs &a, int dev, cudaStream_t st)
 {
 	constexpr int T = GpqLanes<NP>::T; // lanes per QP; 32 / T problems per warp
-	auto kern = qp_gpq_kernel<NP, T>;
+	// n >= 48: the inverse stays in product form (half the elimination work; profiles/README.md)
+	auto kern = qp_gpq_kernel<NP, T, (NP >= QPB_GPQ_PFI_FROM)>;
 	static int per_sm[64] = {};
 	if (!per_sm[dev]) {
 		int b = 0;
@@ -197,7 +205,7 @@ bool bpq_eligible(const KernelArgs &a)
 
 template <int NP> int launch_bpq(const KernelArgs &a, int dev, cudaStream_t st)
 {
-	auto kern = qp_bpq_kernel<NP>;
+	auto kern = qp_bpq_kernel<NP, (NP >= QPB_BPQ_PFI_FROM)>;
 	static int per_sm[64] = {};
 	if (!per_sm[dev]) {
 		int b = 0;

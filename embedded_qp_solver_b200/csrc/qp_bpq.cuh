@@ -93,7 +93,7 @@ template <int T> struct GroupRing {
 	}
 };
 
-template <int NP>
+template <int NP, bool PFI>
 __global__ void __launch_bounds__(BPQ_WARPS * 32, BpqCfg<NP>::MINB)
 qp_bpq_kernel(const KernelArgs p)
 {
@@ -148,18 +148,33 @@ qp_bpq_kernel(const KernelArgs p)
 		}
 
 		// ---- R = (P + rho I)^-1: block Gauss-Jordan, four pivots per step, shifting form ----
+		// PFI = product form: the inverse is kept as the sequence of block eta transformations
+		// instead of being multiplied out.  Only the first L = NC - K chunks are still matrix
+		// columns in step K; chunk L-1 receives the step's eta columns H and is not touched
+		// again.  That halves the elimination work; x = R y becomes NC rank-4 updates of a
+		// vector (see the iteration loop).  The run-time block loop is cut into compile-time
+		// segments of four steps so that L is known per segment up to three.
 		bool bad = false;
-		for (int K = 0; K < NP / 4; ++K) {
+		constexpr int NC = NP / 4;
+		constexpr int SEG = PFI ? 4 : NC;
+		constexpr int NSEG = (NC + SEG - 1) / SEG;
+#pragma unroll
+		for (int seg = 0; seg < NSEG; ++seg) {
+		const int Kseg = (seg + 1) * SEG < NC ? (seg + 1) * SEG : NC;
+		const int Lmax = PFI ? NC - seg * SEG : NC, Lmin = PFI ? NC - (Kseg - 1) : NC;
+		for (int K = seg * SEG; K < Kseg; ++K) {
+			const int L = PFI ? NC - K : NC;
 			float *pb = bc + (K & 1) * C::BUF; // pb[m * ROW + position]: pivot row m
 			// Publish the four pivot rows WITHOUT their owner writing forty stores: the
 			// intermediate matrix of Gauss-Jordan is symmetric up to sign (rows already
 			// pivoted: M[m][c] = -M[c][m]; the others: M[m][c] = M[c][m]), so the entries of
 			// the pivot rows at the columns of MY rows are my own first four columns.  Every
 			// lane writes its 4x4 block (four 128-bit stores, all lanes in parallel).
-			// Column c sits at shifted position (c - 4K) mod n.
-			{
+			// Column c sits at shifted position (c - 4K) mod n.  In product form the columns
+			// of pivoted rows are dead (eta columns): those lanes have nothing to publish.
+			if (!PFI || g >= K) {
 				const float sg = g < K ? -1.0f : 1.0f;
-				const int p0 = 4 * (g >= K ? g - K : g - K + NP / 4);
+				const int p0 = 4 * (g >= K ? g - K : g - K + NC);
 #pragma unroll
 				for (int m = 0; m < 4; ++m) {
 					const float2 a = __fmul2_rn(S[0][m], make_float2(sg, sg));
@@ -173,8 +188,10 @@ qp_bpq_kernel(const KernelArgs p)
 				// load per column)
 #pragma unroll
 				for (int j = 0; j < NP; ++j) {
-					const float4 c = lds128_volatile(&ctab[j < 4 ? j : 4]);
-					S[0][j] = make_float2(c.x, c.y), S[1][j] = make_float2(c.z, c.w);
+					if (j / 4 < Lmin || j / 4 < L) {
+						const float4 c = lds128_volatile(&ctab[j < 4 ? j : 4]);
+						S[0][j] = make_float2(c.x, c.y), S[1][j] = make_float2(c.z, c.w);
+					}
 				}
 			}
 			__syncwarp();
@@ -186,8 +203,8 @@ qp_bpq_kernel(const KernelArgs p)
 				B[m][0] = v.x, B[m][1] = v.y, B[m][2] = v.z, B[m][3] = v.w;
 			}
 			bad |= neg_inv4(B);
-			// H = -(first four columns) x B^-1 = (first four columns) x B; H[m][rp] is the pair of multipliers of pivot
-			// row m for my row pair rp
+			// H = -(first four columns) x B^-1 = (first four columns) x B; H[m][rp] is the
+			// pair of multipliers of pivot row m for my row pair rp
 			float2 H[4][2];
 #pragma unroll
 			for (int m = 0; m < 4; ++m) {
@@ -201,8 +218,7 @@ qp_bpq_kernel(const KernelArgs p)
 				}
 			}
 			// S(:, j-4) <- S(:, j) + H * pivot_rows(:, j)
-#pragma unroll
-			for (int c = 1; c < NP / 4; ++c) {
+			auto update_chunk = [&](int c) {
 				float4 pr[4];
 #pragma unroll
 				for (int m = 0; m < 4; ++m)
@@ -221,10 +237,27 @@ qp_bpq_kernel(const KernelArgs p)
 					S[rp][4 * c - 4] = a0, S[rp][4 * c - 3] = a1, S[rp][4 * c - 2] = a2,
 						      S[rp][4 * c - 1] = a3;
 				}
-			}
+			};
+			auto place_eta = [&](int c) { // chunk c <- H
 #pragma unroll
-			for (int m = 0; m < 4; ++m)
-				S[0][NP - 4 + m] = H[m][0], S[1][NP - 4 + m] = H[m][1];
+				for (int m = 0; m < 4; ++m)
+					S[0][4 * c + m] = H[m][0], S[1][4 * c + m] = H[m][1];
+			};
+#pragma unroll
+			for (int c = 1; c < NC; ++c) {
+				if (c < Lmin) // live in every step of this segment: no test
+					update_chunk(c);
+				else if (c < Lmax) {
+					if (c < L)
+						update_chunk(c);
+					else if (c == L)
+						place_eta(c - 1);
+				} else if (c == Lmax && c == L)
+					place_eta(c - 1);
+			}
+			if (Lmax == NC && L == NC)
+				place_eta(NC - 1);
+		}
 		}
 		__syncwarp();
 
@@ -259,6 +292,29 @@ qp_bpq_kernel(const KernelArgs p)
 				break;
 			if (active) {
 				// admm_update_x (:146-159): y = rho (z - u) - q ; x = R y
+				float xr[4];
+				if constexpr (PFI) {
+					// R = E_{NC-1} ... E_0: E_K maps the four pivot entries v_P (all in lane K
+					// of the group) to B^-1 v_P and adds H_K v_P to every other entry; H_K
+					// sits in chunk NC-1-K, and the pivot rows' H is B^-1 itself.
+					float2 v0 = make_float2(fmaf(rho, z[0] - u[0], -q[0]), fmaf(rho, z[1] - u[1], -q[1]));
+					float2 v1 = make_float2(fmaf(rho, z[2] - u[2], -q[2]), fmaf(rho, z[3] - u[3], -q[3]));
+#pragma unroll
+					for (int K = 0; K < NC; ++K) {
+						const int src = gbase + K;
+						const float p0 = __shfl_sync(am, v0.x, src), p1 = __shfl_sync(am, v0.y, src);
+						const float p2 = __shfl_sync(am, v1.x, src), p3 = __shfl_sync(am, v1.y, src);
+						const int c = 4 * (NC - 1 - K);
+						float2 a0 = (g == K) ? make_float2(0.f, 0.f) : v0;
+						float2 a1 = (g == K) ? make_float2(0.f, 0.f) : v1;
+						a0 = fma2_bc(S[0][c], p0, a0), a1 = fma2_bc(S[1][c], p0, a1);
+						a0 = fma2_bc(S[0][c + 1], p1, a0), a1 = fma2_bc(S[1][c + 1], p1, a1);
+						a0 = fma2_bc(S[0][c + 2], p2, a0), a1 = fma2_bc(S[1][c + 2], p2, a1);
+						a0 = fma2_bc(S[0][c + 3], p3, a0), a1 = fma2_bc(S[1][c + 3], p3, a1);
+						v0 = a0, v1 = a1;
+					}
+					xr[0] = v0.x, xr[1] = v0.y, xr[2] = v1.x, xr[3] = v1.y;
+				} else {
 				*reinterpret_cast<float4 *>(ybuf + 4 * g) =
 					make_float4(fmaf(rho, z[0] - u[0], -q[0]), fmaf(rho, z[1] - u[1], -q[1]),
 						    fmaf(rho, z[2] - u[2], -q[2]), fmaf(rho, z[3] - u[3], -q[3]));
@@ -280,12 +336,12 @@ qp_bpq_kernel(const KernelArgs p)
 					}
 				}
 				__syncwarp(am);
-				float xr[4];
 #pragma unroll
 				for (int rp = 0; rp < 2; ++rp) {
 					const float2 t = __fadd2_rn(__fadd2_rn(acc[rp][0], acc[rp][1]),
 								    __fadd2_rn(acc[rp][2], acc[rp][3]));
 					xr[2 * rp] = t.x, xr[2 * rp + 1] = t.y;
+				}
 				}
 				float rr = 0.f, ss = 0.f, nx = 0.f, nz = 0.f, nu = 0.f;
 #pragma unroll

@@ -40,6 +40,9 @@
 
 namespace qpb {
 
+#ifndef QPB_GPQ_SEG
+#define QPB_GPQ_SEG 4
+#endif
 #ifndef QPB_GPQ_MINB_BIG
 #define QPB_GPQ_MINB_BIG 2
 #endif
@@ -149,7 +152,34 @@ __device__ __forceinline__ void pivot_row_reset(float2 (&row)[NH], const float4 
 #endif
 }
 
-template <int NP, int T>
+// the same restricted to the first `live` 4-column chunks (product-form variant: the
+// chunks behind them hold finished eta columns that must survive)
+template <int NH>
+__device__ __forceinline__ void publish_row_live(const float2 (&row)[NH], float *dst, int live)
+{
+#pragma unroll
+	for (int c = 0; c < NH / 2; ++c)
+		if (c < live)
+			*reinterpret_cast<float4 *>(dst + 4 * c) =
+				make_float4(row[2 * c].x, row[2 * c].y, row[2 * c + 1].x, row[2 * c + 1].y);
+}
+
+template <int NH>
+__device__ __forceinline__ void pivot_row_reset_live(float2 (&row)[NH], const float4 *ctab, int m0,
+						     int live)
+{
+	const float4 e = lds128_volatile(&ctab[m0]);
+	row[0] = make_float2(e.x, e.y), row[1] = make_float2(e.z, e.w);
+#pragma unroll
+	for (int h = 2; h < NH; h += 2) {
+		if (h / 2 < live) {
+			const float4 zz = lds128_volatile(&ctab[4]);
+			row[h] = make_float2(zz.x, zz.y), row[h + 1] = make_float2(zz.z, zz.w);
+		}
+	}
+}
+
+template <int NP, int T, bool PFI>
 __global__ void __launch_bounds__(GPQ_WARPS * 32, GpqOcc<NP, T>::MINB)
 qp_gpq_kernel(const KernelArgs p)
 {
@@ -250,25 +280,41 @@ qp_gpq_kernel(const KernelArgs p)
 			}
 			bad |= neg_inv4(Bi);
 		}
+		// The run-time block loop is cut into compile-time segments: one per register slot,
+		// and in the product-form variant one per four steps, so that the number of chunks
+		// that are still matrix columns is known per segment up to three.
+		constexpr int KPS = T / 4;                   // block steps per slot
+		constexpr int SEG = PFI ? (KPS < QPB_GPQ_SEG ? KPS : QPB_GPQ_SEG) : KPS; // block steps per segment
+		constexpr int NSEG = (NC + SEG - 1) / SEG;
 #pragma unroll
-		for (int ks = 0; ks < RPL; ++ks) {
-			constexpr int KPS = T / 4; // block steps per slot
+		for (int seg = 0; seg < NSEG; ++seg) {
+			const int ks = (seg * SEG) / KPS;            // slot that holds this segment's pivot rows
 			const int ns = (ks + 1 < RPL) ? ks + 1 : ks; // slot after this one
-			const int Kend = (ks + 1) * KPS < NC ? (ks + 1) * KPS : NC;
-			for (int K = ks * KPS; K < Kend; ++K) {
+			const int Kseg = (seg + 1) * SEG < NC ? (seg + 1) * SEG : NC;
+			const int Kslot = (ks + 1) * KPS < NC ? (ks + 1) * KPS : NC;
+			// live chunks L = NC - K in this segment: Lmin..Lmax
+			const int Lmax = PFI ? NC - seg * SEG : NC, Lmin = PFI ? NC - (Kseg - 1) : NC;
+			for (int K = seg * SEG; K < Kseg; ++K) {
 				const int m0 = g - (4 * K - ks * T); // my pivot row inside the block, if any
 				const bool owner = (m0 >= 0) && (m0 < 4);
 				const float *pb = bc + (K & 1) * 4 * ROW;
 				float *pn = bc + ((K + 1) & 1) * 4 * ROW;
 				// next step: same slot, or the first four lanes of the next slot
-				const bool same_slot = K + 1 < Kend;
+				const bool same_slot = K + 1 < Kslot;
 				const bool more = K + 1 < NC;
 				const int m1 = same_slot ? m0 - 4 : g;
 				const bool nowner = more && (m1 >= 0) && (m1 < 4);
+				// product form: only the first L chunks are still matrix columns; position
+				// L-1 receives this step's eta columns H and is never touched again
+				const int L = PFI ? NC - K : NC;
 				// my row was published at the end of the previous step: turn it into -e_m0,
 				// which makes the common update below produce (row m0 of B^-1) x (pivot rows)
-				if (owner)
-					pivot_row_reset<NH>(S[ks], ctab, m0);
+				if (owner) {
+					if constexpr (PFI)
+						pivot_row_reset_live<NH>(S[ks], ctab, m0, L);
+					else
+						pivot_row_reset<NH>(S[ks], ctab, m0);
+				}
 				// H = -(first four columns) x B^-1 = (first four columns) x Bi, two pairs per row
 				float2 H[RPL][2];
 #pragma unroll
@@ -302,7 +348,15 @@ qp_gpq_kernel(const KernelArgs p)
 						S[s][2 * c - 2] = a, S[s][2 * c - 1] = b;
 					}
 				};
-				update_chunk(1);
+				auto place_eta = [&](int c) { // chunk c <- H
+#pragma unroll
+					for (int s = 0; s < RPL; ++s)
+						S[s][2 * c] = H[s][0], S[s][2 * c + 1] = H[s][1];
+				};
+				if (1 < Lmin || 1 < L)
+					update_chunk(1);
+				else
+					place_eta(0);
 				// the next pivot block is complete: publish it and start on its inverse
 				if (nowner) {
 					const float2 a = same_slot ? S[ks][0] : S[ns][0];
@@ -318,17 +372,32 @@ qp_gpq_kernel(const KernelArgs p)
 				}
 				const bool badn = neg_inv4(Bn);
 #pragma unroll
-				for (int c = 2; c < NC; ++c)
-					update_chunk(c);
-#pragma unroll
-				for (int s = 0; s < RPL; ++s)
-					S[s][NH - 2] = H[s][0], S[s][NH - 1] = H[s][1];
+				for (int c = 2; c < NC; ++c) {
+					if (c < Lmin) // live in every step of this segment: no test
+						update_chunk(c);
+					else if (c < Lmax) {
+						if (c < L)
+							update_chunk(c);
+						else if (c == L)
+							place_eta(c - 1);
+					} else if (c == Lmax && c == L)
+						place_eta(c - 1);
+				}
+				if (Lmax == NC && L == NC)
+					place_eta(NC - 1);
 				// the next owners publish their complete rows
 				if (nowner) {
-					if (same_slot)
-						publish_row<NH>(S[ks], pn + m1 * ROW);
-					else
-						publish_row<NH>(S[ns], pn + m1 * ROW);
+					if constexpr (PFI) {
+						if (same_slot)
+							publish_row_live<NH>(S[ks], pn + m1 * ROW, L - 1);
+						else
+							publish_row_live<NH>(S[ns], pn + m1 * ROW, L - 1);
+					} else {
+						if (same_slot)
+							publish_row<NH>(S[ks], pn + m1 * ROW);
+						else
+							publish_row<NH>(S[ns], pn + m1 * ROW);
+					}
 				}
 				__syncwarp();
 				bad |= more && badn;
@@ -367,33 +436,63 @@ qp_gpq_kernel(const KernelArgs p)
 			if (am == 0u)
 				break;
 			if (active) {
-				// admm_update_x (:146-159)
+				// admm_update_x (:146-159): y = rho (z - u) - q ; x = R y
+				float xr[RPL];
+				if constexpr (PFI) {
+					// R is held in product form, R = E_{NC-1} ... E_0: apply the block eta
+					// transformations one after the other.  E_K maps the four pivot
+					// entries v_P to B^-1 v_P and adds H_K v_P to every other entry; H_K sits
+					// in chunk NC-1-K, and the pivot rows' H is B^-1 itself.
 #pragma unroll
-				for (int s = 0; s < RPL; ++s) {
-					const int r = g + T * s;
-					if (r < NP)
-						ybuf[r] = fmaf(rho, z[s] - u[s], -q[s]);
-				}
-				__syncwarp(am);
-				float2 acc[RPL][2];
+					for (int s = 0; s < RPL; ++s)
+						xr[s] = fmaf(rho, z[s] - u[s], -q[s]);
 #pragma unroll
-				for (int s = 0; s < RPL; ++s)
-					acc[s][0] = acc[s][1] = make_float2(0.0f, 0.0f);
+					for (int K = 0; K < NC; ++K) {
+						const int slot = (4 * K) / T, lane0 = (4 * K) % T;
+						const int src = (lane & ~(T - 1)) + lane0;
+						const float p0 = __shfl_sync(am, xr[slot], src);
+						const float p1 = __shfl_sync(am, xr[slot], src + 1);
+						const float p2 = __shfl_sync(am, xr[slot], src + 2);
+						const float p3 = __shfl_sync(am, xr[slot], src + 3);
+						const bool mine = (g >= lane0) && (g < lane0 + 4);
 #pragma unroll
-				for (int j = 0; j < NP; j += 4) {
-					const float4 y = *reinterpret_cast<const float4 *>(ybuf + j);
-					const float2 ylo = make_float2(y.x, y.y), yhi = make_float2(y.z, y.w);
+						for (int s = 0; s < RPL; ++s) {
+							const float2 h01 = S[s][2 * (NC - 1 - K)], h23 = S[s][2 * (NC - 1 - K) + 1];
+							const float b = (s == slot && mine) ? 0.0f : xr[s];
+							xr[s] = fmaf(h01.x, p0, fmaf(h01.y, p1, fmaf(h23.x, p2, fmaf(h23.y, p3, b))));
+						}
+					}
+				} else {
 #pragma unroll
 					for (int s = 0; s < RPL; ++s) {
-						acc[s][0] = __ffma2_rn(S[s][j / 2], ylo, acc[s][0]);
-						acc[s][1] = __ffma2_rn(S[s][j / 2 + 1], yhi, acc[s][1]);
+						const int r = g + T * s;
+						if (r < NP)
+							ybuf[r] = fmaf(rho, z[s] - u[s], -q[s]);
 					}
+					__syncwarp(am);
+					float2 acc[RPL][2];
+#pragma unroll
+					for (int s = 0; s < RPL; ++s)
+						acc[s][0] = acc[s][1] = make_float2(0.0f, 0.0f);
+#pragma unroll
+					for (int j = 0; j < NP; j += 4) {
+						const float4 y = *reinterpret_cast<const float4 *>(ybuf + j);
+						const float2 ylo = make_float2(y.x, y.y), yhi = make_float2(y.z, y.w);
+#pragma unroll
+						for (int s = 0; s < RPL; ++s) {
+							acc[s][0] = __ffma2_rn(S[s][j / 2], ylo, acc[s][0]);
+							acc[s][1] = __ffma2_rn(S[s][j / 2 + 1], yhi, acc[s][1]);
+						}
+					}
+					__syncwarp(am);
+#pragma unroll
+					for (int s = 0; s < RPL; ++s)
+						xr[s] = (acc[s][0].x + acc[s][0].y) + (acc[s][1].x + acc[s][1].y);
 				}
-				__syncwarp(am);
 				float rr = 0.f, ss = 0.f, nx = 0.f, nz = 0.f, nu = 0.f;
 #pragma unroll
 				for (int s = 0; s < RPL; ++s) {
-					const float xs = (acc[s][0].x + acc[s][0].y) + (acc[s][1].x + acc[s][1].y);
+					const float xs = xr[s];
 					x[s] = xs;
 					// admm_update_x_hat (:161-174), _z (:176-190), _u (:192-203)
 					const float xh = relax ? fmaf(alpha, xs, (1.0f - alpha) * z[s]) : xs;
