@@ -28,6 +28,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--shapes", default="4,16,40,64")
     ap.add_argument("--beta", type=float, default=0.5)
+    ap.add_argument("--cold", action="store_true", help="no warm start at n=64")
     ap.add_argument("--kernel", default="auto", choices=["auto", "tpq", "gpq", "bpq"])
     ap.add_argument("--counts", default="", help="override batch sizes, e.g. 24:262144,32:262144")
     args = ap.parse_args()
@@ -45,7 +46,7 @@ def main():
     for n in [int(s) for s in args.shapes.split(",")]:
         count = counts[n]
         P, q = make_batch(count, n, 2026, dev)
-        warm = n == 64
+        warm = n == 64 and not args.cold
         kw = {}
         if warm:
             first = qp.solve_batch(P, q, -args.beta, args.beta, options=opts)
