@@ -455,3 +455,67 @@ def test_kernel_families_agree_on_a_large_batch(qp, n, fams):
         dx = (a["x"] - b["x"]).abs().amax(dim=1)
         assert float(dx[same].max()) <= 2e-5
         assert float((a["z"] - b["z"]).abs().amax(dim=1)[same].max()) <= 2e-5
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 7, 63, 64])
+def test_edge_dimensions_and_tiny_batches(qp, orc, n):
+    """Smallest and largest dimensions, batches of 1, 2 and 33 problems (less than a warp,
+    one more than a warp)."""
+    for count in (1, 2, 33):
+        P, q, lb, ub = problems.wellcond(count, n, seed=40 + n + count, beta=0.5)
+        o = orc.admm(P.astype(np.float64), q.astype(np.float64), lb, ub)
+        res = solve_dev(qp, P, q, lb, ub)
+        ok = nondegenerate(o["margins"])
+        assert np.array_equal(res["iters"][ok], o["iters"][ok])
+        assert np.array_equal(res["status"][ok], o["status"][ok])
+        assert rel_err(res["x"].astype(np.float64), o["x"])[ok].max(initial=0.0) <= X_TOL
+
+
+def test_zero_iterations_empty_batch_and_unwritten_outputs(qp):
+    """iterations = 0 returns x = 0 with status 1 like the reference's loop that never runs
+    (qp_solvers.c:284; x is zero-initialised pool memory there); count = 0 is a no-op;
+    output arrays the caller does not pass are not written."""
+    P, q, lb, ub = problems.wellcond(50, 16, seed=3, beta=0.5)
+    r = solve_dev(qp, P, q, lb, ub, options=qp.Options(max_iter=0))
+    assert np.all(r["iters"] == 0) and np.all(r["status"] == qp.STATUS_MAX_ITER)
+    assert np.all(r["x"] == 0)
+    tP, tq = dev(P[:0], q[:0])
+    e = qp.solve_batch(tP, tq, -1.0, 1.0)
+    assert e["x"].shape == (0, 16)
+    # only x requested through the C ABI
+    import ctypes as C
+    from embedded_qp_solver_b200 import api
+    lib = qp.load_library()
+    tP, tq = dev(P, q)
+    x = torch.full((50, 16), 7.0, device="cuda")
+    pb = api.qp_batch()
+    pb.n, pb.count, pb.mem, pb.P, pb.q = 16, 50, api.MEM_DEVICE, tP.data_ptr(), tq.data_ptr()
+    pb.lb_scalar, pb.ub_scalar = -0.5, 0.5
+    sol = api.qp_batch_solution()
+    sol.x = x.data_ptr()
+    assert lib.qp_solve_batch(C.byref(pb), C.byref(sol), None) == 0
+    torch.cuda.synchronize()
+    full = qp.solve_batch(tP, tq, -0.5, 0.5)
+    assert torch.equal(x, full["x"])
+
+
+def test_api_misuse_returns_codes_never_exits(qp):
+    import ctypes as C
+    from embedded_qp_solver_b200 import api
+    lib = qp.load_library()
+    pb, sol = api.qp_batch(), api.qp_batch_solution()
+    assert lib.qp_solve_batch(None, C.byref(sol), None) == api.QP_ERR_INVALID
+    pb.n, pb.count, pb.mem = 0, 1, api.MEM_DEVICE
+    assert lib.qp_solve_batch(C.byref(pb), C.byref(sol), None) == api.QP_ERR_INVALID
+    pb.n = 65
+    assert lib.qp_solve_batch(C.byref(pb), C.byref(sol), None) == api.QP_ERR_UNSUPPORTED
+    pb.n, pb.P, pb.q = 16, None, None
+    assert lib.qp_solve_batch(C.byref(pb), C.byref(sol), None) == api.QP_ERR_INVALID
+    t = torch.zeros(16 * 16 + 16, device="cuda")
+    pb.P, pb.q = t.data_ptr(), t.data_ptr()
+    bad = qp.Options(rho=-1.0).to_c()
+    assert lib.qp_solve_batch(C.byref(pb), C.byref(sol), C.byref(bad)) == api.QP_ERR_INVALID
+    bad = qp.Options(alpha=2.5).to_c()
+    assert lib.qp_solve_batch(C.byref(pb), C.byref(sol), C.byref(bad)) == api.QP_ERR_INVALID
+    bad = qp.Options(device=99).to_c()
+    assert lib.qp_solve_batch(C.byref(pb), C.byref(sol), C.byref(bad)) == api.QP_ERR_NO_DEVICE
