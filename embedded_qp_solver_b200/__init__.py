@@ -12,7 +12,7 @@ from .api import (ABI_SYMBOLS, KERNEL_AUTO, KERNEL_BPQ, KERNEL_GPQ, KERNEL_TPQ, 
                   STATUS_NONFINITE, STATUS_SINGULAR, Matrix, Options, QpError, QuadraticForm,
                   Workspace, admm, admm_many, algorithmic_bytes, algorithmic_flops, eval_batch,
                   kernel_for, load_library, newton_batch, newton_method_with_line_search,
-                  probe_fp32_tflops, probe_hbm_gbs, read_problem_file, solve_batch,
+                  probe_fp32_tflops, probe_hbm_gbs, read_problem_file, solve_batch, solve_general_batch,
                   write_problem_file)
 from . import problems  # noqa: F401
 
@@ -20,6 +20,6 @@ __all__ = [
     "ABI_SYMBOLS", "KERNEL_AUTO", "KERNEL_BPQ", "KERNEL_GPQ", "KERNEL_TPQ", "LIB_PATH", "QP_MAX_DIM", "STATUS_CONVERGED", "STATUS_MAX_ITER",
     "STATUS_NONFINITE", "STATUS_SINGULAR", "Matrix", "Options", "QpError", "QuadraticForm",
     "Workspace", "admm", "admm_many", "algorithmic_bytes", "algorithmic_flops", "eval_batch",
-    "kernel_for", "load_library", "newton_batch", "newton_method_with_line_search", "probe_fp32_tflops", "probe_hbm_gbs", "read_problem_file", "solve_batch", "write_problem_file",
+    "kernel_for", "load_library", "newton_batch", "newton_method_with_line_search", "probe_fp32_tflops", "probe_hbm_gbs", "read_problem_file", "solve_batch", "solve_general_batch", "write_problem_file",
     "problems",
 ]

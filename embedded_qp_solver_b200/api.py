@@ -21,6 +21,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libqpb200.so")
 
 QP_MAX_DIM = 64
+QP_MAX_ROWS = 128
 STATUS_CONVERGED, STATUS_MAX_ITER, STATUS_SINGULAR, STATUS_NONFINITE = 0, 1, 2, 3
 QP_OK, QP_ERR_INVALID, QP_ERR_UNSUPPORTED, QP_ERR_CUDA, QP_ERR_NO_DEVICE = 0, -1, -2, -3, -4
 QP_ERR_IO = -5
@@ -40,6 +41,17 @@ class qp_batch(C.Structure):
 
 class qp_batch_solution(C.Structure):
     _fields_ = [("x", C.c_void_p), ("z", C.c_void_p), ("lam", C.c_void_p),
+                ("status", C.c_void_p), ("iters", C.c_void_p)]
+
+
+class qp_general_batch(C.Structure):
+    _fields_ = [("n", C.c_uint32), ("m", C.c_uint32), ("mem", C.c_uint32), ("pad", C.c_uint32),
+                ("count", C.c_size_t), ("P", C.c_void_p), ("q", C.c_void_p), ("A", C.c_void_p),
+                ("l", C.c_void_p), ("u", C.c_void_p), ("z0", C.c_void_p), ("u0", C.c_void_p)]
+
+
+class qp_general_solution(C.Structure):
+    _fields_ = [("x", C.c_void_p), ("z", C.c_void_p), ("y", C.c_void_p),
                 ("status", C.c_void_p), ("iters", C.c_void_p)]
 
 
@@ -68,6 +80,7 @@ ABI_SYMBOLS = [
     "qp_device_count", "qp_kernel_for", "qp_probe_fp32_tflops", "qp_probe_hbm_gbs",
     "qp_newton_batch", "qp_newton_qf",
     "qp_problem_file_write", "qp_problem_file_count", "qp_problem_file_read",
+    "qp_solve_general_batch",
 ]
 
 _lib = None
@@ -137,6 +150,9 @@ def load_library(path: Optional[str] = None):
     lib.qp_problem_file_count.restype = C.c_longlong
     lib.qp_problem_file_read.argtypes = [C.c_char_p, C.c_size_t, C.c_size_t, C.c_uint32, _dp, _dp]
     lib.qp_problem_file_read.restype = C.c_int
+    lib.qp_solve_general_batch.argtypes = [C.POINTER(qp_general_batch),
+                                           C.POINTER(qp_general_solution), C.POINTER(qp_options)]
+    lib.qp_solve_general_batch.restype = C.c_int
     lib.qp_last_error.restype = C.c_char_p
     lib.qp_device_count.restype = C.c_int
     lib.qp_kernel_for.argtypes = [C.c_uint32, C.c_int]
@@ -322,6 +338,44 @@ def eval_batch(P, q, x, r: float = 0.0):
     if rc != QP_OK:
         raise QpError(rc, "qp_eval_batch")
     return f
+
+
+def solve_general_batch(P, q, A, l, u, z0=None, u0=None, options: Optional[Options] = None):
+    """``l <= A x <= u`` rows (``qp_solve_general_batch``): the reference's ADMM iteration for
+    the splitting A x = z.  Returns dict(x, z, y, status, iters); device tensors in, device
+    tensors out; numpy in, numpy out."""
+    lib = load_library()
+    count, n = int(P.shape[0]), int(P.shape[1])
+    m = int(A.shape[1])
+    hP, aP, dev = _as_f32(P, (count, n, n), "P")
+    hq, aq, _ = _as_f32(q, (count, n), "q")
+    hA, aA, _ = _as_f32(A, (count, m, n), "A")
+    hl, al, _ = _as_f32(l, (count, m), "l")
+    hu, au, _ = _as_f32(u, (count, m), "u")
+    hz0, az0, _ = _as_f32(z0, (count, m), "z0")
+    hu0, au0, _ = _as_f32(u0, (count, m), "u0")
+    pb = qp_general_batch()
+    pb.n, pb.m, pb.count, pb.mem = n, m, count, (MEM_DEVICE if dev else MEM_HOST)
+    pb.P, pb.q, pb.A, pb.l, pb.u, pb.z0, pb.u0 = aP, aq, aA, al, au, az0, au0
+    copt = (options or Options()).to_c()
+    shapes = {"x": ((count, n), "f"), "z": ((count, m), "f"), "y": ((count, m), "f"),
+              "status": ((count,), "i"), "iters": ((count,), "i")}
+    if dev:
+        import torch
+        d = hP.device
+        out = {k: torch.empty(sh, dtype=torch.float32 if t == "f" else torch.int32, device=d)
+               for k, (sh, t) in shapes.items()}
+        copt.device = d.index
+        copt.stream = C.c_void_p(torch.cuda.current_stream(d).cuda_stream or None)
+        addr = {k: v.data_ptr() for k, v in out.items()}
+    else:
+        out = {k: np.empty(sh, np.float32 if t == "f" else np.int32) for k, (sh, t) in shapes.items()}
+        addr = {k: v.ctypes.data for k, v in out.items()}
+    sol = qp_general_solution(addr["x"], addr["z"], addr["y"], addr["status"], addr["iters"])
+    rc = lib.qp_solve_general_batch(C.byref(pb), C.byref(sol), C.byref(copt))
+    if rc != QP_OK:
+        raise QpError(rc, "qp_solve_general_batch")
+    return out
 
 
 def newton_batch(P, q, x0=None, iterations: int = 10, r: float = 0.0, want_f: bool = False):

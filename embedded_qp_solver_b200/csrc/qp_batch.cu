@@ -25,6 +25,7 @@
 #include <vector>
 
 #include "qp_bpq.cuh"
+#include "qp_gen.cuh"
 #include "qp_gpq.cuh"
 #include "qp_newton.cuh"
 #include "qp_tpq.cuh"
@@ -946,6 +947,111 @@ extern "C" int qp_newton_batch(const qp_batch *pb, const float *x0, unsigned ite
 		return rc;
 	if (e != cudaSuccess) {
 		g_err = std::string("qp_newton_batch: ") + cudaGetErrorString(e);
+		return QP_ERR_CUDA;
+	}
+	return QP_OK;
+}
+
+// ----------------------------------------------------------------------------------------
+// general rows l <= A x <= u (qp_gen.cuh)
+// ----------------------------------------------------------------------------------------
+static int launch_gen(const GenArgs &a, int dev, cudaStream_t st)
+{
+	const size_t smem = GEN_WARPS * gen_smem_floats_per_warp(a.n, a.m) * sizeof(float);
+	const size_t smem_max = GEN_WARPS * gen_smem_floats_per_warp(QP_MAX_DIM, QP_MAX_ROWS) * sizeof(float);
+	static bool attr_done[64] = {};
+	if (!attr_done[dev]) {
+		QP_CUDA(cudaFuncSetAttribute(qp_gen_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+					     int(smem_max)));
+		attr_done[dev] = true;
+	}
+	int per_sm = 1;
+	QP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, qp_gen_kernel, GEN_WARPS * 32, smem));
+	per_sm = std::max(1, per_sm);
+	const unsigned long long need = (a.count + GEN_WARPS - 1) / GEN_WARPS;
+	const unsigned long long grid =
+		std::max(1ull, std::min((unsigned long long)dev_sms(dev) * per_sm, need));
+	qp_gen_kernel<<<dim3((unsigned)grid), dim3(GEN_WARPS * 32), smem, st>>>(a);
+	QP_CUDA(cudaGetLastError());
+	return QP_OK;
+}
+
+extern "C" int qp_solve_general_batch(const qp_general_batch *pb, const qp_general_solution *sol,
+				      const qp_options *opt_in)
+{
+	if (!pb || !sol || pb->n == 0 || pb->m == 0)
+		return QP_ERR_INVALID;
+	if (pb->n > QP_MAX_DIM || pb->m > QP_MAX_ROWS)
+		return QP_ERR_UNSUPPORTED;
+	if (pb->mem != QP_MEM_HOST && pb->mem != QP_MEM_DEVICE)
+		return QP_ERR_INVALID;
+	if ((pb->z0 == nullptr) != (pb->u0 == nullptr))
+		return QP_ERR_INVALID;
+	qp_options opt;
+	if (opt_in)
+		opt = *opt_in;
+	else
+		qp_options_default(&opt);
+	int rc = check_options(opt);
+	if (rc != QP_OK)
+		return rc;
+	if (pb->count == 0)
+		return QP_OK;
+	if (!pb->P || !pb->q || !pb->A || !pb->l || !pb->u || !sol->x)
+		return QP_ERR_INVALID;
+	const int dev = resolve_device(opt.device);
+	if (dev < 0)
+		return QP_ERR_NO_DEVICE;
+	DeviceGuard g;
+	if (g.enter(dev) != QP_OK)
+		return QP_ERR_NO_DEVICE;
+	const size_t n = pb->n, m = pb->m, c = pb->count;
+	GenArgs a = {};
+	a.count = c, a.n = int(n), a.m = int(m);
+	a.rho = opt.rho, a.alpha = opt.alpha, a.reltol = opt.reltol, a.max_iter = opt.max_iter;
+	a.eps_abs_pri = float(std::sqrt(double(m)) * double(opt.abstol));
+	a.eps_abs_dual = float(std::sqrt(double(n)) * double(opt.abstol));
+	if (pb->mem == QP_MEM_DEVICE) {
+		a.P = pb->P, a.q = pb->q, a.A = pb->A, a.l = pb->l, a.u = pb->u, a.z0 = pb->z0, a.u0 = pb->u0;
+		a.x = sol->x, a.z = sol->z, a.y = sol->y, a.status = sol->status, a.iters = sol->iters;
+		return launch_gen(a, dev, static_cast<cudaStream_t>(opt.stream));
+	}
+	// host pointers: one staging allocation, synchronous
+	const size_t fin = c * (n * n + n + m * n + 4 * m), fout = c * (n + 2 * m + 2);
+	float *d = nullptr;
+	QP_CUDA(cudaMalloc(&d, (fin + fout) * 4));
+	float *dP = d, *dq = dP + c * n * n, *dA = dq + c * n, *dl = dA + c * m * n, *du = dl + c * m,
+	      *dz0 = du + c * m, *du0 = dz0 + c * m, *dx = du0 + c * m, *dz = dx + c * n, *dy = dz + c * m;
+	int32_t *dst = reinterpret_cast<int32_t *>(dy + c * m), *dit = dst + c;
+	struct Cp {
+		void *dst;
+		const void *src;
+		size_t bytes;
+	} ins[] = { { dP, pb->P, c * n * n * 4 }, { dq, pb->q, c * n * 4 },  { dA, pb->A, c * m * n * 4 },
+		    { dl, pb->l, c * m * 4 },     { du, pb->u, c * m * 4 },  { dz0, pb->z0, c * m * 4 },
+		    { du0, pb->u0, c * m * 4 } };
+	cudaError_t e = cudaSuccess;
+	for (const Cp &cp : ins)
+		if (cp.src && e == cudaSuccess)
+			e = cudaMemcpy(cp.dst, cp.src, cp.bytes, cudaMemcpyHostToDevice);
+	rc = QP_OK;
+	if (e == cudaSuccess) {
+		a.P = dP, a.q = dq, a.A = dA, a.l = dl, a.u = du;
+		a.z0 = pb->z0 ? dz0 : nullptr, a.u0 = pb->u0 ? du0 : nullptr;
+		a.x = dx, a.z = dz, a.y = dy, a.status = dst, a.iters = dit;
+		rc = launch_gen(a, dev, nullptr);
+		Cp outs[] = { { sol->x, dx, c * n * 4 },      { sol->z, dz, c * m * 4 },
+			      { sol->y, dy, c * m * 4 },      { sol->status, dst, c * 4 },
+			      { sol->iters, dit, c * 4 } };
+		for (const Cp &cp : outs)
+			if (cp.dst && rc == QP_OK && e == cudaSuccess)
+				e = cudaMemcpy(cp.dst, cp.src, cp.bytes, cudaMemcpyDeviceToHost);
+	}
+	cudaFree(d);
+	if (rc != QP_OK)
+		return rc;
+	if (e != cudaSuccess) {
+		g_err = std::string("qp_solve_general_batch: ") + cudaGetErrorString(e);
 		return QP_ERR_CUDA;
 	}
 	return QP_OK;

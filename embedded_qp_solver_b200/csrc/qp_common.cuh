@@ -150,6 +150,50 @@ __device__ __forceinline__ float warp_sum(float v)
 	return v;
 }
 
+// In-place inverse of a symmetric positive definite n x n matrix in SHARED memory (row
+// stride ld), by one warp: Gauss-Jordan without pivoting, lanes own columns lane and
+// lane + 32 (n <= 64).  `col` is an n-float scratch vector in shared memory.  Returns
+// true when a pivot is not strictly positive.  Used by the correctness-first kernels
+// (qp_newton.cuh, qp_gen.cuh); the tuned kernels invert in registers.
+__device__ __forceinline__ bool smem_gauss_jordan(float *W, int n, int ld, float *col, int lane)
+{
+	const int i0 = lane, i1 = lane + 32;
+	const bool h0 = i0 < n, h1 = i1 < n;
+	bool bad = false;
+	for (int k = 0; k < n; ++k) {
+		const float piv = W[k * ld + k];
+		bad |= !(piv > 0.0f);
+		const float dinv = 1.0f / piv;
+		__syncwarp();
+		// scaled pivot row, kept in registers for the elimination below
+		float p0 = 0.f, p1 = 0.f;
+		if (h0) {
+			p0 = (i0 == k) ? dinv : W[k * ld + i0] * dinv;
+			W[k * ld + i0] = p0;
+		}
+		if (h1) {
+			p1 = (i1 == k) ? dinv : W[k * ld + i1] * dinv;
+			W[k * ld + i1] = p1;
+		}
+		// column k (the multipliers) is copied out first, so that its owner can rewrite
+		// it while the others still read it
+		if (h0) col[i0] = W[i0 * ld + k];
+		if (h1) col[i1] = W[i1 * ld + k];
+		__syncwarp();
+		for (int i = 0; i < n; ++i) {
+			if (i == k)
+				continue;
+			const float f = col[i];
+			if (h0)
+				W[i * ld + i0] = (i0 == k) ? -f * p0 : fmaf(-f, p0, W[i * ld + i0]);
+			if (h1)
+				W[i * ld + i1] = (i1 == k) ? -f * p1 : fmaf(-f, p1, W[i * ld + i1]);
+		}
+		__syncwarp();
+	}
+	return bad;
+}
+
 __device__ __forceinline__ bool finite_f(float v)
 {
 	return (v - v) == 0.0f;

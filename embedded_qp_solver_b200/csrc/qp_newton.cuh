@@ -79,39 +79,8 @@ __global__ void __launch_bounds__(NEWTON_WARPS * 32) qp_newton_kernel(const Newt
 		float x1 = (h1 && a.x0) ? __ldg(a.x0 + vo + i1) : 0.f;
 		__syncwarp();
 
-		// ---- W <- P^-1: Gauss-Jordan, lanes own columns lane and lane + 32 ---------------------
-		bool bad = false;
-		for (int k = 0; k < n; ++k) {
-			const float piv = W[k * ld + k];
-			bad |= !(piv > 0.0f);
-			const float dinv = 1.0f / piv;
-			__syncwarp();
-			// scaled pivot row, kept in registers for the elimination below
-			float p0 = 0.f, p1 = 0.f;
-			if (h0) {
-				p0 = (i0 == k) ? dinv : W[k * ld + i0] * dinv;
-				W[k * ld + i0] = p0;
-			}
-			if (h1) {
-				p1 = (i1 == k) ? dinv : W[k * ld + i1] * dinv;
-				W[k * ld + i1] = p1;
-			}
-			// column k (the multipliers) is copied out first, so that its owner can rewrite
-			// it while the others still read it
-			if (h0) vg[i0] = W[i0 * ld + k];
-			if (h1) vg[i1] = W[i1 * ld + k];
-			__syncwarp();
-			for (int i = 0; i < n; ++i) {
-				if (i == k)
-					continue;
-				const float f = vg[i];
-				if (h0)
-					W[i * ld + i0] = (i0 == k) ? -f * p0 : fmaf(-f, p0, W[i * ld + i0]);
-				if (h1)
-					W[i * ld + i1] = (i1 == k) ? -f * p1 : fmaf(-f, p1, W[i * ld + i1]);
-			}
-			__syncwarp();
-		}
+		// ---- W <- P^-1 -----------------------------------------------------------------------
+		const bool bad = smem_gauss_jordan(W, n, ld, vg, lane);
 
 		// ---- Newton steps ---------------------------------------------------------------------
 		auto matvec = [&](const float *M, const float *v, float &o0, float &o1) {

@@ -173,6 +173,41 @@ int qp_newton_batch(const qp_batch *prob, const float *x0, unsigned iterations,
 		    const qp_options *opt);
 
 /*
+ * General inequality rows  l <= A x <= u  (SURVEY.md 8(f) rank 3).  The reference has only
+ * the box; this entry point runs the SAME scaled-form ADMM (qp_solvers.c:255-319) for the
+ * splitting A x = z:  (P + rho A'A) x = rho A'(z - u) - q;  z = clip(alpha A x + (1-alpha) z
+ * + u, l, u);  u += alpha A x + (1-alpha) z_old - z;  stop when ||A x - z|| < sqrt(m) abstol
+ * + reltol max(||A x||, ||z||) and rho ||A'(z - z_old)|| < sqrt(n) abstol + reltol rho ||A'u||.
+ * With A = I it is the reference's iteration line by line (and is tested against the same
+ * golden vectors); for other A there is no reference behaviour to match.
+ * n <= QP_MAX_DIM, m <= QP_MAX_ROWS.  P + rho A'A must be positive definite.
+ */
+#define QP_MAX_ROWS 128
+typedef struct qp_general_batch {
+	uint32_t n;       /* variables                                            */
+	uint32_t m;       /* rows of A                                            */
+	uint32_t mem;     /* QP_MEM_HOST or QP_MEM_DEVICE, for every pointer      */
+	uint32_t pad;
+	size_t count;
+	const float *P;   /* [count][n][n] row-major, symmetric                   */
+	const float *q;   /* [count][n]                                           */
+	const float *A;   /* [count][m][n] row-major                              */
+	const float *l;   /* [count][m]; -INFINITY for a one-sided row            */
+	const float *u;   /* [count][m]; +INFINITY for a one-sided row            */
+	const float *z0;  /* [count][m] warm start of z, or NULL = 0              */
+	const float *u0;  /* [count][m] warm start of the scaled dual, or NULL    */
+} qp_general_batch;
+typedef struct qp_general_solution {
+	float *x;         /* [count][n], required                                 */
+	float *z;         /* [count][m] clipped A x, or NULL                      */
+	float *y;         /* [count][m] multipliers of the rows (rho u), or NULL  */
+	int32_t *status;  /* [count] QP_STATUS_*, or NULL                         */
+	int32_t *iters;   /* [count], or NULL                                     */
+} qp_general_solution;
+int qp_solve_general_batch(const qp_general_batch *prob, const qp_general_solution *sol,
+			   const qp_options *opt);
+
+/*
  * Entry points on the reference's own structs (binary64, pool-owned).  The
  * two structs below are layout-identical to `struct _matrix`
  * (matrix/matrix_type/matrix_type.h:20-23: rows in bits 31:16 and columns in
