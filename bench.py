@@ -377,7 +377,7 @@ def run_ours(args, rank, local_rank, world):
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": config_of(args, world),
-            "clocks": sampler.report(), "e2e": e2e, "gpu_launches": args.steps,
+            "clocks": sampler.report(), "e2e": e2e, "gpu_launches": args.steps * world,
             "roofline": roofline, "cpu_baseline": cpu,
             "mean_iters": mean_iters, "not_converged": n_bad}
     print(json.dumps(line), flush=True)
