@@ -46,7 +46,10 @@ namespace qpb {
 #ifndef QPB_GPQ_MINB_BIG
 #define QPB_GPQ_MINB_BIG 2
 #endif
-constexpr int GPQ_WARPS = 4; // warps per CTA
+#ifndef QPB_GPQ_WARPS
+#define QPB_GPQ_WARPS 4
+#endif
+constexpr int GPQ_WARPS = QPB_GPQ_WARPS; // warps per CTA
 
 // lanes per QP for a padded dimension
 template <int NP> struct GpqLanes {
