@@ -303,9 +303,15 @@ def run_ours(args, rank, local_rank, world):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
         same = bool(torch.equal(hout["iters"], out["iters"].cpu()))
+        # the caller hands over full row-major matrices; the library may send only their
+        # upper triangles over PCIe (qp_host_path_packs)
+        packs = qp.host_path_packs(n)
+        wire_p = (n * (n + 1) // 2 + 3) // 4 * 4 if packs else n * n
         e2e = {"value": count * world / dt, "unit": UNIT,
                "h2d_bytes_per_step": (n * n + n) * 4 * count,
                "d2h_bytes_per_step": (3 * n + 2) * 4 * count,
+               "h2d_bytes_on_the_wire_per_step": (wire_p + n) * 4 * count,
+               "host_packs_upper_triangle": bool(packs),
                "steps": ksteps, "ms_per_step": dt * 1e3, "matches_device_path": same,
                "host_memory": "pinned"}
         del hP, hq, hout

@@ -80,7 +80,7 @@ ABI_SYMBOLS = [
     "qp_device_count", "qp_kernel_for", "qp_probe_fp32_tflops", "qp_probe_hbm_gbs",
     "qp_newton_batch", "qp_newton_qf",
     "qp_problem_file_write", "qp_problem_file_count", "qp_problem_file_read",
-    "qp_solve_general_batch",
+    "qp_solve_general_batch", "qp_host_path_packs",
 ]
 
 _lib = None
@@ -153,6 +153,8 @@ def load_library(path: Optional[str] = None):
     lib.qp_solve_general_batch.argtypes = [C.POINTER(qp_general_batch),
                                            C.POINTER(qp_general_solution), C.POINTER(qp_options)]
     lib.qp_solve_general_batch.restype = C.c_int
+    lib.qp_host_path_packs.argtypes = [C.c_uint32]
+    lib.qp_host_path_packs.restype = C.c_int
     lib.qp_last_error.restype = C.c_char_p
     lib.qp_device_count.restype = C.c_int
     lib.qp_kernel_for.argtypes = [C.c_uint32, C.c_int]
@@ -532,6 +534,11 @@ def admm_many(qfs, iterations: int, lb: float = -1e12, ub: float = 1e12):
     if rc != QP_OK:
         raise QpError(rc, "qp_admm_qf_batch")
     return x, st, it
+
+
+def host_path_packs(n: int) -> bool:
+    """True when the host-memory path sends packed upper triangles of P over PCIe."""
+    return bool(load_library().qp_host_path_packs(n))
 
 
 def kernel_for(n: int, aligned16: bool = True) -> str:

@@ -24,7 +24,14 @@ struct KernelArgs {
 	float eps_abs;         // sqrt(n) * abstol   (qp_solvers.c:242, :252)
 	float reltol;
 	unsigned max_iter;
+	int p_packed;          // tpq: P holds packed upper triangles, tpq_packed_stride(n) floats each
 };
+
+// floats per problem of the packed upper triangle (row-major, i <= j), padded to 16 bytes
+__host__ __device__ constexpr int tpq_packed_stride(int n)
+{
+	return (n * (n + 1) / 2 + 3) / 4 * 4;
+}
 
 // ---- PTX wrappers ---------------------------------------------------------
 

@@ -55,6 +55,11 @@ template <int N, bool BOUNDS, bool WARM> struct TpqLayout {
 	using Cfg = TpqCfg<N, BOUNDS, WARM>;
 	static constexpr int PAD = (N >= 8) ? 4 : 0;          // floats of padding per P slot
 	static constexpr int PSLOT = N * N + PAD;             // floats per P slot
+	// packed upper triangles (host path, qp_batch.cu): record and slot sizes; the slot is
+	// an odd number of 16-byte units so that the lanes' 128-bit reads do not conflict
+	static constexpr int PK = tpq_packed_stride(N);
+	static constexpr int PKSLOT = ((PK / 4) % 2) ? PK : PK + 4;
+	static_assert(PKSLOT <= PSLOT, "packed slots must fit the stage");
 	static constexpr int NVEC_STAGE = 1 + (BOUNDS ? 2 : 0) + (WARM ? 2 : 0);
 	static constexpr int STAGE_P = 32 * PSLOT;
 	static constexpr int STAGE = STAGE_P + NVEC_STAGE * 32 * N; // floats per stage
@@ -169,9 +174,17 @@ qp_tpq_kernel(const KernelArgs p)
 		float *st = ring + s * L::STAGE;
 		if (lane == 0)
 			mbar_expect_tx(&full_bar[s],
-				       uint32_t(cnt) * (N * N + L::NVEC_STAGE * N) * 4u);
+				       uint32_t(cnt) * ((p.p_packed ? L::PK : N * N) + L::NVEC_STAGE * N) * 4u);
 		__syncwarp();
-		if (L::PAD > 0) {
+		if (p.p_packed) {
+			if (L::PKSLOT != L::PK) {
+				if (lane < cnt)
+					bulk_g2s(st + lane * L::PKSLOT, p.P + (first + lane) * L::PK,
+						 L::PK * 4, &full_bar[s]);
+			} else if (lane == 0) {
+				bulk_g2s(st, p.P + first * L::PK, uint32_t(cnt) * L::PK * 4, &full_bar[s]);
+			}
+		} else if (L::PAD > 0) {
 			if (lane < cnt)
 				bulk_g2s(st + lane * L::PSLOT, p.P + (first + lane) * (N * N),
 					 N * N * 4, &full_bar[s]);
@@ -235,6 +248,19 @@ qp_tpq_kernel(const KernelArgs p)
 		{
 			const float *st = ring + s * L::STAGE;
 			const float4 *slot4 = reinterpret_cast<const float4 *>(st + lane * L::PSLOT);
+			if (p.p_packed) {
+				// the record is the upper triangle in the order a[] keeps it
+				const float4 *pk4 = reinterpret_cast<const float4 *>(st + lane * L::PKSLOT);
+#pragma unroll
+				for (int k = 0; k < L::PK / 4; ++k) {
+					const float4 v = pk4[k];
+					const float e[4] = { v.x, v.y, v.z, v.w };
+#pragma unroll
+					for (int t = 0; t < 4; ++t)
+						if (4 * k + t < N * (N + 1) / 2)
+							a[4 * k + t] = e[t];
+				}
+			} else
 #pragma unroll
 			for (int i = 0; i < N; ++i) {
 #pragma unroll

@@ -264,6 +264,12 @@ long long qp_problem_file_count(const char *path, uint32_t *n);
 int qp_problem_file_read(const char *path, size_t first, size_t count,
 			 uint32_t n, double *P, double *q);
 
+/* 1 when the QP_MEM_HOST path packs the upper triangles of P on the host before the copy
+ * (n = 8, 12, 16, at least 12 hardware threads, QPB200_HOST_PACK != 0): P is symmetric and
+ * the kernels read only its upper triangle, so 544 instead of 1 024 bytes per problem cross
+ * PCIe at n = 16. */
+int qp_host_path_packs(uint32_t n);
+
 /* Diagnostics. */
 const char *qp_last_error(void);      /* text of the last QP_ERR_CUDA, per thread */
 int qp_device_count(void);
