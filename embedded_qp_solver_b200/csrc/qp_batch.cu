@@ -388,16 +388,20 @@ public:
 		for (std::thread &w : workers_)
 			w.join();
 	}
-	// body(part, parts) on every worker; returns when all are done
-	void run(const std::function<void(unsigned, unsigned)> &body)
+	// body(part, parts) on every worker, asynchronously; wait() returns when all are done
+	void start(std::function<void(unsigned, unsigned)> body)
 	{
 		std::unique_lock<std::mutex> lk(mu_);
-		body_ = &body;
+		done_.wait(lk, [this] { return pending_ == 0; }); // a previous call that returned early
+		body_ = std::move(body);
 		pending_ = unsigned(workers_.size());
 		++gen_;
 		cv_.notify_all();
+	}
+	void wait()
+	{
+		std::unique_lock<std::mutex> lk(mu_);
 		done_.wait(lk, [this] { return pending_ == 0; });
-		body_ = nullptr;
 	}
 
 private:
@@ -405,17 +409,16 @@ private:
 	{
 		unsigned long seen = 0;
 		for (;;) {
-			const std::function<void(unsigned, unsigned)> *b;
 			{
 				std::unique_lock<std::mutex> lk(mu_);
 				cv_.wait(lk, [&] { return gen_ != seen; });
 				seen = gen_;
 				if (stop_)
 					return;
-				b = body_;
 			}
-			if (b)
-				(*b)(id, unsigned(workers_.size()));
+			// body_ is not replaced before every worker has reported back
+			if (body_)
+				body_(id, unsigned(workers_.size()));
 			{
 				std::lock_guard<std::mutex> lk(mu_);
 				if (--pending_ == 0)
@@ -426,7 +429,7 @@ private:
 	std::vector<std::thread> workers_;
 	std::mutex mu_;
 	std::condition_variable cv_, done_;
-	const std::function<void(unsigned, unsigned)> *body_ = nullptr;
+	std::function<void(unsigned, unsigned)> body_;
 	unsigned pending_ = 0;
 	unsigned long gen_ = 0;
 	bool stop_ = false;
@@ -692,12 +695,46 @@ int run_shard(qp_workspace *ws, DeviceCtx &ctx, const qp_batch &pb, const qp_bat
 		// one core moves ~10 GB/s; PCIe wants ~85 GB/s of packing traffic: use the cores
 		ctx.pool = new HostPool(std::min(32u, std::max(2u, (hw - 1) / unsigned(ws->devs.size()))));
 
-	size_t k = 0;
-	for (size_t first = lo; first < hi; first += chunk, ++k) {
-		Slot &s = ctx.slot[k % DEPTH];
+	// packing of chunk k+1 runs on the pool while this thread enqueues chunk k
+	auto start_pack = [&](size_t kk, size_t first) -> int {
+		Slot &s = ctx.slot[kk % DEPTH];
 		int rc = retire(s);
 		if (rc != QP_OK)
 			return rc;
+		if (!s.hpk)
+			QP_CUDA(cudaMallocHost(&s.hpk, chunk * size_t(pk) * 4));
+		const size_t c = std::min(chunk, hi - first);
+		const float *src = pb.P + first * size_t(n) * n;
+		float *dst = s.hpk;
+		const int nn = int(n), pkk = pk;
+		ctx.pool->start([=](unsigned part, unsigned parts) {
+			const size_t a = c * part / parts, b = c * (part + 1) / parts;
+			pack_upper(src + a * size_t(nn) * nn, dst + a * size_t(pkk), b - a, nn);
+		});
+		return QP_OK;
+	};
+	if (pack && lo < hi) {
+		int rc = start_pack(0, lo);
+		if (rc != QP_OK)
+			return rc;
+	}
+
+	size_t k = 0;
+	for (size_t first = lo; first < hi; first += chunk, ++k) {
+		Slot &s = ctx.slot[k % DEPTH];
+		int rc = QP_OK;
+		if (pack) {
+			ctx.pool->wait(); // chunk k is packed (its slot was retired by start_pack)
+			if (first + chunk < hi)
+				rc = start_pack(k + 1, first + chunk);
+		} else {
+			rc = retire(s);
+		}
+		if (rc != QP_OK) {
+			if (pack)
+				ctx.pool->wait();
+			return rc;
+		}
 		const size_t c = std::min(chunk, hi - first);
 		s.first = first, s.cnt = c;
 		cudaStream_t st = s.stream;
@@ -709,17 +746,8 @@ int run_shard(qp_workspace *ws, DeviceCtx &ctx, const qp_batch &pb, const qp_bat
 			size_t per;
 		} ins[] = { { pb.P, s.dP, size_t(n) * n }, { pb.q, s.dq, n },  { pb.lb, s.dlb, n },
 			    { pb.ub, s.dub, n },           { pb.z0, s.dz0, n }, { pb.u0, s.du0, n } };
-		if (pack) {
-			if (!s.hpk)
-				QP_CUDA(cudaMallocHost(&s.hpk, chunk * size_t(pk) * 4));
-			const float *src = pb.P + first * size_t(n) * n;
-			float *dst = s.hpk;
-			ctx.pool->run([&](unsigned part, unsigned parts) {
-				const size_t a = c * part / parts, b = c * (part + 1) / parts;
-				pack_upper(src + a * size_t(n) * n, dst + a * size_t(pk), b - a, int(n));
-			});
+		if (pack)
 			QP_CUDA(cudaMemcpyAsync(s.dP, s.hpk, c * size_t(pk) * 4, cudaMemcpyHostToDevice, st));
-		}
 		if (pin_in) {
 			for (const In &i : ins)
 				if (i.src && !(pack && i.src == pb.P))
