@@ -507,10 +507,25 @@ bool host_pack_enabled()
 
 // One core packs ~10 GB/s and the copy engine wants ~85 GB/s of it: with fewer than 12
 // hardware threads the direct copy of the full matrices is the faster path.
+//
+// Packing trades PCIe bytes for host-memory traffic (about 2.1 KB instead of 1.1 KB per
+// problem at n = 16), so it only pays while the host's DRAM is not the shared bottleneck:
+// it is used for at most two GPUs per host -- counting the ranks of a torchrun job
+// (LOCAL_WORLD_SIZE) -- and needs 12 hardware threads per GPU.
+static unsigned host_threads_per_gpu(unsigned gpus_in_this_process)
+{
+	unsigned ranks = 1;
+	if (const char *e = std::getenv("LOCAL_WORLD_SIZE"))
+		ranks = unsigned(std::max(1, std::atoi(e)));
+	const unsigned sharers = std::max(1u, ranks * std::max(1u, gpus_in_this_process));
+	if (sharers > 2)
+		return 0;
+	return std::thread::hardware_concurrency() / sharers;
+}
+
 extern "C" int qp_host_path_packs(uint32_t n)
 {
-	return host_pack_enabled() && (n == 8 || n == 12 || n == 16) &&
-	       std::thread::hardware_concurrency() >= 12;
+	return host_pack_enabled() && (n == 8 || n == 12 || n == 16) && host_threads_per_gpu(1) >= 12;
 }
 
 // ----------------------------------------------------------------------------------------
@@ -686,14 +701,14 @@ int run_shard(qp_workspace *ws, DeviceCtx &ctx, const qp_batch &pb, const qp_bat
 	};
 
 	// pack the upper triangles of P on the host when the thread-per-QP kernel will run
-	const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
-	const bool pack = qp_host_path_packs(n) &&
+	const unsigned tpg = host_threads_per_gpu(unsigned(ws->devs.size()));
+	const bool pack = qp_host_path_packs(n) && tpg >= 12 &&
 			  (opt.kernel == QP_KERNEL_AUTO || opt.kernel == QP_KERNEL_TPQ) &&
 			  ((pb.lb == nullptr) == (pb.ub == nullptr)) && ((pb.z0 == nullptr) == (pb.u0 == nullptr));
 	const int pk = tpq_packed_stride(int(n));
 	if (pack && !ctx.pool)
 		// one core moves ~10 GB/s; PCIe wants ~85 GB/s of packing traffic: use the cores
-		ctx.pool = new HostPool(std::min(32u, std::max(2u, (hw - 1) / unsigned(ws->devs.size()))));
+		ctx.pool = new HostPool(std::min(32u, tpg - 1));
 
 	// packing of chunk k+1 runs on the pool while this thread enqueues chunk k
 	auto start_pack = [&](size_t kk, size_t first) -> int {
