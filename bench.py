@@ -37,7 +37,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-METRIC = "batched QP solves/sec at n=16,m=32"
+METRIC = "batched QP solves/sec at n=16,m=32"  # the headline shape; --n N renames it
 UNIT = "QP/s"
 
 
@@ -393,7 +393,9 @@ def run_ours(args, rank, local_rank, world):
 
 
 def main():
+    global METRIC
     args = parse()
+    METRIC = f"batched QP solves/sec at n={args.n},m={2 * args.n}"
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
