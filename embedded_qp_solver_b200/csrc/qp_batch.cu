@@ -179,11 +179,16 @@ template <int N> int launch_tpq_n(const KernelArgs &a, int dev, cudaStream_t st)
 	return launch_tpq<N, false, false, false>(a, dev, st);
 }
 
-template <int NP> int launch_gpq(const KernelArgs &a, int dev, cudaStream_t st)
+// Product form or full inverse (qp_gpq.cuh, qp_bpq.cuh)?  The product form halves the
+// elimination but makes every iteration a chain of NC shuffle -> FMA steps.  Measured
+// (profiles/README.md): n = 64 warm start (1.1 iterations) +19 %, n = 40 cold start on
+// well-conditioned problems (10 iterations) +4 %, n = 40 condensed MPC (36 iterations) -13 %.
+// A warm start is the caller's statement that few iterations are expected: product form
+// with (z0, u0), full inverse without.
+template <int NP, bool PFI> int launch_gpq_form(const KernelArgs &a, int dev, cudaStream_t st)
 {
 	constexpr int T = GpqLanes<NP>::T; // lanes per QP; 32 / T problems per warp
-	// n >= 48: the inverse stays in product form (half the elimination work; profiles/README.md)
-	auto kern = qp_gpq_kernel<NP, T, (NP >= QPB_GPQ_PFI_FROM)>;
+	auto kern = qp_gpq_kernel<NP, T, PFI>;
 	static int per_sm[64] = {};
 	if (!per_sm[dev]) {
 		int b = 0;
@@ -199,6 +204,15 @@ template <int NP> int launch_gpq(const KernelArgs &a, int dev, cudaStream_t st)
 	return QP_OK;
 }
 
+template <int NP> int launch_gpq(const KernelArgs &a, int dev, cudaStream_t st)
+{
+	if constexpr (NP >= QPB_GPQ_PFI_FROM) {
+		if (a.z0 != nullptr)
+			return launch_gpq_form<NP, true>(a, dev, st);
+	}
+	return launch_gpq_form<NP, false>(a, dev, st);
+}
+
 bool bpq_eligible(const KernelArgs &a)
 {
 	const int n = a.n;
@@ -211,9 +225,9 @@ bool bpq_eligible(const KernelArgs &a)
 	return true;
 }
 
-template <int NP> int launch_bpq(const KernelArgs &a, int dev, cudaStream_t st)
+template <int NP, bool PFI> int launch_bpq_form(const KernelArgs &a, int dev, cudaStream_t st)
 {
-	auto kern = qp_bpq_kernel<NP, (NP >= QPB_BPQ_PFI_FROM)>;
+	auto kern = qp_bpq_kernel<NP, PFI>;
 	static int per_sm[64] = {};
 	if (!per_sm[dev]) {
 		int b = 0;
@@ -227,6 +241,15 @@ template <int NP> int launch_bpq(const KernelArgs &a, int dev, cudaStream_t st)
 	kern<<<dim3((unsigned)grid), dim3(BPQ_WARPS * 32), 0, st>>>(a);
 	QP_CUDA(cudaGetLastError());
 	return QP_OK;
+}
+
+template <int NP> int launch_bpq(const KernelArgs &a, int dev, cudaStream_t st)
+{
+	if constexpr (NP >= QPB_BPQ_PFI_FROM) {
+		if (a.z0 != nullptr)
+			return launch_bpq_form<NP, true>(a, dev, st);
+	}
+	return launch_bpq_form<NP, false>(a, dev, st);
 }
 
 // which kernel family solves this batch (QP_KERNEL_*), 0 = none

@@ -285,102 +285,147 @@ qp_bpq_kernel(const KernelArgs p)
 		int status = QP_STATUS_MAX_ITER;
 		unsigned it = 0;
 		bool active = valid && !bad && p.max_iter > 0; // uniform inside a group
-		float *ybuf = bc;
+		// x = R y for my four rows, y broadcast from shared memory (full-inverse variant)
+		auto publish_y = [&](float *yb) {
+			*reinterpret_cast<float4 *>(yb + 4 * g) =
+				make_float4(fmaf(rho, z[0] - u[0], -q[0]), fmaf(rho, z[1] - u[1], -q[1]),
+					    fmaf(rho, z[2] - u[2], -q[2]), fmaf(rho, z[3] - u[3], -q[3]));
+		};
+		auto matvec = [&](const float *yb, float (&xo)[4]) {
+			// four partial sums per row pair keep the FFMA2 chains short
+			float2 acc[2][4];
+#pragma unroll
+			for (int rp = 0; rp < 2; ++rp)
+				acc[rp][0] = acc[rp][1] = acc[rp][2] = acc[rp][3] = make_float2(0.0f, 0.0f);
+#pragma unroll
+			for (int j = 0; j < NP; j += 4) {
+				const float4 y = *reinterpret_cast<const float4 *>(yb + j);
+#pragma unroll
+				for (int rp = 0; rp < 2; ++rp) {
+					acc[rp][0] = fma2_bc(S[rp][j], y.x, acc[rp][0]);
+					acc[rp][1] = fma2_bc(S[rp][j + 1], y.y, acc[rp][1]);
+					acc[rp][2] = fma2_bc(S[rp][j + 2], y.z, acc[rp][2]);
+					acc[rp][3] = fma2_bc(S[rp][j + 3], y.w, acc[rp][3]);
+				}
+			}
+#pragma unroll
+			for (int rp = 0; rp < 2; ++rp) {
+				const float2 t = __fadd2_rn(__fadd2_rn(acc[rp][0], acc[rp][1]),
+							    __fadd2_rn(acc[rp][2], acc[rp][3]));
+				xo[2 * rp] = t.x, xo[2 * rp + 1] = t.y;
+			}
+		};
+		// element-wise part of one iteration with x = xr: admm_update_x_hat (:161-174),
+		// _z (:176-190), _u (:192-203) and the five partial sums of squares (:205-253)
+		auto elementwise = [&](const float (&xr)[4], float &rr, float &ss, float &nx, float &nz,
+				       float &nu) {
+			rr = ss = nx = nz = nu = 0.f;
+#pragma unroll
+			for (int s = 0; s < 4; ++s) {
+				const float xs = xr[s];
+				x[s] = xs;
+				const float xh = relax ? fmaf(alpha, xs, (1.0f - alpha) * z[s]) : xs;
+				const float zn = fminf(fmaxf(xh + u[s], lo[s]), hi[s]);
+				const float dz = zn - z[s];
+				ss = fmaf(dz, dz, ss);
+				u[s] += xh - zn;
+				const float dr = xs - zn;
+				rr = fmaf(dr, dr, rr);
+				nx = fmaf(xs, xs, nx);
+				nz = fmaf(zn, zn, nz);
+				nu = fmaf(u[s], u[s], nu);
+				z[s] = zn;
+			}
+		};
+		// stop test (:233-253, :308), squared form as in qp_tpq.cuh; lane 0 of the group
+		// decides for everybody
+		auto converged = [&](float rr, float ss, float nx, float nz, float nu, unsigned am) {
+			const float eps_pri = fmaf(p.reltol, sqrt_approx(fmaxf(nx, nz)), p.eps_abs);
+			const float eps_dual = fmaf(relrho, sqrt_approx(nu), p.eps_abs);
+			int conv = (rr < eps_pri * eps_pri) && (rho2 * ss < eps_dual * eps_dual);
+			if constexpr ((T & (T - 1)) != 0)
+				conv = __shfl_sync(am, conv, gbase);
+			return conv != 0;
+		};
+
+		if constexpr (PFI) {
 		for (;;) {
 			const unsigned am = __ballot_sync(FULL, active);
 			if (am == 0u)
 				break;
 			if (active) {
-				// admm_update_x (:146-159): y = rho (z - u) - q ; x = R y
+				// admm_update_x (:146-159): y = rho (z - u) - q ; x = R y with
+				// R = E_{NC-1} ... E_0: E_K maps the four pivot entries v_P (all in lane K
+				// of the group) to B^-1 v_P and adds H_K v_P to every other entry; H_K
+				// sits in chunk NC-1-K, and the pivot rows' H is B^-1 itself.
 				float xr[4];
-				if constexpr (PFI) {
-					// R = E_{NC-1} ... E_0: E_K maps the four pivot entries v_P (all in lane K
-					// of the group) to B^-1 v_P and adds H_K v_P to every other entry; H_K
-					// sits in chunk NC-1-K, and the pivot rows' H is B^-1 itself.
-					float2 v0 = make_float2(fmaf(rho, z[0] - u[0], -q[0]), fmaf(rho, z[1] - u[1], -q[1]));
-					float2 v1 = make_float2(fmaf(rho, z[2] - u[2], -q[2]), fmaf(rho, z[3] - u[3], -q[3]));
+				float2 v0 = make_float2(fmaf(rho, z[0] - u[0], -q[0]), fmaf(rho, z[1] - u[1], -q[1]));
+				float2 v1 = make_float2(fmaf(rho, z[2] - u[2], -q[2]), fmaf(rho, z[3] - u[3], -q[3]));
 #pragma unroll
-					for (int K = 0; K < NC; ++K) {
-						const int src = gbase + K;
-						const float p0 = __shfl_sync(am, v0.x, src), p1 = __shfl_sync(am, v0.y, src);
-						const float p2 = __shfl_sync(am, v1.x, src), p3 = __shfl_sync(am, v1.y, src);
-						const int c = 4 * (NC - 1 - K);
-						float2 a0 = (g == K) ? make_float2(0.f, 0.f) : v0;
-						float2 a1 = (g == K) ? make_float2(0.f, 0.f) : v1;
-						a0 = fma2_bc(S[0][c], p0, a0), a1 = fma2_bc(S[1][c], p0, a1);
-						a0 = fma2_bc(S[0][c + 1], p1, a0), a1 = fma2_bc(S[1][c + 1], p1, a1);
-						a0 = fma2_bc(S[0][c + 2], p2, a0), a1 = fma2_bc(S[1][c + 2], p2, a1);
-						a0 = fma2_bc(S[0][c + 3], p3, a0), a1 = fma2_bc(S[1][c + 3], p3, a1);
-						v0 = a0, v1 = a1;
-					}
-					xr[0] = v0.x, xr[1] = v0.y, xr[2] = v1.x, xr[3] = v1.y;
-				} else {
-				*reinterpret_cast<float4 *>(ybuf + 4 * g) =
-					make_float4(fmaf(rho, z[0] - u[0], -q[0]), fmaf(rho, z[1] - u[1], -q[1]),
-						    fmaf(rho, z[2] - u[2], -q[2]), fmaf(rho, z[3] - u[3], -q[3]));
-				__syncwarp(am);
-				// four partial sums per row pair keep the FFMA2 chains short
-				float2 acc[2][4];
-#pragma unroll
-				for (int rp = 0; rp < 2; ++rp)
-					acc[rp][0] = acc[rp][1] = acc[rp][2] = acc[rp][3] = make_float2(0.0f, 0.0f);
-#pragma unroll
-				for (int j = 0; j < NP; j += 4) {
-					const float4 y = *reinterpret_cast<const float4 *>(ybuf + j);
-#pragma unroll
-					for (int rp = 0; rp < 2; ++rp) {
-						acc[rp][0] = fma2_bc(S[rp][j], y.x, acc[rp][0]);
-						acc[rp][1] = fma2_bc(S[rp][j + 1], y.y, acc[rp][1]);
-						acc[rp][2] = fma2_bc(S[rp][j + 2], y.z, acc[rp][2]);
-						acc[rp][3] = fma2_bc(S[rp][j + 3], y.w, acc[rp][3]);
-					}
+				for (int K = 0; K < NC; ++K) {
+					const int src = gbase + K;
+					const float p0 = __shfl_sync(am, v0.x, src), p1 = __shfl_sync(am, v0.y, src);
+					const float p2 = __shfl_sync(am, v1.x, src), p3 = __shfl_sync(am, v1.y, src);
+					const int c = 4 * (NC - 1 - K);
+					float2 a0 = (g == K) ? make_float2(0.f, 0.f) : v0;
+					float2 a1 = (g == K) ? make_float2(0.f, 0.f) : v1;
+					a0 = fma2_bc(S[0][c], p0, a0), a1 = fma2_bc(S[1][c], p0, a1);
+					a0 = fma2_bc(S[0][c + 1], p1, a0), a1 = fma2_bc(S[1][c + 1], p1, a1);
+					a0 = fma2_bc(S[0][c + 2], p2, a0), a1 = fma2_bc(S[1][c + 2], p2, a1);
+					a0 = fma2_bc(S[0][c + 3], p3, a0), a1 = fma2_bc(S[1][c + 3], p3, a1);
+					v0 = a0, v1 = a1;
 				}
-				__syncwarp(am);
-#pragma unroll
-				for (int rp = 0; rp < 2; ++rp) {
-					const float2 t = __fadd2_rn(__fadd2_rn(acc[rp][0], acc[rp][1]),
-								    __fadd2_rn(acc[rp][2], acc[rp][3]));
-					xr[2 * rp] = t.x, xr[2 * rp + 1] = t.y;
-				}
-				}
-				float rr = 0.f, ss = 0.f, nx = 0.f, nz = 0.f, nu = 0.f;
-#pragma unroll
-				for (int s = 0; s < 4; ++s) {
-					const float xs = xr[s];
-					x[s] = xs;
-					// admm_update_x_hat (:161-174), _z (:176-190), _u (:192-203)
-					const float xh = relax ? fmaf(alpha, xs, (1.0f - alpha) * z[s]) : xs;
-					const float zn = fminf(fmaxf(xh + u[s], lo[s]), hi[s]);
-					const float dz = zn - z[s];
-					ss = fmaf(dz, dz, ss);
-					u[s] += xh - zn;
-					const float dr = xs - zn;
-					rr = fmaf(dr, dr, rr);
-					nx = fmaf(xs, xs, nx);
-					nz = fmaf(zn, zn, nz);
-					nu = fmaf(u[s], u[s], nu);
-					z[s] = zn;
-				}
-				rr = ring.sum(rr, am);
-				ss = ring.sum(ss, am);
-				nx = ring.sum(nx, am);
-				nz = ring.sum(nz, am);
-				nu = ring.sum(nu, am);
+				xr[0] = v0.x, xr[1] = v0.y, xr[2] = v1.x, xr[3] = v1.y;
+				float rr, ss, nx, nz, nu;
+				elementwise(xr, rr, ss, nx, nz, nu);
+				rr = ring.sum(rr, am), ss = ring.sum(ss, am), nx = ring.sum(nx, am);
+				nz = ring.sum(nz, am), nu = ring.sum(nu, am);
 				++it;
-				// stop test (:233-253, :308), squared form as in qp_tpq.cuh; lane 0 of the
-				// group decides for everybody
-				const float eps_pri = fmaf(p.reltol, sqrt_approx(fmaxf(nx, nz)), p.eps_abs);
-				const float eps_dual = fmaf(relrho, sqrt_approx(nu), p.eps_abs);
-				int conv = (rr < eps_pri * eps_pri) && (rho2 * ss < eps_dual * eps_dual);
-				if constexpr ((T & (T - 1)) != 0)
-					conv = __shfl_sync(am, conv, gbase);
-				if (conv) {
+				if (converged(rr, ss, nx, nz, nu, am)) {
 					status = QP_STATUS_CONVERGED;
 					active = false;
 				} else if (it >= p.max_iter) {
 					active = false;
 				}
 			}
+		}
+		} else {
+		// Full inverse.  The loop is software-pipelined: the mat-vec of the NEXT iteration is
+		// started before the five group reductions and the stop decision of this one are
+		// known (it only reads z, u, which the decision does not change), so the shuffle
+		// chains overlap the FMAs instead of heading a serial chain of ~300 cycles per
+		// iteration.  One mat-vec per problem is wasted (the one after convergence).
+		float xr[4] = { 0.f, 0.f, 0.f, 0.f };
+		{
+			const unsigned am = __ballot_sync(FULL, active);
+			if (active) {
+				publish_y(bc);
+				__syncwarp(am);
+				matvec(bc, xr);
+			}
+		}
+		for (;;) {
+			const unsigned am = __ballot_sync(FULL, active);
+			if (am == 0u)
+				break;
+			if (active) {
+				float rr, ss, nx, nz, nu;
+				elementwise(xr, rr, ss, nx, nz, nu);
+				++it;
+				float *yb = bc + (it & 1u) * C::BUF; // two buffers: no second barrier needed
+				publish_y(yb);
+				__syncwarp(am);
+				rr = ring.sum(rr, am), ss = ring.sum(ss, am), nx = ring.sum(nx, am);
+				nz = ring.sum(nz, am), nu = ring.sum(nu, am);
+				matvec(yb, xr);
+				if (converged(rr, ss, nx, nz, nu, am)) {
+					status = QP_STATUS_CONVERGED;
+					active = false;
+				} else if (it >= p.max_iter) {
+					active = false;
+				}
+			}
+		}
 		}
 		__syncwarp();
 

@@ -29,6 +29,8 @@ def main():
     ap.add_argument("--shapes", default="4,16,40,64")
     ap.add_argument("--beta", type=float, default=0.5)
     ap.add_argument("--cold", action="store_true", help="no warm start at n=64")
+    ap.add_argument("--mpc", action="store_true",
+                    help="n=40: condensed linear-MPC problems (BASELINE config 4; 4096 distinct, tiled)")
     ap.add_argument("--kernel", default="auto", choices=["auto", "tpq", "gpq", "bpq"])
     ap.add_argument("--counts", default="", help="override batch sizes, e.g. 24:262144,32:262144")
     args = ap.parse_args()
@@ -45,21 +47,30 @@ def main():
         counts[int(k)] = int(v)
     for n in [int(s) for s in args.shapes.split(",")]:
         count = counts[n]
-        P, q = make_batch(count, n, 2026, dev)
+        beta = args.beta
+        if args.mpc and n == 40:
+            from embedded_qp_solver_b200 import problems
+            Pm, qm, lbm, ubm = problems.mpc(4096, seed=2026)
+            reps = count // 4096
+            P = torch.from_numpy(Pm).to(dev).repeat(reps, 1, 1).contiguous()
+            q = torch.from_numpy(qm).to(dev).repeat(reps, 1).contiguous()
+            beta = float(ubm[0, 0])
+        else:
+            P, q = make_batch(count, n, 2026, dev)
         warm = n == 64 and not args.cold
         kw = {}
         if warm:
-            first = qp.solve_batch(P, q, -args.beta, args.beta, options=opts)
+            first = qp.solve_batch(P, q, -beta, beta, options=opts)
             q = q + 0.01 * torch.randn_like(q)
             kw = dict(z0=first["z"].clone(), u0=first["lam"].clone())
         out = None
         for _ in range(3):
-            out = qp.solve_batch(P, q, -args.beta, args.beta, out=out, options=opts, **kw)
+            out = qp.solve_batch(P, q, -beta, beta, out=out, options=opts, **kw)
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(args.steps):
-            qp.solve_batch(P, q, -args.beta, args.beta, out=out, options=opts, **kw)
+            qp.solve_batch(P, q, -beta, beta, out=out, options=opts, **kw)
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / args.steps
@@ -67,7 +78,7 @@ def main():
         bytes_per = qp.algorithmic_bytes(n, warm=warm, with_z=True, bound_arrays=False)
         flops_per = qp.algorithmic_flops(n, k)
         rate = count / (ms * 1e-3)
-        line = {"shape": f"n={n},m={2 * n}", "count": count, "kernel": qp.kernel_for(n) if args.kernel == "auto" else f"{args.kernel}<{n}>",
+        line = {"shape": f"n={n},m={2 * n}" + (" mpc" if args.mpc and n == 40 else ""), "count": count, "kernel": qp.kernel_for(n) if args.kernel == "auto" else f"{args.kernel}<{n}>",
                 "warm_start": warm, "qp_per_s": rate, "ms_per_step": ms, "mean_iters": k,
                 "not_converged": int((out["status"] != 0).sum()),
                 "hbm": {"achieved_gbs": bytes_per * rate / 1e9, "peak": hbm_peak,
