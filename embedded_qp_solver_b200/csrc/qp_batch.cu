@@ -183,8 +183,9 @@ template <int N> int launch_tpq_n(const KernelArgs &a, int dev, cudaStream_t st)
 // elimination but makes every iteration a chain of NC shuffle -> FMA steps.  Measured
 // (profiles/README.md): n = 64 warm start (1.1 iterations) +19 %, n = 40 cold start on
 // well-conditioned problems (10 iterations) +4 %, n = 40 condensed MPC (36 iterations) -13 %.
-// A warm start is the caller's statement that few iterations are expected: product form
-// with (z0, u0), full inverse without.
+// The break-even iteration count grows with n (elimination ~ n^3, iteration ~ n^2): at
+// n >= 48 the product form is used always; at n <= 40 a warm start is taken as the caller's
+// statement that few iterations are expected: product form with (z0, u0), full inverse without.
 template <int NP, bool PFI> int launch_gpq_form(const KernelArgs &a, int dev, cudaStream_t st)
 {
 	constexpr int T = GpqLanes<NP>::T; // lanes per QP; 32 / T problems per warp
@@ -206,11 +207,11 @@ template <int NP, bool PFI> int launch_gpq_form(const KernelArgs &a, int dev, cu
 
 template <int NP> int launch_gpq(const KernelArgs &a, int dev, cudaStream_t st)
 {
-	if constexpr (NP >= QPB_GPQ_PFI_FROM) {
-		if (a.z0 != nullptr)
-			return launch_gpq_form<NP, true>(a, dev, st);
-	}
-	return launch_gpq_form<NP, false>(a, dev, st);
+	// n >= 48: the elimination dominates up to ~20-30 iterations: always the product form
+	if constexpr (NP >= QPB_GPQ_PFI_FROM)
+		return launch_gpq_form<NP, true>(a, dev, st);
+	else
+		return launch_gpq_form<NP, false>(a, dev, st);
 }
 
 bool bpq_eligible(const KernelArgs &a)

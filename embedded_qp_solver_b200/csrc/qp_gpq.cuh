@@ -433,102 +433,155 @@ qp_gpq_kernel(const KernelArgs p)
 		int status = QP_STATUS_MAX_ITER;
 		unsigned it = 0;
 		bool active = valid && !bad && p.max_iter > 0; // uniform inside a group
-		float *ybuf = bc;
+		// element-wise part of one iteration with x = xr: admm_update_x_hat (:161-174),
+		// _z (:176-190), _u (:192-203) and the five partial sums of squares (:205-253)
+		auto elementwise = [&](const float (&xr)[RPL], float &rr, float &ss, float &nx, float &nz,
+				       float &nu) {
+			rr = ss = nx = nz = nu = 0.f;
+#pragma unroll
+			for (int s = 0; s < RPL; ++s) {
+				const float xs = xr[s];
+				x[s] = xs;
+				const float xh = relax ? fmaf(alpha, xs, (1.0f - alpha) * z[s]) : xs;
+				const float zn = fminf(fmaxf(xh + u[s], lo[s]), hi[s]);
+				const float dz = zn - z[s];
+				ss = fmaf(dz, dz, ss);
+				u[s] += xh - zn;
+				const float dr = xs - zn;
+				rr = fmaf(dr, dr, rr);
+				nx = fmaf(xs, xs, nx);
+				nz = fmaf(zn, zn, nz);
+				nu = fmaf(u[s], u[s], nu);
+				z[s] = zn;
+			}
+		};
+		auto reduce5 = [&](float &rr, float &ss, float &nx, float &nz, float &nu, unsigned am) {
+#pragma unroll
+			for (int o = T / 2; o > 0; o >>= 1) {
+				rr += __shfl_xor_sync(am, rr, o);
+				ss += __shfl_xor_sync(am, ss, o);
+				nx += __shfl_xor_sync(am, nx, o);
+				nz += __shfl_xor_sync(am, nz, o);
+				nu += __shfl_xor_sync(am, nu, o);
+			}
+		};
+		// stop test (:233-253, :308), squared form as in qp_tpq.cuh
+		auto converged = [&](float rr, float ss, float nx, float nz, float nu) {
+			const float eps_pri = fmaf(p.reltol, sqrt_approx(fmaxf(nx, nz)), p.eps_abs);
+			const float eps_dual = fmaf(relrho, sqrt_approx(nu), p.eps_abs);
+			return (rr < eps_pri * eps_pri) && (rho2 * ss < eps_dual * eps_dual);
+		};
+
+		if constexpr (PFI) {
 		for (;;) {
 			const unsigned am = __ballot_sync(FULL, active);
 			if (am == 0u)
 				break;
 			if (active) {
-				// admm_update_x (:146-159): y = rho (z - u) - q ; x = R y
+				// admm_update_x (:146-159): y = rho (z - u) - q ; x = R y.
+				// R is held in product form, R = E_{NC-1} ... E_0: apply the block eta
+				// transformations one after the other.  E_K maps the four pivot entries
+				// v_P to B^-1 v_P and adds H_K v_P to every other entry; H_K sits in chunk
+				// NC-1-K, and the pivot rows' H is B^-1 itself.
 				float xr[RPL];
-				if constexpr (PFI) {
-					// R is held in product form, R = E_{NC-1} ... E_0: apply the block eta
-					// transformations one after the other.  E_K maps the four pivot
-					// entries v_P to B^-1 v_P and adds H_K v_P to every other entry; H_K sits
-					// in chunk NC-1-K, and the pivot rows' H is B^-1 itself.
 #pragma unroll
-					for (int s = 0; s < RPL; ++s)
-						xr[s] = fmaf(rho, z[s] - u[s], -q[s]);
+				for (int s = 0; s < RPL; ++s)
+					xr[s] = fmaf(rho, z[s] - u[s], -q[s]);
 #pragma unroll
-					for (int K = 0; K < NC; ++K) {
-						const int slot = (4 * K) / T, lane0 = (4 * K) % T;
-						const int src = (lane & ~(T - 1)) + lane0;
-						const float p0 = __shfl_sync(am, xr[slot], src);
-						const float p1 = __shfl_sync(am, xr[slot], src + 1);
-						const float p2 = __shfl_sync(am, xr[slot], src + 2);
-						const float p3 = __shfl_sync(am, xr[slot], src + 3);
-						const bool mine = (g >= lane0) && (g < lane0 + 4);
-#pragma unroll
-						for (int s = 0; s < RPL; ++s) {
-							const float2 h01 = S[s][2 * (NC - 1 - K)], h23 = S[s][2 * (NC - 1 - K) + 1];
-							const float b = (s == slot && mine) ? 0.0f : xr[s];
-							xr[s] = fmaf(h01.x, p0, fmaf(h01.y, p1, fmaf(h23.x, p2, fmaf(h23.y, p3, b))));
-						}
-					}
-				} else {
+				for (int K = 0; K < NC; ++K) {
+					const int slot = (4 * K) / T, lane0 = (4 * K) % T;
+					const int src = (lane & ~(T - 1)) + lane0;
+					const float p0 = __shfl_sync(am, xr[slot], src);
+					const float p1 = __shfl_sync(am, xr[slot], src + 1);
+					const float p2 = __shfl_sync(am, xr[slot], src + 2);
+					const float p3 = __shfl_sync(am, xr[slot], src + 3);
+					const bool mine = (g >= lane0) && (g < lane0 + 4);
 #pragma unroll
 					for (int s = 0; s < RPL; ++s) {
-						const int r = g + T * s;
-						if (r < NP)
-							ybuf[r] = fmaf(rho, z[s] - u[s], -q[s]);
+						const float2 h01 = S[s][2 * (NC - 1 - K)], h23 = S[s][2 * (NC - 1 - K) + 1];
+						const float b = (s == slot && mine) ? 0.0f : xr[s];
+						xr[s] = fmaf(h01.x, p0, fmaf(h01.y, p1, fmaf(h23.x, p2, fmaf(h23.y, p3, b))));
 					}
-					__syncwarp(am);
-					float2 acc[RPL][2];
-#pragma unroll
-					for (int s = 0; s < RPL; ++s)
-						acc[s][0] = acc[s][1] = make_float2(0.0f, 0.0f);
-#pragma unroll
-					for (int j = 0; j < NP; j += 4) {
-						const float4 y = *reinterpret_cast<const float4 *>(ybuf + j);
-						const float2 ylo = make_float2(y.x, y.y), yhi = make_float2(y.z, y.w);
-#pragma unroll
-						for (int s = 0; s < RPL; ++s) {
-							acc[s][0] = __ffma2_rn(S[s][j / 2], ylo, acc[s][0]);
-							acc[s][1] = __ffma2_rn(S[s][j / 2 + 1], yhi, acc[s][1]);
-						}
-					}
-					__syncwarp(am);
-#pragma unroll
-					for (int s = 0; s < RPL; ++s)
-						xr[s] = (acc[s][0].x + acc[s][0].y) + (acc[s][1].x + acc[s][1].y);
 				}
-				float rr = 0.f, ss = 0.f, nx = 0.f, nz = 0.f, nu = 0.f;
-#pragma unroll
-				for (int s = 0; s < RPL; ++s) {
-					const float xs = xr[s];
-					x[s] = xs;
-					// admm_update_x_hat (:161-174), _z (:176-190), _u (:192-203)
-					const float xh = relax ? fmaf(alpha, xs, (1.0f - alpha) * z[s]) : xs;
-					const float zn = fminf(fmaxf(xh + u[s], lo[s]), hi[s]);
-					const float dz = zn - z[s];
-					ss = fmaf(dz, dz, ss);
-					u[s] += xh - zn;
-					const float dr = xs - zn;
-					rr = fmaf(dr, dr, rr);
-					nx = fmaf(xs, xs, nx);
-					nz = fmaf(zn, zn, nz);
-					nu = fmaf(u[s], u[s], nu);
-					z[s] = zn;
-				}
-#pragma unroll
-				for (int o = T / 2; o > 0; o >>= 1) {
-					rr += __shfl_xor_sync(am, rr, o);
-					ss += __shfl_xor_sync(am, ss, o);
-					nx += __shfl_xor_sync(am, nx, o);
-					nz += __shfl_xor_sync(am, nz, o);
-					nu += __shfl_xor_sync(am, nu, o);
-				}
+				float rr, ss, nx, nz, nu;
+				elementwise(xr, rr, ss, nx, nz, nu);
+				reduce5(rr, ss, nx, nz, nu, am);
 				++it;
-				// stop test (:233-253, :308), squared form as in qp_tpq.cuh
-				const float eps_pri = fmaf(p.reltol, sqrt_approx(fmaxf(nx, nz)), p.eps_abs);
-				const float eps_dual = fmaf(relrho, sqrt_approx(nu), p.eps_abs);
-				if ((rr < eps_pri * eps_pri) && (rho2 * ss < eps_dual * eps_dual)) {
+				if (converged(rr, ss, nx, nz, nu)) {
 					status = QP_STATUS_CONVERGED;
 					active = false;
 				} else if (it >= p.max_iter) {
 					active = false;
 				}
 			}
+		}
+		} else {
+		// Full inverse: x = R y is a register-resident mat-vec with y broadcast from shared
+		// memory.  The loop is software-pipelined: the mat-vec of the NEXT iteration is issued
+		// before the five reductions and the stop decision of this one are known (it reads
+		// only z and u), so the shuffle chains overlap the FMAs.  One mat-vec per problem is
+		// wasted (the one after convergence).  y alternates between two buffers, so one
+		// barrier per iteration is enough.
+		auto publish_y = [&](float *yb) {
+#pragma unroll
+			for (int s = 0; s < RPL; ++s) {
+				const int r = g + T * s;
+				if (r < NP)
+					yb[r] = fmaf(rho, z[s] - u[s], -q[s]);
+			}
+		};
+		auto matvec = [&](const float *yb, float (&xo)[RPL]) {
+			float2 acc[RPL][2];
+#pragma unroll
+			for (int s = 0; s < RPL; ++s)
+				acc[s][0] = acc[s][1] = make_float2(0.0f, 0.0f);
+#pragma unroll
+			for (int j = 0; j < NP; j += 4) {
+				const float4 y = *reinterpret_cast<const float4 *>(yb + j);
+				const float2 ylo = make_float2(y.x, y.y), yhi = make_float2(y.z, y.w);
+#pragma unroll
+				for (int s = 0; s < RPL; ++s) {
+					acc[s][0] = __ffma2_rn(S[s][j / 2], ylo, acc[s][0]);
+					acc[s][1] = __ffma2_rn(S[s][j / 2 + 1], yhi, acc[s][1]);
+				}
+			}
+#pragma unroll
+			for (int s = 0; s < RPL; ++s)
+				xo[s] = (acc[s][0].x + acc[s][0].y) + (acc[s][1].x + acc[s][1].y);
+		};
+		float xr[RPL];
+#pragma unroll
+		for (int s = 0; s < RPL; ++s)
+			xr[s] = 0.0f;
+		{
+			const unsigned am = __ballot_sync(FULL, active);
+			if (active) {
+				publish_y(bc);
+				__syncwarp(am);
+				matvec(bc, xr);
+			}
+		}
+		for (;;) {
+			const unsigned am = __ballot_sync(FULL, active);
+			if (am == 0u)
+				break;
+			if (active) {
+				float rr, ss, nx, nz, nu;
+				elementwise(xr, rr, ss, nx, nz, nu);
+				++it;
+				float *yb = bc + (it & 1u) * 4 * ROW;
+				publish_y(yb);
+				__syncwarp(am);
+				reduce5(rr, ss, nx, nz, nu, am);
+				matvec(yb, xr);
+				if (converged(rr, ss, nx, nz, nu)) {
+					status = QP_STATUS_CONVERGED;
+					active = false;
+				} else if (it >= p.max_iter) {
+					active = false;
+				}
+			}
+		}
 		}
 		__syncwarp();
 
