@@ -80,7 +80,7 @@ ABI_SYMBOLS = [
     "qp_device_count", "qp_kernel_for", "qp_probe_fp32_tflops", "qp_probe_hbm_gbs",
     "qp_newton_batch", "qp_newton_qf",
     "qp_problem_file_write", "qp_problem_file_count", "qp_problem_file_read",
-    "qp_solve_general_batch", "qp_host_path_packs",
+    "qp_solve_general_batch", "qp_host_path_packs", "qp_gradient_batch", "qp_gradient_qf",
 ]
 
 _lib = None
@@ -140,9 +140,12 @@ def load_library(path: Optional[str] = None):
                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_float,
                                     C.POINTER(qp_options)]
     lib.qp_newton_batch.restype = C.c_int
-    lib.qp_newton_qf.argtypes = [C.POINTER(qp_ref_quadratic_form), C.POINTER(C.c_double), C.c_uint,
-                                 C.POINTER(C.c_double), _ip, _ip]
-    lib.qp_newton_qf.restype = C.c_int
+    lib.qp_gradient_batch.argtypes = lib.qp_newton_batch.argtypes
+    lib.qp_gradient_batch.restype = C.c_int
+    for fn in (lib.qp_newton_qf, lib.qp_gradient_qf):
+        fn.argtypes = [C.POINTER(qp_ref_quadratic_form), C.POINTER(C.c_double), C.c_uint,
+                       C.POINTER(C.c_double), _ip, _ip]
+        fn.restype = C.c_int
     _dp = C.POINTER(C.c_double)
     lib.qp_problem_file_write.argtypes = [C.c_char_p, C.c_uint32, C.c_size_t, _dp, _dp, C.c_int]
     lib.qp_problem_file_write.restype = C.c_int
@@ -380,7 +383,14 @@ def solve_general_batch(P, q, A, l, u, z0=None, u0=None, options: Optional[Optio
     return out
 
 
-def newton_batch(P, q, x0=None, iterations: int = 10, r: float = 0.0, want_f: bool = False):
+def gradient_batch(P, q, x0=None, iterations: int = 10000, r: float = 0.0, want_f: bool = False):
+    """Batched ``gradient_descent_with_line_search`` (qp_solvers.c:65-101); same interface
+    as :func:`newton_batch`; ``iterations`` defaults to the reference's GRAD_ITERATIONS."""
+    return newton_batch(P, q, x0, iterations, r, want_f, _entry="qp_gradient_batch")
+
+
+def newton_batch(P, q, x0=None, iterations: int = 10, r: float = 0.0, want_f: bool = False,
+                 _entry: str = "qp_newton_batch"):
     """Batched ``newton_method_with_line_search`` (qp_solvers.c:103-144): returns a
     dict(x, status, steps[, f]).  Device tensors in, device tensors out; numpy in,
     numpy out.  ``iterations`` defaults to the reference's HESS_ITERATIONS."""
@@ -409,10 +419,10 @@ def newton_batch(P, q, x0=None, iterations: int = 10, r: float = 0.0, want_f: bo
         if want_f:
             out["f"] = np.empty(count, np.float32)
         addr = {k: v.ctypes.data for k, v in out.items()}
-    rc = lib.qp_newton_batch(C.byref(pb), ax0, int(iterations), addr["x"], addr["status"],
-                             addr["steps"], addr.get("f"), float(r), C.byref(copt))
+    rc = getattr(lib, _entry)(C.byref(pb), ax0, int(iterations), addr["x"], addr["status"],
+                              addr["steps"], addr.get("f"), float(r), C.byref(copt))
     if rc != QP_OK:
-        raise QpError(rc, "qp_newton_batch")
+        raise QpError(rc, _entry)
     return out
 
 
@@ -495,8 +505,16 @@ def admm(x0, iterations: int, qf: QuadraticForm, lb: float = -1e12, ub: float = 
     return x
 
 
+def gradient_descent_with_line_search(x0, iterations: int, qf: QuadraticForm,
+                                      info: Optional[dict] = None) -> np.ndarray:
+    """``struct _matrix *gradient_descent_with_line_search(x0, iterations, qf)``
+    (qp_solvers.c:65-101) on the GPU; x returned as an n x 1 float64 array."""
+    return newton_method_with_line_search(x0, iterations, qf, info, _entry="qp_gradient_qf")
+
+
 def newton_method_with_line_search(x0, iterations: int, qf: QuadraticForm,
-                                   info: Optional[dict] = None) -> np.ndarray:
+                                   info: Optional[dict] = None,
+                                   _entry: str = "qp_newton_qf") -> np.ndarray:
     """``struct _matrix *newton_method_with_line_search(x0, iterations, qf)``
     (qp_solvers.c:103-144) on the GPU; x returned as an n x 1 float64 array."""
     lib = load_library()
@@ -506,12 +524,12 @@ def newton_method_with_line_search(x0, iterations: int, qf: QuadraticForm,
     x0a = None
     if x0 is not None:
         x0a = np.ascontiguousarray(x0.array if isinstance(x0, Matrix) else x0, np.float64).reshape(-1)
-    rc = lib.qp_newton_qf(C.byref(qf.c),
-                          x0a.ctypes.data_as(C.POINTER(C.c_double)) if x0a is not None else None,
-                          int(iterations), x.ctypes.data_as(C.POINTER(C.c_double)),
-                          C.byref(st), C.byref(it))
+    rc = getattr(lib, _entry)(C.byref(qf.c),
+                              x0a.ctypes.data_as(C.POINTER(C.c_double)) if x0a is not None else None,
+                              int(iterations), x.ctypes.data_as(C.POINTER(C.c_double)),
+                              C.byref(st), C.byref(it))
     if rc != QP_OK:
-        raise QpError(rc, "qp_newton_qf")
+        raise QpError(rc, _entry)
     if info is not None:
         info["status"], info["steps"] = st.value, it.value
     return x

@@ -69,3 +69,26 @@ struct _matrix *newton_b200(struct _matrix *x0, unsigned iterations,
 	}
 	return x;
 }
+
+/*
+ * Drop-in for gradient_descent_with_line_search() (qp_solvers/qp_solvers.h:4-7,
+ * qp_solvers.c:65-101), same signature, same ownership of the result:
+ *
+ *     test_optimizer(qf, GRAD_ITERATIONS, x0, "gradient_b200", gradient_b200);
+ */
+struct _matrix *gradient_b200(struct _matrix *x0, unsigned iterations,
+			      struct _quadratic_form *qf)
+{
+	struct _matrix *x = matrix_alloc(Nx1);
+	if (!x)
+		return 0;
+	int rc = qp_gradient_qf((const struct qp_ref_quadratic_form *)qf,
+				x0 ? x0->elements : 0, iterations, x->elements, 0, 0);
+	if (rc != QP_OK) {
+		fprintf(stderr, "gradient_b200: qp_gradient_qf failed (%d) %s\n", rc,
+			qp_last_error());
+		matrix_free(x);
+		return 0;
+	}
+	return x;
+}

@@ -1139,9 +1139,9 @@ static int launch_newton(const NewtonArgs &a, int dev, cudaStream_t st)
 	return QP_OK;
 }
 
-extern "C" int qp_newton_batch(const qp_batch *pb, const float *x0, unsigned iterations, float *x,
-			       int32_t *status, int32_t *steps, float *f, float r,
-			       const qp_options *opt_in)
+static int descent_batch(int gradient, const qp_batch *pb, const float *x0, unsigned iterations,
+			 float *x, int32_t *status, int32_t *steps, float *f, float r,
+			 const qp_options *opt_in)
 {
 	if (!pb || !x || pb->n == 0)
 		return QP_ERR_INVALID;
@@ -1166,7 +1166,7 @@ extern "C" int qp_newton_batch(const qp_batch *pb, const float *x0, unsigned ite
 		return QP_ERR_NO_DEVICE;
 	const size_t n = pb->n, c = pb->count;
 	NewtonArgs a = {};
-	a.count = c, a.n = int(n), a.iterations = iterations, a.r = r;
+	a.count = c, a.n = int(n), a.iterations = iterations, a.r = r, a.gradient = gradient;
 	if (pb->mem == QP_MEM_DEVICE) {
 		a.P = pb->P, a.q = pb->q, a.x0 = x0, a.x = x, a.fval = f, a.status = status, a.steps = steps;
 		return launch_newton(a, dev, static_cast<cudaStream_t>(opt.stream));
@@ -1200,10 +1200,24 @@ extern "C" int qp_newton_batch(const qp_batch *pb, const float *x0, unsigned ite
 	if (rc != QP_OK)
 		return rc;
 	if (e != cudaSuccess) {
-		g_err = std::string("qp_newton_batch: ") + cudaGetErrorString(e);
+		g_err = std::string(gradient ? "qp_gradient_batch: " : "qp_newton_batch: ") + cudaGetErrorString(e);
 		return QP_ERR_CUDA;
 	}
 	return QP_OK;
+}
+
+extern "C" int qp_newton_batch(const qp_batch *pb, const float *x0, unsigned iterations, float *x,
+			       int32_t *status, int32_t *steps, float *f, float r,
+			       const qp_options *opt)
+{
+	return descent_batch(0, pb, x0, iterations, x, status, steps, f, r, opt);
+}
+
+extern "C" int qp_gradient_batch(const qp_batch *pb, const float *x0, unsigned iterations, float *x,
+				 int32_t *status, int32_t *steps, float *f, float r,
+				 const qp_options *opt)
+{
+	return descent_batch(1, pb, x0, iterations, x, status, steps, f, r, opt);
 }
 
 // ----------------------------------------------------------------------------------------
@@ -1409,8 +1423,8 @@ extern "C" int qp_admm_qf(const struct qp_ref_quadratic_form *qf, unsigned itera
 	return qp_admm_qf_batch(one, 1, iterations, lb, ub, xo, status, iters, nullptr);
 }
 
-extern "C" int qp_newton_qf(const struct qp_ref_quadratic_form *qf, const double *x0,
-			    unsigned iterations, double *x_out, int32_t *status, int32_t *steps)
+static int descent_qf(int gradient, const struct qp_ref_quadratic_form *qf, const double *x0,
+		      unsigned iterations, double *x_out, int32_t *status, int32_t *steps)
 {
 	if (!qf || !qf->p || !qf->q || !qf->p->elements || !qf->q->elements || !x_out)
 		return QP_ERR_INVALID;
@@ -1430,13 +1444,25 @@ extern "C" int qp_newton_qf(const struct qp_ref_quadratic_form *qf, const double
 	qp_batch pb;
 	std::memset(&pb, 0, sizeof(pb));
 	pb.n = n, pb.mem = QP_MEM_HOST, pb.count = 1, pb.P = P.data(), pb.q = q.data();
-	const int rc = qp_newton_batch(&pb, x0f.data(), iterations, x.data(), status, steps, nullptr,
-				       0.0f, nullptr);
+	const int rc = descent_batch(gradient, &pb, x0f.data(), iterations, x.data(), status, steps,
+				     nullptr, 0.0f, nullptr);
 	if (rc != QP_OK)
 		return rc;
 	for (size_t k = 0; k < n; ++k)
 		x_out[k] = double(x[k]);
 	return QP_OK;
+}
+
+extern "C" int qp_newton_qf(const struct qp_ref_quadratic_form *qf, const double *x0,
+			    unsigned iterations, double *x_out, int32_t *status, int32_t *steps)
+{
+	return descent_qf(0, qf, x0, iterations, x_out, status, steps);
+}
+
+extern "C" int qp_gradient_qf(const struct qp_ref_quadratic_form *qf, const double *x0,
+			      unsigned iterations, double *x_out, int32_t *status, int32_t *steps)
+{
+	return descent_qf(1, qf, x0, iterations, x_out, status, steps);
 }
 
 extern "C" const char *qp_kernel_for(uint32_t n, int al16)

@@ -1,6 +1,8 @@
-// qp_newton.cuh -- batched unconstrained minimiser: the reference's
-// newton_method_with_line_search() (/root/reference/qp_solvers/qp_solvers.c:103-144) with
-// its line_search() (:37-63) and armijo() (:21-35), one warp per problem, any n <= 64.
+// qp_newton.cuh -- batched unconstrained minimisers: the reference's
+// newton_method_with_line_search() (/root/reference/qp_solvers/qp_solvers.c:103-144) and
+// gradient_descent_with_line_search() (:65-101, the same loop with d = -grad and no
+// inverse) with their line_search() (:37-63) and armijo() (:21-35), one warp per problem,
+// any n <= 64.
 //
 // This is the cross-check path of SURVEY.md 8(f) rank 2 (with the box inactive the ADMM
 // answer is the Newton answer), not the headline kernel: P and its inverse live in shared
@@ -40,6 +42,7 @@ struct NewtonArgs {
 	int n;
 	unsigned iterations;
 	float r; // constant term of the objective, for fval only
+	int gradient; // 1: gradient_descent_with_line_search (qp_solvers.c:65-101): d = -g, no inverse
 };
 
 __host__ __device__ inline int newton_ld(int n)
@@ -79,8 +82,8 @@ __global__ void __launch_bounds__(NEWTON_WARPS * 32) qp_newton_kernel(const Newt
 		float x1 = (h1 && a.x0) ? __ldg(a.x0 + vo + i1) : 0.f;
 		__syncwarp();
 
-		// ---- W <- P^-1 -----------------------------------------------------------------------
-		const bool bad = smem_gauss_jordan(W, n, ld, vg, lane);
+		// ---- W <- P^-1 (Newton only) ---------------------------------------------------------
+		const bool bad = a.gradient ? false : smem_gauss_jordan(W, n, ld, vg, lane);
 
 		// ---- Newton steps ---------------------------------------------------------------------
 		auto matvec = [&](const float *M, const float *v, float &o0, float &o1) {
@@ -113,9 +116,10 @@ __global__ void __launch_bounds__(NEWTON_WARPS * 32) qp_newton_kernel(const Newt
 				if (h0) vg[i0] = g0;
 				if (h1) vg[i1] = g1;
 				__syncwarp();
-				float d0, d1;
-				matvec(W, vg, d0, d1);
-				d0 = -d0, d1 = -d1; // :129-132
+				float d0 = g0, d1 = g1; // gradient descent: d = -grad (:87-90)
+				if (!a.gradient)
+					matvec(W, vg, d0, d1); // Newton: d = -hessian_inv grad (:129-132)
+				d0 = -d0, d1 = -d1;
 				if (h0) vd[i0] = d0;
 				if (h1) vd[i1] = d1;
 				__syncwarp();

@@ -173,6 +173,17 @@ int qp_newton_batch(const qp_batch *prob, const float *x0, unsigned iterations,
 		    const qp_options *opt);
 
 /*
+ * The reference's third solver, same arguments and outputs:
+ *     x = gradient_descent_with_line_search(x0, iterations, qf)
+ *                                         qp_solvers/qp_solvers.c:65-101
+ * (main.c:42-44): d = -(P x + q), the same line search, the same stop test;
+ * no matrix is inverted, so status 2 does not occur.
+ */
+int qp_gradient_batch(const qp_batch *prob, const float *x0, unsigned iterations,
+		      float *x, int32_t *status, int32_t *steps, float *f, float r,
+		      const qp_options *opt);
+
+/*
  * General inequality rows  l <= A x <= u  (SURVEY.md 8(f) rank 3).  The reference has only
  * the box; this entry point runs the SAME scaled-form ADMM (qp_solvers.c:255-319) for the
  * splitting A x = z:  (P + rho A'A) x = rho A'(z - u) - q;  z = clip(alpha A x + (1-alpha) z
@@ -244,6 +255,9 @@ int qp_admm_qf_batch(const struct qp_ref_quadratic_form *const *qfs,
 int qp_newton_qf(const struct qp_ref_quadratic_form *qf, const double *x0,
 		 unsigned iterations, double *x_out, int32_t *status,
 		 int32_t *steps);
+int qp_gradient_qf(const struct qp_ref_quadratic_form *qf, const double *x0,
+		   unsigned iterations, double *x_out, int32_t *status,
+		   int32_t *steps);
 
 /*
  * The reference's problem file: [double n][P, n*n doubles row-major][q, n doubles],

@@ -72,9 +72,10 @@ class Oracle:
             f = getattr(self.lib, f"qp_oracle_eval_{suf}")
             f.restype = ct
             f.argtypes = [p, p, ct, p, C.c_uint]
-            f = getattr(self.lib, f"qp_oracle_newton_{suf}")
-            f.restype = C.c_int
-            f.argtypes = [C.c_uint, p, p, p, C.c_uint, p]
+            for name in ("newton", "gradient"):
+                f = getattr(self.lib, f"qp_oracle_{name}_{suf}")
+                f.restype = C.c_int
+                f.argtypes = [C.c_uint, p, p, p, C.c_uint, p]
         f = self.lib.qp_oracle_admm_timed_f64
         f.restype = C.c_double
         f.argtypes = [C.c_uint, C.c_ulong] + [C.POINTER(C.c_double)] * 4 + \
@@ -142,6 +143,17 @@ class Oracle:
             P.shape[0], _ptr(P, ct), _ptr(q, ct), _ptr(x0, ct), int(max_iter), _ptr(x, ct))
         return x, steps
 
+    def gradient(self, P, q, x0, max_iter=10000, dtype=np.float64):
+        """gradient_descent_with_line_search (qp_solvers.c:65-101); returns (x, steps)."""
+        suf, ct = self._suf(dtype)
+        P = np.ascontiguousarray(P, dtype=dtype)
+        q = np.ascontiguousarray(q, dtype=dtype)
+        x0 = np.ascontiguousarray(x0, dtype=dtype)
+        x = np.zeros_like(q)
+        steps = getattr(self.lib, f"qp_oracle_gradient_{suf}")(
+            P.shape[0], _ptr(P, ct), _ptr(q, ct), _ptr(x0, ct), int(max_iter), _ptr(x, ct))
+        return x, steps
+
     def admm_timed(self, P, q, lb, ub, max_iter=REF_MAX_ITER):
         """Seconds for solving the packed f64 batch with the port; x returned."""
         P = np.ascontiguousarray(P, dtype=np.float64)
@@ -183,6 +195,8 @@ class Reference:
         self.lib.qpref_admm_many.argtypes = [d, d, d, d, C.c_ulong, C.c_uint, d]
         self.lib.qpref_newton.restype = C.c_int
         self.lib.qpref_newton.argtypes = [d, d, d, C.c_uint, d]
+        self.lib.qpref_gradient.restype = C.c_int
+        self.lib.qpref_gradient.argtypes = [d, d, d, C.c_uint, d]
         self.lib.qpref_eval.restype = C.c_double
         self.lib.qpref_eval.argtypes = [d, d, C.c_double, d]
         self.lib.qpref_invert.restype = C.c_int
@@ -214,6 +228,16 @@ class Reference:
         x0 = np.ascontiguousarray(x0, dtype=np.float64)
         x = np.zeros(self.n)
         rc = self.lib.qpref_newton(_ptr(P, d), _ptr(q, d), _ptr(x0, d), int(max_iter), _ptr(x, d))
+        assert rc == 0
+        return x
+
+    def gradient(self, P, q, x0, max_iter=10000):
+        d = C.c_double
+        P = np.ascontiguousarray(P, dtype=np.float64)
+        q = np.ascontiguousarray(q, dtype=np.float64)
+        x0 = np.ascontiguousarray(x0, dtype=np.float64)
+        x = np.zeros(self.n)
+        rc = self.lib.qpref_gradient(_ptr(P, d), _ptr(q, d), _ptr(x0, d), int(max_iter), _ptr(x, d))
         assert rc == 0
         return x
 

@@ -19,6 +19,8 @@ struct _matrix *admm_b200(struct _matrix *x0, unsigned iterations,
 
 struct _matrix *newton_b200(struct _matrix *x0, unsigned iterations,
 			    struct _quadratic_form *qf);
+struct _matrix *gradient_b200(struct _matrix *x0, unsigned iterations,
+			      struct _quadratic_form *qf);
 
 static int ready = 0;
 
@@ -144,4 +146,47 @@ int compat_write_reference_file(unsigned seed, double *P_out, double *q_out)
 	matrix_free(q);
 	matrix_free(p);
 	return 0;
+}
+
+/* and for gradient descent (main.c:42-44) */
+int compat_run_gradient(unsigned seed, double *x_ref, double *x_gpu, double *f_out)
+{
+	if (!ready) {
+		kmalloc_init();
+		ready = 1;
+	}
+	srand(seed);
+	struct _matrix *p = matrix_alloc(NxN);
+	struct _matrix *q = matrix_alloc(Nx1);
+	struct _matrix *x0 = matrix_alloc(Nx1);
+	struct _quadratic_form *qf = quadratic_form_alloc(p, q, 0);
+	if (!p || !q || !x0 || !qf)
+		return -1;
+	matirx_random_pos_def(p, P_RAND_ENTRY_MIN, P_RAND_ENTRY_MAX);
+	matrix_random(q, Q_RAND_ENTRY_MIN, Q_RAND_ENTRY_MAX);
+	matrix_random(x0, X_RAND_ENTRY_MIN, X_RAND_ENTRY_MAX);
+
+	test_optimizer(qf, GRAD_ITERATIONS, x0, "gradient", gradient_descent_with_line_search);
+	test_optimizer(qf, GRAD_ITERATIONS, x0, "gradient_b200", gradient_b200);
+
+	struct _matrix *a = gradient_descent_with_line_search(x0, GRAD_ITERATIONS, qf);
+	struct _matrix *b = gradient_b200(x0, GRAD_ITERATIONS, qf);
+	int rc = 0;
+	if (!a || !b) {
+		rc = -2;
+	} else {
+		memcpy(x_ref, a->elements, sizeof(double) * N_DIM);
+		memcpy(x_gpu, b->elements, sizeof(double) * N_DIM);
+		f_out[0] = quadratic_form_eval(qf, a);
+		f_out[1] = quadratic_form_eval(qf, b);
+	}
+	if (a)
+		matrix_free(a);
+	if (b)
+		matrix_free(b);
+	quadratic_form_free(qf);
+	matrix_free(x0);
+	matrix_free(q);
+	matrix_free(p);
+	return rc;
 }

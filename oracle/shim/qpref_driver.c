@@ -9,6 +9,7 @@
  * Reference entry points exercised (paths relative to /root/reference):
  *   admm                            qp_solvers/qp_solvers.c:255-319
  *   newton_method_with_line_search  qp_solvers/qp_solvers.c:103-144
+ *   gradient_descent_with_line_search  qp_solvers/qp_solvers.c:65-101
  *   quadratic_form_eval             qp_solvers/qp.c:9-27
  *   matrix_invert                   matrix/matrix_ops/matrix_ops.c:551-630
  *   inversion_test/scalar_prod_test test/test.c:37-87
@@ -136,6 +137,31 @@ int qpref_newton(const double *P, const double *q, const double *x0_in,
 	memcpy(x0->elements, x0_in, sizeof(double) * N_DIM);
 
 	struct _matrix *x = newton_method_with_line_search(x0, iterations, qf);
+	memcpy(x_out, x->elements, sizeof(double) * N_DIM);
+
+	matrix_free(x);
+	quadratic_form_free(qf);
+	matrix_free(x0);
+	matrix_free(qv);
+	matrix_free(p);
+	return 0;
+}
+
+int qpref_gradient(const double *P, const double *q, const double *x0_in,
+		   unsigned iterations, double *x_out)
+{
+	qpref_init();
+	struct _matrix *p = matrix_alloc(NxN);
+	struct _matrix *qv = matrix_alloc(Nx1);
+	struct _matrix *x0 = matrix_alloc(Nx1);
+	if (!p || !qv || !x0)
+		return -1;
+	struct _quadratic_form *qf = quadratic_form_alloc(p, qv, 0);
+	memcpy(p->elements, P, sizeof(double) * N_DIM * N_DIM);
+	memcpy(qv->elements, q, sizeof(double) * N_DIM);
+	memcpy(x0->elements, x0_in, sizeof(double) * N_DIM);
+
+	struct _matrix *x = gradient_descent_with_line_search(x0, iterations, qf);
 	memcpy(x_out, x->elements, sizeof(double) * N_DIM);
 
 	matrix_free(x);

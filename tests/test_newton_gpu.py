@@ -110,3 +110,36 @@ def test_newton_status_and_api_misuse(qp):
     assert np.array_equal(r0["x"], x0) and np.all(np.delete(r0["status"], 2) == 1)
     with pytest.raises(qp.QpError):
         qp.newton_batch(np.zeros((1, 65, 65), np.float32), np.zeros((1, 65), np.float32))
+
+
+@pytest.mark.parametrize("n", [4, 16, 40, 64])
+def test_gradient_descent_against_oracle(qp, orc, n):
+    """qp_gradient_batch vs the oracle's restatement of gradient_descent_with_line_search
+    (qp_solvers.c:65-101; bit-identical to the unmodified reference,
+    tests/test_oracle_vs_ref.py).  Every step takes a discrete decision (how often alpha is
+    shrunk), so binary32 and binary64 follow the same path only while no decision is a near
+    tie: the bar is the same step count on most problems, x within 1e-3 there, and the
+    reference's own stop criterion ||P x + q|| < 0.1 everywhere."""
+    count = 48 if n <= 16 else 16
+    P, q, _, _ = problems.wellcond(count, n, seed=1400 + n)
+    rng = np.random.default_rng(n)
+    x0 = rng.uniform(-10, 10, (count, n)).astype(np.float32)
+    xs, ss = [], []
+    for c in range(count):
+        x, s = orc.gradient(P[c].astype(np.float64), q[c].astype(np.float64),
+                            x0[c].astype(np.float64), max_iter=10000)
+        xs.append(x), ss.append(s)
+    xo, so = np.array(xs), np.array(ss)
+    r = qp.gradient_batch(torch.from_numpy(P).cuda(), torch.from_numpy(q).cuda(),
+                          torch.from_numpy(x0).cuda(), iterations=10000)
+    torch.cuda.synchronize()
+    x, steps, st = r["x"].cpu().numpy(), r["steps"].cpu().numpy(), r["status"].cpu().numpy()
+    assert np.all(st == 0)
+    same = steps == so
+    assert same.mean() >= 0.7 and np.max(np.abs(steps - so)) <= 2
+    assert rel_err(x[same].astype(np.float64), xo[same]).max() <= 1e-3
+    g = np.einsum("cij,cj->ci", P.astype(np.float64), x.astype(np.float64)) + q
+    assert np.linalg.norm(g, axis=1).max() < 0.1 * (1 + 1e-3)
+    # the cap is honoured and reported
+    capped = qp.gradient_batch(P, q, x0, iterations=3)
+    assert np.all(capped["steps"] == 3) and np.all(capped["status"] == 1)

@@ -61,3 +61,19 @@ def test_reference_invert_and_eval_match_restatement(orc):
     q = rng.standard_normal(n)
     x = rng.standard_normal(n)
     assert ref.eval(A, q, 0.5, x) == orc.eval(A, q, 0.5, x)
+
+
+@pytest.mark.parametrize("n", [4, 16, 40])
+def test_gradient_restatement_is_bit_identical_to_the_reference(orc, n):
+    """gradient_descent_with_line_search (qp_solvers.c:65-101) of the unmodified reference
+    vs the plain-C restatement, started where the reference's tests start it (random x0)."""
+    import oracle
+    from embedded_qp_solver_b200 import problems
+    ref = oracle.Reference(n)
+    P, q, _, _ = problems.wellcond(5, n, seed=9)
+    rng = np.random.default_rng(n)
+    for c in range(5):
+        x0 = rng.uniform(-10, 10, n)
+        xr = ref.gradient(P[c].astype(np.float64), q[c].astype(np.float64), x0, 10000)
+        xo, steps = orc.gradient(P[c].astype(np.float64), q[c].astype(np.float64), x0, 10000)
+        assert np.array_equal(xr, xo) and 0 < steps < 10000
