@@ -14,8 +14,14 @@
  *     qp_solvers/qp_solvers.h:14-16            qp_admm_qf_batch()
  *     qp_solvers/qp_solvers.c:255-319
  *   quadratic_form_eval()  qp.h:20-21        qp_eval_batch()
+ *   newton_method_with_line_search()         qp_newton_batch(), qp_newton_qf()
+ *     qp_solvers/qp_solvers.h:9-12
+ *   gradient_descent_with_line_search()      qp_gradient_batch(), qp_gradient_qf()
+ *     qp_solvers/qp_solvers.h:4-7
+ *   test_reference() file, test/test.c:108   qp_problem_file_write/count/read()
  *   kmalloc_init()/static pools              qp_workspace_create()/destroy()
  *     kmalloc/kmalloc.h:16-18
+ *   (no counterpart: rows l <= A x <= u)     qp_solve_general_batch()
  *
  * Plain C: pointers and sizes only.  All arrays are caller-owned; the library
  * never allocates or frees memory that the caller sees.  Element order of
