@@ -136,12 +136,12 @@ bool tpq_eligible(const KernelArgs &a)
 	return true;
 }
 
-template <int N, bool B, bool W, bool R>
+template <int N, bool B, bool W, bool R, bool PK>
 int launch_tpq(const KernelArgs &a, int dev, cudaStream_t st)
 {
 	using L = TpqLayout<N, B, W>;
 	using Cfg = TpqCfg<N, B, W>;
-	auto kern = qp_tpq_kernel<N, B, W, R>;
+	auto kern = qp_tpq_kernel<N, B, W, R, PK>;
 	static bool attr_done[64] = {};
 	if (!attr_done[dev]) {
 		QP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -158,34 +158,37 @@ int launch_tpq(const KernelArgs &a, int dev, cudaStream_t st)
 	return QP_OK;
 }
 
-template <int N> int launch_tpq_n(const KernelArgs &a, int dev, cudaStream_t st)
+template <int N, bool PK> int launch_tpq_v(const KernelArgs &a, int dev, cudaStream_t st)
 {
 	const bool b = a.lb != nullptr, w = a.z0 != nullptr;
 	if (a.alpha != 1.0f) { // over-relaxation: separate instantiation, not a branch in the loop
 		if (b && w)
-			return launch_tpq<N, true, true, true>(a, dev, st);
+			return launch_tpq<N, true, true, true, PK>(a, dev, st);
 		if (b)
-			return launch_tpq<N, true, false, true>(a, dev, st);
+			return launch_tpq<N, true, false, true, PK>(a, dev, st);
 		if (w)
-			return launch_tpq<N, false, true, true>(a, dev, st);
-		return launch_tpq<N, false, false, true>(a, dev, st);
+			return launch_tpq<N, false, true, true, PK>(a, dev, st);
+		return launch_tpq<N, false, false, true, PK>(a, dev, st);
 	}
 	if (b && w)
-		return launch_tpq<N, true, true, false>(a, dev, st);
+		return launch_tpq<N, true, true, false, PK>(a, dev, st);
 	if (b)
-		return launch_tpq<N, true, false, false>(a, dev, st);
+		return launch_tpq<N, true, false, false, PK>(a, dev, st);
 	if (w)
-		return launch_tpq<N, false, true, false>(a, dev, st);
-	return launch_tpq<N, false, false, false>(a, dev, st);
+		return launch_tpq<N, false, true, false, PK>(a, dev, st);
+	return launch_tpq<N, false, false, false, PK>(a, dev, st);
 }
 
-// Product form or full inverse (qp_gpq.cuh, qp_bpq.cuh)?  The product form halves the
-// elimination but makes every iteration a chain of NC shuffle -> FMA steps.  Measured
-// (profiles/README.md): n = 64 warm start (1.1 iterations) +19 %, n = 40 cold start on
-// well-conditioned problems (10 iterations) +4 %, n = 40 condensed MPC (36 iterations) -13 %.
-// The break-even iteration count grows with n (elimination ~ n^3, iteration ~ n^2): at
-// n >= 48 the product form is used always; at n <= 40 a warm start is taken as the caller's
-// statement that few iterations are expected: product form with (z0, u0), full inverse without.
+// packed upper triangles arrive only from the host path, for n = 8, 12, 16
+template <int N> int launch_tpq_n(const KernelArgs &a, int dev, cudaStream_t st)
+{
+	if constexpr (N >= 8) {
+		if (a.p_packed)
+			return launch_tpq_v<N, true>(a, dev, st);
+	}
+	return launch_tpq_v<N, false>(a, dev, st);
+}
+
 template <int NP, bool PFI> int launch_gpq_form(const KernelArgs &a, int dev, cudaStream_t st)
 {
 	constexpr int T = GpqLanes<NP>::T; // lanes per QP; 32 / T problems per warp

@@ -126,7 +126,7 @@ __device__ __forceinline__ void ldlt_solve(const float (&a)[N * (N + 1) / 2], fl
 
 // ---- the kernel -----------------------------------------------------------------
 
-template <int N, bool BOUNDS, bool WARM, bool RELAX>
+template <int N, bool BOUNDS, bool WARM, bool RELAX, bool PACKED_IN>
 __global__ void
 __launch_bounds__(TpqCfg<N, BOUNDS, WARM>::WARPS * 32, TpqCfg<N, BOUNDS, WARM>::MINB)
 qp_tpq_kernel(const KernelArgs p)
@@ -174,9 +174,9 @@ qp_tpq_kernel(const KernelArgs p)
 		float *st = ring + s * L::STAGE;
 		if (lane == 0)
 			mbar_expect_tx(&full_bar[s],
-				       uint32_t(cnt) * ((p.p_packed ? L::PK : N * N) + L::NVEC_STAGE * N) * 4u);
+				       uint32_t(cnt) * ((PACKED_IN ? L::PK : N * N) + L::NVEC_STAGE * N) * 4u);
 		__syncwarp();
-		if (p.p_packed) {
+		if (PACKED_IN) {
 			if (L::PKSLOT != L::PK) {
 				if (lane < cnt)
 					bulk_g2s(st + lane * L::PKSLOT, p.P + (first + lane) * L::PK,
@@ -248,7 +248,7 @@ qp_tpq_kernel(const KernelArgs p)
 		{
 			const float *st = ring + s * L::STAGE;
 			const float4 *slot4 = reinterpret_cast<const float4 *>(st + lane * L::PSLOT);
-			if (p.p_packed) {
+			if (PACKED_IN) {
 				// the record is the upper triangle in the order a[] keeps it
 				const float4 *pk4 = reinterpret_cast<const float4 *>(st + lane * L::PKSLOT);
 #pragma unroll
