@@ -39,7 +39,11 @@ namespace qpb {
 // 227 KB of shared memory are both filled
 template <int N, bool BOUNDS, bool WARM> struct TpqCfg;
 template <bool B, bool W> struct TpqCfg<16, B, W> {
+#ifdef QPB_TPQ16_W12
+	static constexpr int WARPS = 12, STAGES = 3, MINB = 1;
+#else
 	static constexpr int WARPS = 8, STAGES = (B ? 3 : 4), MINB = 1;
+#endif
 };
 template <bool B, bool W> struct TpqCfg<12, B, W> { static constexpr int WARPS = 12, STAGES = 3, MINB = 1; };
 template <bool B, bool W> struct TpqCfg<8, B, W>  { static constexpr int WARPS = 8, STAGES = 4, MINB = 2; };
