@@ -40,7 +40,7 @@ namespace qpb {
 template <int N, bool BOUNDS, bool WARM> struct TpqCfg;
 template <bool B, bool W> struct TpqCfg<16, B, W> {
 #ifdef QPB_TPQ16_W12
-	static constexpr int WARPS = 12, STAGES = 3, MINB = 1;
+	static constexpr int WARPS = (B ? 8 : 12), STAGES = 3, MINB = 1;
 #else
 	static constexpr int WARPS = 8, STAGES = (B ? 3 : 4), MINB = 1;
 #endif
