@@ -87,3 +87,40 @@ def test_missing_library_fails_loudly(qp, tmp_path):
     from embedded_qp_solver_b200 import api
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         api.load_library(str(tmp_path / "nope.so"))
+
+
+def test_header_is_plain_c99_and_matches_the_ctypes_mirror(qp, tmp_path):
+    """include/qp_batch.h compiled as C99 by gcc (a C host binds it directly): struct sizes
+    and field offsets the compiler sees are the ones the ctypes mirror uses."""
+    import shutil
+    import subprocess
+    from embedded_qp_solver_b200 import api
+    if not shutil.which("gcc"):
+        pytest.skip("no gcc")
+    src = tmp_path / "probe.c"
+    src.write_text("""
+#include <stdio.h>
+#include <stddef.h>
+#include "qp_batch.h"
+int main(void) {
+    printf("%zu %zu %zu %zu %zu %zu %zu\\n", sizeof(qp_batch), sizeof(qp_batch_solution),
+           sizeof(qp_options), sizeof(qp_general_batch), sizeof(qp_general_solution),
+           sizeof(struct qp_ref_matrix), sizeof(struct qp_ref_quadratic_form));
+    printf("%zu %zu %zu %zu %zu\\n", offsetof(qp_batch, count), offsetof(qp_batch, z0),
+           offsetof(qp_options, stream), offsetof(qp_options, kernel), offsetof(qp_general_batch, A));
+    return 0;
+}
+""")
+    exe = tmp_path / "probe"
+    inc = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include")
+    subprocess.run(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-I", inc, "-o", str(exe),
+                    str(src)], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()
+    sizes = [int(v) for v in out[:7]]
+    assert sizes == [C.sizeof(api.qp_batch), C.sizeof(api.qp_batch_solution),
+                     C.sizeof(api.qp_options), C.sizeof(api.qp_general_batch),
+                     C.sizeof(api.qp_general_solution), C.sizeof(api.qp_ref_matrix),
+                     C.sizeof(api.qp_ref_quadratic_form)]
+    offs = [int(v) for v in out[7:]]
+    assert offs == [api.qp_batch.count.offset, api.qp_batch.z0.offset, api.qp_options.stream.offset,
+                    api.qp_options.kernel.offset, api.qp_general_batch.A.offset]
