@@ -36,7 +36,7 @@ class qp_batch(C.Structure):
     _fields_ = [("n", C.c_uint32), ("mem", C.c_uint32), ("count", C.c_size_t),
                 ("P", C.c_void_p), ("q", C.c_void_p), ("lb", C.c_void_p), ("ub", C.c_void_p),
                 ("lb_scalar", C.c_float), ("ub_scalar", C.c_float),
-                ("z0", C.c_void_p), ("u0", C.c_void_p)]
+                ("z0", C.c_void_p), ("u0", C.c_void_p), ("rho", C.c_void_p)]
 
 
 class qp_batch_solution(C.Structure):
@@ -214,12 +214,14 @@ def _as_f32(a, shape, what):
 
 def solve_batch(P, q, lb=None, ub=None, z0=None, u0=None, options: Optional[Options] = None,
                 out: Optional[dict] = None, workspace: Optional["Workspace"] = None,
-                want=("x", "z", "lam", "status", "iters")) -> dict:
+                want=("x", "z", "lam", "status", "iters"), rho=None) -> dict:
     """Solve ``count`` box QPs: the batched replacement of a loop of the
     reference's ``admm(x0, iterations, qf)`` (qp_solvers.c:255-319).
 
     P [count,n,n], q [count,n] float32; lb/ub each an array [count,n], a Python
     scalar, or None (= -/+1e12, the reference's host box, config.h:29-30).
+    rho: None (``options.rho`` for every problem, the reference's RHO_ADMM) or
+    an array [count] of per-problem penalties.
     CUDA torch tensors take the device path (kernel launched on the current
     torch stream, no synchronisation, outputs are torch tensors on that
     device); numpy arrays / CPU tensors take the host path (copies, sharded
@@ -259,6 +261,12 @@ def solve_batch(P, q, lb=None, ub=None, z0=None, u0=None, options: Optional[Opti
                 raise ValueError(f"{name} must live where P lives")
             setattr(pb, name, a)
             keep.append(h)
+    if rho is not None:
+        h, a, d = _as_f32(rho, (count,), "rho")
+        if d != dev:
+            raise ValueError("rho must live where P lives")
+        pb.rho = a
+        keep.append(h)
 
     res = {} if out is None else out
     sol = qp_batch_solution()

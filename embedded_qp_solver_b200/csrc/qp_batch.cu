@@ -345,6 +345,7 @@ KernelArgs make_args(const qp_batch &pb, const qp_batch_solution &sol, const qp_
 	a.n = int(pb.n);
 	a.lb_s = pb.lb_scalar, a.ub_s = pb.ub_scalar;
 	a.rho = o.rho, a.alpha = o.alpha;
+	a.rho_v = pb.rho;
 	// sqrt(nrows) * abstol, evaluated in double like qp_solvers.c:242 and rounded once
 	a.eps_abs = float(std::sqrt(double(pb.n)) * double(o.abstol));
 	a.reltol = o.reltol;
@@ -563,11 +564,11 @@ static constexpr int DEPTH = 3;
 struct Slot {
 	// device buffers for one chunk
 	float *dP = nullptr, *dq = nullptr, *dlb = nullptr, *dub = nullptr, *dz0 = nullptr,
-	      *du0 = nullptr;
+	      *du0 = nullptr, *drho = nullptr;
 	float *dx = nullptr, *dz = nullptr, *dlam = nullptr;
 	int32_t *dstatus = nullptr, *diters = nullptr;
 	// pinned staging (allocated on first use with pageable caller memory)
-	float *hin = nullptr;  // P | q | lb | ub | z0 | u0
+	float *hin = nullptr;  // P | q | lb | ub | z0 | u0 | rho
 	float *hout = nullptr; // x | z | lam | status | iters
 	float *hpk = nullptr;  // packed upper triangles of P (pinned), n = 8, 12, 16
 	cudaStream_t stream = nullptr;
@@ -594,7 +595,7 @@ namespace {
 
 size_t in_floats(uint32_t n)
 {
-	return size_t(n) * n + 5ull * n;
+	return size_t(n) * n + 5ull * n + 1;
 }
 size_t out_floats(uint32_t n)
 {
@@ -667,7 +668,8 @@ int alloc_ctx(DeviceCtx &c, uint32_t n, size_t chunk)
 		s.dub = s.dlb + chunk * n;
 		s.dz0 = s.dub + chunk * n;
 		s.du0 = s.dz0 + chunk * n;
-		s.dx = s.du0 + chunk * n;
+		s.drho = s.du0 + chunk * n;
+		s.dx = s.drho + chunk;
 		s.dz = s.dx + chunk * n;
 		s.dlam = s.dz + chunk * n;
 		s.dstatus = reinterpret_cast<int32_t *>(s.dlam + chunk * n);
@@ -700,7 +702,8 @@ int run_shard(qp_workspace *ws, DeviceCtx &ctx, const qp_batch &pb, const qp_bat
 	const uint32_t n = pb.n;
 	const size_t chunk = ws->chunk;
 	const bool pin_in = is_pinned(pb.P) && is_pinned(pb.q) && is_pinned(pb.lb) &&
-			    is_pinned(pb.ub) && is_pinned(pb.z0) && is_pinned(pb.u0);
+			    is_pinned(pb.ub) && is_pinned(pb.z0) && is_pinned(pb.u0) &&
+			    is_pinned(pb.rho);
 	const bool pin_out = is_pinned(sol.x) && is_pinned(sol.z) && is_pinned(sol.lambda) &&
 			     is_pinned(sol.status) && is_pinned(sol.iters);
 
@@ -787,7 +790,8 @@ int run_shard(qp_workspace *ws, DeviceCtx &ctx, const qp_batch &pb, const qp_bat
 			float *dst;
 			size_t per;
 		} ins[] = { { pb.P, s.dP, size_t(n) * n }, { pb.q, s.dq, n },  { pb.lb, s.dlb, n },
-			    { pb.ub, s.dub, n },           { pb.z0, s.dz0, n }, { pb.u0, s.du0, n } };
+			    { pb.ub, s.dub, n },           { pb.z0, s.dz0, n }, { pb.u0, s.du0, n },
+			    { pb.rho, s.drho, 1 } };
 		if (pack)
 			QP_CUDA(cudaMemcpyAsync(s.dP, s.hpk, c * size_t(pk) * 4, cudaMemcpyHostToDevice, st));
 		if (pin_in) {
@@ -816,6 +820,7 @@ int run_shard(qp_workspace *ws, DeviceCtx &ctx, const qp_batch &pb, const qp_bat
 		dpb.P = s.dP, dpb.q = s.dq;
 		dpb.lb = pb.lb ? s.dlb : nullptr, dpb.ub = pb.ub ? s.dub : nullptr;
 		dpb.z0 = pb.z0 ? s.dz0 : nullptr, dpb.u0 = pb.u0 ? s.du0 : nullptr;
+		dpb.rho = pb.rho ? s.drho : nullptr;
 		qp_batch_solution dsol;
 		dsol.x = sol.x ? s.dx : nullptr, dsol.z = sol.z ? s.dz : nullptr;
 		dsol.lambda = sol.lambda ? s.dlam : nullptr;

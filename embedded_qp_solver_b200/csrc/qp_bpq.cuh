@@ -118,15 +118,17 @@ qp_bpq_kernel(const KernelArgs p)
 	// the idle lanes (grp == G) fold into the last T lanes so that their shuffles stay in range
 	const GroupRing<T> ring(grp < G ? gbase : 32 - T, grp < G ? g : lane - (32 - T));
 	float *bc = sm + (warp * C::GG + grp) * C::GROUP; // bc[buf * BUF + 4 * j + m]
-	const float rho = p.rho, alpha = p.alpha;
+	const float alpha = p.alpha;
 	const bool relax = (alpha != 1.0f);
-	const float rho2 = rho * rho, relrho = p.reltol * rho;
 
 	const unsigned long long stride = (unsigned long long)gridDim.x * BPQ_WARPS * G;
 	for (unsigned long long base = ((unsigned long long)blockIdx.x * BPQ_WARPS + warp) * G;
 	     base < p.count; base += stride) {
 		const unsigned long long prob = base + grp;
 		const bool valid = (grp < G) && (prob < p.count);
+		// penalty of this group's problem (qp_batch.rho)
+		const float rho = (p.rho_v && valid) ? __ldg(p.rho_v + prob) : p.rho;
+		const float rho2 = rho * rho, relrho = p.reltol * rho;
 
 		// ---- load: rows 4g..4g+3 of P + rho I, read as column blocks of the symmetric P ------
 		float2 S[2][NP]; // S[rp][j] = (row 4g+2rp, row 4g+2rp+1) at column j
@@ -154,7 +156,7 @@ qp_bpq_kernel(const KernelArgs p)
 		// again.  That halves the elimination work; x = R y becomes NC rank-4 updates of a
 		// vector (see the iteration loop).  The run-time block loop is cut into compile-time
 		// segments of four steps so that L is known per segment up to three.
-		bool bad = false;
+		bool bad = !(rho > 0.0f && rho < 3.0e38f);
 		constexpr int NC = NP / 4;
 		constexpr int SEG = PFI ? 4 : NC;
 		constexpr int NSEG = (NC + SEG - 1) / SEG;

@@ -21,6 +21,7 @@ struct KernelArgs {
 	int n;
 	float lb_s, ub_s;      // scalar box when lb/ub are null
 	float rho, alpha;
+	const float *rho_v;    // [count] per-problem rho, or null: rho for all
 	float eps_abs;         // sqrt(n) * abstol   (qp_solvers.c:242, :252)
 	float reltol;
 	unsigned max_iter;

@@ -209,15 +209,17 @@ qp_gpq_kernel(const KernelArgs p)
 	const int grp = lane / T;     // group inside the warp
 	const int n = p.n;
 	float *bc = sm + warp * SM::WARP + grp * SM::GROUP; // bc[(buf*4+m)*ROW + j]
-	const float rho = p.rho, alpha = p.alpha;
+	const float alpha = p.alpha;
 	const bool relax = (alpha != 1.0f);
-	const float rho2 = rho * rho, relrho = p.reltol * rho;
 
 	const unsigned long long stride = (unsigned long long)gridDim.x * GPQ_WARPS * G;
 	for (unsigned long long base = ((unsigned long long)blockIdx.x * GPQ_WARPS + warp) * G;
 	     base < p.count; base += stride) {
 		const unsigned long long prob = base + grp;
 		const bool valid = prob < p.count;
+		// penalty of this group's problem (qp_batch.rho)
+		const float rho = (p.rho_v && valid) ? __ldg(p.rho_v + prob) : p.rho;
+		const float rho2 = rho * rho, relrho = p.reltol * rho;
 
 		// ---- load: the owner of row r takes column r of the symmetric P ------------------
 		// S[s][h] = (row element 2h, row element 2h+1) of row g + T*s
@@ -270,7 +272,7 @@ qp_gpq_kernel(const KernelArgs p)
 		// the next owners publish just their 4x4 block, and its inverse is computed while
 		// the remaining chunks of step K are being updated.  At the end of step K the next
 		// owners publish their complete rows, so step K+1 starts with everything it needs.
-		bool bad = false;
+		bool bad = !(rho > 0.0f && rho < 3.0e38f);
 		float Bi[4][4]; // minus the inverse of the current pivot block
 		{
 			if (g < 4)

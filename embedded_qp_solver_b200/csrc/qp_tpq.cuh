@@ -240,6 +240,8 @@ qp_tpq_kernel(const KernelArgs p)
 		const unsigned long long left = p.count - first;
 		const int cnt = left < 32ull ? int(left) : 32;
 		const bool valid = lane < cnt;
+		// penalty of this thread's problem (qp_batch.rho), requested before the wait
+		const float rho = (p.rho_v && valid) ? __ldg(p.rho_v + first + lane) : p.rho;
 
 		// wait until the stage has been armed for this round, then for its bytes
 		while (stage_round[s] < round + 1)
@@ -315,8 +317,8 @@ qp_tpq_kernel(const KernelArgs p)
 		// ---- factor P + rho I  (replaces matrix_invert, matrix_ops.c:551-630) ----------
 #pragma unroll
 		for (int i = 0; i < N; ++i)
-			a[sidx<N>(i, i)] += p.rho;
-		const bool bad = ldlt_factor<N>(a);
+			a[sidx<N>(i, i)] += rho;
+		const bool bad = ldlt_factor<N>(a) || !(rho > 0.0f && rho < 3.0e38f);
 
 		// ---- ADMM iterations (qp_solvers.c:284-310) ------------------------------------
 #pragma unroll
@@ -326,7 +328,7 @@ qp_tpq_kernel(const KernelArgs p)
 		int my_status = QP_STATUS_MAX_ITER;
 		unsigned it = 0;
 		bool active = valid && !bad && p.max_iter > 0;
-		const float rho = p.rho, alpha = p.alpha;
+		const float alpha = p.alpha;
 		const float rho2 = rho * rho, relrho = p.reltol * rho;
 
 		// q lives in shared memory; it is fetched one iteration ahead (at the end of the

@@ -92,6 +92,10 @@ typedef struct qp_batch {
 	const float *z0;     /* [count][n] warm start of z, or NULL = 0            */
 	const float *u0;     /* [count][n] warm start of u, or NULL = 0
 	                        (the reference zeroes both, qp_solvers.c:263-264)  */
+	const float *rho;    /* [count] penalty of each problem (> 0), or NULL:
+	                        qp_options.rho for all (the reference's RHO_ADMM,
+	                        qp_solvers.c:281).  A problem whose entry is not a
+	                        positive finite number ends with QP_STATUS_SINGULAR */
 } qp_batch;
 
 /* Caller-owned outputs; any pointer may be NULL to skip that output. */

@@ -38,7 +38,7 @@ def test_default_options_are_the_reference_constants(qp):
 
 def test_struct_sizes_match_header(qp):
     from embedded_qp_solver_b200 import api
-    assert C.sizeof(api.qp_batch) == 72
+    assert C.sizeof(api.qp_batch) == 80
     assert C.sizeof(api.qp_batch_solution) == 40
     assert C.sizeof(api.qp_options) == 48
 

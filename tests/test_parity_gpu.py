@@ -545,3 +545,69 @@ def test_host_path_equals_device_path(qp, n):
     dw = solve_dev(qp, P, q2, lb, ub, z0=d["z"], u0=d["lam"])
     hw = qp.solve_batch(P, q2, lb, ub, z0=d["z"], u0=d["lam"], options=small)
     assert np.array_equal(hw["x"], dw["x"]) and np.array_equal(hw["iters"], dw["iters"])
+
+
+# ---- per-problem rho (qp_batch.rho) -----------------------------
+
+@pytest.mark.parametrize("n", [4, 12, 16, 20, 40, 64])
+def test_per_problem_rho_against_oracle(qp, orc, n):
+    """Every problem carries its own penalty; the oracle (the reference's iteration with its
+    RHO_ADMM made an argument) is run once per distinct value."""
+    count = 600 if n <= 16 else 96
+    P, q, lb, ub = problems.wellcond(count, n, seed=4200 + n, beta=0.5)
+    values = np.array([0.4, 1.0, 1.7, 3.0], np.float32)
+    rho = values[np.arange(count) % len(values)]
+    trho = torch.from_numpy(rho).cuda()
+    tP, tq, tlb, tub = dev(P, q, lb, ub)
+    r = qp.solve_batch(tP, tq, tlb, tub, rho=trho)
+    torch.cuda.synchronize()
+    res = {k: v.cpu().numpy() for k, v in r.items()}
+    for v in values:
+        m = rho == v
+        o = orc.admm(P[m].astype(np.float64), q[m].astype(np.float64), lb[m], ub[m], rho=float(v))
+        ok = nondegenerate(o["margins"]) & (o["status"] == 0)
+        assert ok.sum() >= 0.5 * m.sum()
+        assert np.array_equal(res["iters"][m][ok], o["iters"][ok]), (n, v)
+        assert np.array_equal(res["status"][m][ok], o["status"][ok]), (n, v)
+        assert rel_err(res["x"][m][ok].astype(np.float64), o["x"][ok]).max() <= X_TOL
+        assert np.max(np.abs(res["lam"][m][ok] - float(v) * o["u"][ok])) <= 1e-3
+
+
+@pytest.mark.parametrize("n", [8, 16, 32, 40, 56])
+def test_constant_rho_array_equals_the_option(qp, n):
+    """A rho array filled with one value is bit-identical to passing it in qp_options."""
+    P, q, lb, ub = problems.wellcond(257, n, seed=4300 + n, beta=0.5)
+    tP, tq, tlb, tub = dev(P, q, lb, ub)
+    a = qp.solve_batch(tP, tq, tlb, tub, options=qp.Options(rho=1.5))
+    b = qp.solve_batch(tP, tq, tlb, tub, rho=torch.full((257,), 1.5, device="cuda"))
+    torch.cuda.synchronize()
+    for k in a:
+        assert torch.equal(a[k], b[k]), (n, k)
+
+
+@pytest.mark.parametrize("n", [16, 40, 64])
+def test_bad_rho_entries_are_flagged_per_problem(qp, n):
+    P, q, lb, ub = problems.wellcond(64, n, seed=4400 + n, beta=0.5)
+    rho = np.ones(64, np.float32)
+    rho[[3, 17, 40, 41]] = [0.0, -1.0, np.nan, np.inf]
+    tP, tq, tlb, tub = dev(P, q, lb, ub)
+    r = qp.solve_batch(tP, tq, tlb, tub, rho=torch.from_numpy(rho).cuda())
+    torch.cuda.synchronize()
+    st = r["status"].cpu().numpy()
+    bad = np.zeros(64, bool)
+    bad[[3, 17, 40, 41]] = True
+    assert np.all(st[bad] == qp.STATUS_SINGULAR) and np.all(st[~bad] == qp.STATUS_CONVERGED)
+    assert np.all(r["iters"].cpu().numpy()[bad] == 0)
+
+
+@pytest.mark.parametrize("n", [16, 40])
+def test_per_problem_rho_host_path(qp, n):
+    count = 5000 if n == 16 else 700
+    P, q, lb, ub = problems.wellcond(count, n, seed=4500 + n, beta=0.5)
+    rho = np.random.default_rng(5).uniform(0.5, 2.0, count).astype(np.float32)
+    h = qp.solve_batch(P, q, lb, ub, rho=rho)
+    tP, tq, tlb, tub = dev(P, q, lb, ub)
+    d = qp.solve_batch(tP, tq, tlb, tub, rho=torch.from_numpy(rho).cuda())
+    torch.cuda.synchronize()
+    for k in h:
+        assert np.array_equal(np.asarray(h[k]), d[k].cpu().numpy()), (n, k)
