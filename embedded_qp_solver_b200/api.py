@@ -20,13 +20,14 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libqpb200.so")
 
-QP_MAX_DIM = 64
+QP_MAX_DIM = 64        # Newton, gradient, general rows
+QP_MAX_DIM_BOX = 128   # box ADMM (solve_batch, admm)
 QP_MAX_ROWS = 128
 STATUS_CONVERGED, STATUS_MAX_ITER, STATUS_SINGULAR, STATUS_NONFINITE = 0, 1, 2, 3
 QP_OK, QP_ERR_INVALID, QP_ERR_UNSUPPORTED, QP_ERR_CUDA, QP_ERR_NO_DEVICE = 0, -1, -2, -3, -4
 QP_ERR_IO = -5
 MEM_HOST, MEM_DEVICE = 0, 1
-KERNEL_AUTO, KERNEL_TPQ, KERNEL_GPQ, KERNEL_BPQ = 0, 1, 2, 3
+KERNEL_AUTO, KERNEL_TPQ, KERNEL_GPQ, KERNEL_BPQ, KERNEL_CPQ = 0, 1, 2, 3, 4
 
 _fp = C.POINTER(C.c_float)
 _ip = C.POINTER(C.c_int32)
@@ -183,7 +184,7 @@ class Options:
     device: int = -1
     stream: int = 0
     chunk: int = 0
-    kernel: int = 0   # KERNEL_AUTO / KERNEL_TPQ / KERNEL_GPQ / KERNEL_BPQ
+    kernel: int = 0   # KERNEL_AUTO / KERNEL_TPQ / KERNEL_GPQ / KERNEL_BPQ / KERNEL_CPQ
 
     def to_c(self) -> qp_options:
         return qp_options(self.rho, self.alpha, self.abstol, self.reltol, int(self.max_iter),

@@ -32,6 +32,7 @@
 #endif
 
 #include "qp_bpq.cuh"
+#include "qp_cpq.cuh"
 #include "qp_gen.cuh"
 #include "qp_gpq.cuh"
 #include "qp_newton.cuh"
@@ -256,15 +257,27 @@ template <int NP> int launch_bpq(const KernelArgs &a, int dev, cudaStream_t st)
 	return launch_bpq_form<NP, false>(a, dev, st);
 }
 
+template <int TT> int launch_cpq(const KernelArgs &a, int dev, cudaStream_t st)
+{
+	const unsigned long long grid = std::min<unsigned long long>(a.count, 2ull * dev_sms(dev));
+	qp_cpq_kernel<TT><<<dim3((unsigned)grid), dim3(CPQ_THREADS), 0, st>>>(a);
+	QP_CUDA(cudaGetLastError());
+	return QP_OK;
+}
+
 // which kernel family solves this batch (QP_KERNEL_*), 0 = none
 int pick_kernel(const KernelArgs &a, uint32_t forced)
 {
 	const bool t = tpq_eligible(a), b = bpq_eligible(a), g = a.n >= 1 && a.n <= QP_MAX_DIM;
+	const bool c = a.n >= 1 && a.n <= QP_MAX_DIM_BOX;
 	switch (forced) {
 	case QP_KERNEL_TPQ: return t ? QP_KERNEL_TPQ : 0;
 	case QP_KERNEL_BPQ: return b ? QP_KERNEL_BPQ : 0;
 	case QP_KERNEL_GPQ: return g ? QP_KERNEL_GPQ : 0;
+	case QP_KERNEL_CPQ: return c ? QP_KERNEL_CPQ : 0;
 	}
+	if (a.n > QP_MAX_DIM)
+		return c ? QP_KERNEL_CPQ : 0;
 	if (t)
 		return QP_KERNEL_TPQ;
 	if (b && a.n >= 24) // measured at n = 24, 32, 40: bpq ahead of gpq by 12, 11 and 27 % (profiles/README.md)
@@ -306,6 +319,18 @@ int launch_solver(const KernelArgs &a, int dev, cudaStream_t st, uint32_t forced
 		case 64: return launch_gpq<64>(a, dev, st);
 		}
 		break;
+	case QP_KERNEL_CPQ:
+		switch ((a.n + 15) / 16) {
+		case 1: return launch_cpq<1>(a, dev, st);
+		case 2: return launch_cpq<2>(a, dev, st);
+		case 3: return launch_cpq<3>(a, dev, st);
+		case 4: return launch_cpq<4>(a, dev, st);
+		case 5: return launch_cpq<5>(a, dev, st);
+		case 6: return launch_cpq<6>(a, dev, st);
+		case 7: return launch_cpq<7>(a, dev, st);
+		case 8: return launch_cpq<8>(a, dev, st);
+		}
+		break;
 	}
 	return QP_ERR_UNSUPPORTED;
 }
@@ -316,7 +341,7 @@ int check_problem(const qp_batch *pb, const qp_batch_solution *sol)
 		return QP_ERR_INVALID;
 	if (pb->n == 0)
 		return QP_ERR_INVALID;
-	if (pb->n > QP_MAX_DIM)
+	if (pb->n > QP_MAX_DIM_BOX)
 		return QP_ERR_UNSUPPORTED;
 	if (pb->mem != QP_MEM_HOST && pb->mem != QP_MEM_DEVICE)
 		return QP_ERR_INVALID;
@@ -888,7 +913,7 @@ extern "C" int qp_workspace_create(uint32_t n, size_t max_count, uint32_t device
 {
 	if (!out || n == 0)
 		return QP_ERR_INVALID;
-	if (n > QP_MAX_DIM)
+	if (n > QP_MAX_DIM_BOX)
 		return QP_ERR_UNSUPPORTED;
 	std::vector<int> devs = mask_devices(device_mask, resolve_device(-1));
 	if (devs.empty())
@@ -1360,7 +1385,7 @@ extern "C" int qp_admm_qf_batch(const struct qp_ref_quadratic_form *const *qfs, 
 	const unsigned n = ref_rows(qfs[0]->p);
 	if (n == 0)
 		return QP_ERR_INVALID;
-	if (n > QP_MAX_DIM)
+	if (n > QP_MAX_DIM_BOX)
 		return QP_ERR_UNSUPPORTED;
 	for (size_t i = 0; i < count; ++i)
 		if (ref_rows(qfs[i]->p) != n || ref_cols(qfs[i]->p) != n ||
@@ -1476,7 +1501,7 @@ extern "C" int qp_gradient_qf(const struct qp_ref_quadratic_form *qf, const doub
 extern "C" const char *qp_kernel_for(uint32_t n, int al16)
 {
 	static thread_local char buf[32];
-	if (n == 0 || n > QP_MAX_DIM)
+	if (n == 0 || n > QP_MAX_DIM_BOX)
 		return "unsupported";
 	KernelArgs a = {};
 	a.n = int(n);
@@ -1485,6 +1510,7 @@ extern "C" const char *qp_kernel_for(uint32_t n, int al16)
 	switch (pick_kernel(a, QP_KERNEL_AUTO)) {
 	case QP_KERNEL_TPQ: std::snprintf(buf, sizeof buf, "tpq<%u>", n); break;
 	case QP_KERNEL_BPQ: std::snprintf(buf, sizeof buf, "bpq<%u>", n); break;
+	case QP_KERNEL_CPQ: std::snprintf(buf, sizeof buf, "cpq<%u>", (n + 15) / 16 * 16); break;
 	default: std::snprintf(buf, sizeof buf, "gpq<%u>", (n + 7) / 8 * 8); break;
 	}
 	return buf;

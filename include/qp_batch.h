@@ -46,8 +46,11 @@ extern "C" {
 
 #define QP_B200_ABI_VERSION 1
 
-/* largest problem dimension the kernels accept */
+/* largest problem dimension: the box ADMM entry points (qp_solve_batch, qp_solve_batch_ws,
+ * qp_admm_qf, qp_admm_qf_batch) take n <= QP_MAX_DIM_BOX; the Newton, gradient and
+ * general-rows entry points take n <= QP_MAX_DIM */
 #define QP_MAX_DIM 64
+#define QP_MAX_DIM_BOX 128
 
 /* Per-problem outcome, written to qp_batch_solution.status.  The reference
  * returns no status; these are defined on its state:        */
@@ -129,6 +132,7 @@ typedef struct qp_options {
 #define QP_KERNEL_TPQ  1 /* one QP per thread:       n = 4, 8, 12, 16              */
 #define QP_KERNEL_GPQ  2 /* cyclic rows per lane:    any n <= 64                   */
 #define QP_KERNEL_BPQ  3 /* four rows per lane:      n = 8, 16, 24, 32, 40         */
+#define QP_KERNEL_CPQ  4 /* one CTA per QP:          any n <= 128 (auto: n > 64)   */
 
 void qp_options_default(qp_options *opt);
 

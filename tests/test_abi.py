@@ -50,7 +50,7 @@ def test_api_misuse_returns_error_codes(qp):
     assert lib.qp_solve_batch(None, C.byref(sol), None) == api.QP_ERR_INVALID
     pb.n, pb.count = 0, 1
     assert lib.qp_solve_batch(C.byref(pb), C.byref(sol), None) == api.QP_ERR_INVALID
-    pb.n = 65
+    pb.n = api.QP_MAX_DIM_BOX + 1
     assert lib.qp_solve_batch(C.byref(pb), C.byref(sol), None) == api.QP_ERR_UNSUPPORTED
     pb.n = 16  # null P with count > 0
     assert lib.qp_solve_batch(C.byref(pb), C.byref(sol), None) == api.QP_ERR_INVALID
@@ -70,7 +70,7 @@ def test_kernel_selection(qp):
     assert qp.kernel_for(40) == "bpq<40>" and qp.kernel_for(64) == "gpq<64>"
     assert qp.kernel_for(40, aligned16=False) == "gpq<40>" and qp.kernel_for(33) == "gpq<40>"
     assert qp.kernel_for(24) == "bpq<24>" and qp.kernel_for(32) == "bpq<32>" and qp.kernel_for(48) == "gpq<48>"
-    assert qp.kernel_for(13) == "gpq<16>" and qp.kernel_for(65) == "unsupported"
+    assert qp.kernel_for(13) == "gpq<16>" and qp.kernel_for(65) == "cpq<80>" and qp.kernel_for(129) == "unsupported"
 
 
 def test_roofline_bookkeeping(qp):

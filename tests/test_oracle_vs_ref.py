@@ -7,7 +7,7 @@ import pytest
 import oracle
 from embedded_qp_solver_b200 import problems
 
-SHAPES = [n for n in (4, 8, 16, 40, 64) if oracle.ref_available(n)]
+SHAPES = [n for n in (4, 8, 16, 40, 64, 96, 128) if oracle.ref_available(n)]
 pytestmark = pytest.mark.skipif(not SHAPES, reason="oracle/_ref not built (no /root/reference)")
 
 

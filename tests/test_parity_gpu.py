@@ -367,14 +367,16 @@ def test_full_size_headline_properties(qp, orc):
 
 # every kernel family at every shape it accepts (qp_options.kernel forces the family)
 FAMILIES = ([("tpq", n) for n in (4, 8, 12, 16)] + [("bpq", n) for n in (8, 16, 24, 32, 40)] +
-            [("gpq", n) for n in (4, 8, 13, 16, 24, 32, 40, 56, 64)])
+            [("gpq", n) for n in (4, 8, 13, 16, 24, 32, 40, 56, 64)] +
+            [("cpq", n) for n in (5, 16, 40, 64, 65, 80, 97, 112, 128)])
 
 
 @pytest.mark.parametrize("family,n", FAMILIES, ids=[f"{f}{n}" for f, n in FAMILIES])
 def test_every_kernel_family_against_oracle(qp, orc, family, n):
     """Cold start with the scalar box, then warm start with per-coordinate bounds and
     over-relaxation, each family forced; batch sizes that leave ragged warps/groups."""
-    kern = {"tpq": qp.KERNEL_TPQ, "bpq": qp.KERNEL_BPQ, "gpq": qp.KERNEL_GPQ}[family]
+    kern = {"tpq": qp.KERNEL_TPQ, "bpq": qp.KERNEL_BPQ, "gpq": qp.KERNEL_GPQ,
+            "cpq": qp.KERNEL_CPQ}[family]
     count = 333 if n <= 24 else 77
     P, q, lb, ub = problems.wellcond(count, n, seed=900 + n, beta=0.5)
     P64, q64 = P.astype(np.float64), q.astype(np.float64)
@@ -417,7 +419,8 @@ def test_forced_family_that_cannot_take_the_batch_is_refused(qp):
 def test_status_codes_every_family(qp):
     """A pivot <= 0 is status 2 (the reference prints "singular matrix",
     matrix_ops.c:511-515), a NaN in q is status 3; neighbours are unaffected."""
-    for kern, n in ((qp.KERNEL_TPQ, 8), (qp.KERNEL_BPQ, 40), (qp.KERNEL_GPQ, 40)):
+    for kern, n in ((qp.KERNEL_TPQ, 8), (qp.KERNEL_BPQ, 40), (qp.KERNEL_GPQ, 40),
+                    (qp.KERNEL_CPQ, 40), (qp.KERNEL_AUTO, 100)):
         P, q, lb, ub = problems.wellcond(70, n, seed=77, beta=0.5)
         P[3] = -P[3] - 3 * np.eye(n, dtype=np.float32)  # P + I negative definite
         q[5, 1] = np.nan
@@ -430,19 +433,21 @@ def test_status_codes_every_family(qp):
 
 
 @pytest.mark.parametrize("n,fams", [(8, ("tpq", "bpq", "gpq")), (16, ("tpq", "bpq", "gpq")),
-                                    (24, ("bpq", "gpq")), (40, ("bpq", "gpq"))])
+                                    (24, ("bpq", "gpq")), (40, ("bpq", "gpq")),
+                                    (64, ("gpq", "cpq"))])
 def test_kernel_families_agree_on_a_large_batch(qp, n, fams):
     """No sanitizer on this pool: a batch large enough to fill the persistent grid several
     times over (grid-stride loops, ragged tail, every warp slot) solved by each family;
     the families share no code below the dispatcher except the 4x4 pivot inverse."""
-    count = 200_003 if n <= 16 else 60_001
+    count = 200_003 if n <= 16 else (60_001 if n <= 40 else 20_001)
     gen = torch.Generator(device="cuda").manual_seed(5 + n)
     G = torch.randn((count, n, n), generator=gen, device="cuda")
     P = torch.baddbmm(torch.eye(n, device="cuda").expand(count, n, n), G.transpose(1, 2), G,
                       alpha=1.0 / n)
     P = (0.5 * (P + P.transpose(1, 2))).contiguous()
     q = torch.randn((count, n), generator=gen, device="cuda")
-    kern = {"tpq": qp.KERNEL_TPQ, "bpq": qp.KERNEL_BPQ, "gpq": qp.KERNEL_GPQ}
+    kern = {"tpq": qp.KERNEL_TPQ, "bpq": qp.KERNEL_BPQ, "gpq": qp.KERNEL_GPQ,
+            "cpq": qp.KERNEL_CPQ}
     res = {f: qp.solve_batch(P, q, -0.5, 0.5, options=qp.Options(kernel=kern[f])) for f in fams}
     torch.cuda.synchronize()
     a = res[fams[0]]
@@ -457,7 +462,7 @@ def test_kernel_families_agree_on_a_large_batch(qp, n, fams):
         assert float((a["z"] - b["z"]).abs().amax(dim=1)[same].max()) <= 2e-5
 
 
-@pytest.mark.parametrize("n", [1, 2, 3, 7, 63, 64])
+@pytest.mark.parametrize("n", [1, 2, 3, 7, 63, 64, 65, 127, 128])
 def test_edge_dimensions_and_tiny_batches(qp, orc, n):
     """Smallest and largest dimensions, batches of 1, 2 and 33 problems (less than a warp,
     one more than a warp)."""
@@ -611,3 +616,29 @@ def test_per_problem_rho_host_path(qp, n):
     torch.cuda.synchronize()
     for k in h:
         assert np.array_equal(np.asarray(h[k]), d[k].cpu().numpy()), (n, k)
+
+
+# ---- n > 64: one CTA per QP (qp_cpq.cuh) ---------------------------------------------------------
+
+def test_dimensions_above_128_are_refused_and_above_64_take_cpq(qp):
+    assert qp.kernel_for(65) == "cpq<80>" and qp.kernel_for(128) == "cpq<128>"
+    assert qp.kernel_for(129) == "unsupported"
+    P = torch.eye(129, device="cuda").repeat(2, 1, 1).contiguous()
+    q = torch.zeros((2, 129), device="cuda")
+    with pytest.raises(qp.QpError) as e:
+        qp.solve_batch(P, q, -1.0, 1.0)
+    assert e.value.code == -2
+
+
+@pytest.mark.parametrize("n", [96, 128])
+def test_large_dimension_host_path_and_per_problem_rho(qp, orc, n):
+    count = 150
+    P, q, lb, ub = problems.wellcond(count, n, seed=7000 + n, beta=0.5)
+    rho = np.where(np.arange(count) % 2 == 0, 1.0, 2.0).astype(np.float32)
+    h = qp.solve_batch(P, q, lb, ub, rho=rho)
+    for v in (1.0, 2.0):
+        m = rho == v
+        o = orc.admm(P[m].astype(np.float64), q[m].astype(np.float64), lb[m], ub[m], rho=v)
+        ok = nondegenerate(o["margins"]) & (o["status"] == 0)
+        assert np.array_equal(np.asarray(h["iters"])[m][ok], o["iters"][ok])
+        assert rel_err(np.asarray(h["x"])[m][ok].astype(np.float64), o["x"][ok]).max() <= X_TOL

@@ -31,7 +31,7 @@ def main():
     ap.add_argument("--cold", action="store_true", help="no warm start at n=64")
     ap.add_argument("--mpc", action="store_true",
                     help="n=40: condensed linear-MPC problems (BASELINE config 4; 4096 distinct, tiled)")
-    ap.add_argument("--kernel", default="auto", choices=["auto", "tpq", "gpq", "bpq"])
+    ap.add_argument("--kernel", default="auto", choices=["auto", "tpq", "gpq", "bpq", "cpq"])
     ap.add_argument("--counts", default="", help="override batch sizes, e.g. 24:262144,32:262144")
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
@@ -39,7 +39,7 @@ def main():
     fp32_peak = qp.probe_fp32_tflops(0, 5)
     peaks = os.path.join(ROOT, "MEASURED_PEAKS.json")
     hbm_peak = float(json.load(open(peaks))["hbm_gbs"]) if os.path.exists(peaks) else 6650.0
-    kern = {"auto": qp.KERNEL_AUTO, "tpq": qp.KERNEL_TPQ, "gpq": qp.KERNEL_GPQ, "bpq": qp.KERNEL_BPQ}[args.kernel]
+    kern = {"auto": qp.KERNEL_AUTO, "tpq": qp.KERNEL_TPQ, "gpq": qp.KERNEL_GPQ, "bpq": qp.KERNEL_BPQ, "cpq": qp.KERNEL_CPQ}[args.kernel]
     opts = qp.Options(kernel=kern)
     counts = dict(SHAPES)
     for item in filter(None, args.counts.split(",")):
