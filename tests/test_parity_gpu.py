@@ -642,3 +642,78 @@ def test_large_dimension_host_path_and_per_problem_rho(qp, orc, n):
         ok = nondegenerate(o["margins"]) & (o["status"] == 0)
         assert np.array_equal(np.asarray(h["iters"])[m][ok], o["iters"][ok])
         assert rel_err(np.asarray(h["x"])[m][ok].astype(np.float64), o["x"][ok]).max() <= X_TOL
+
+
+# ---- the other BASELINE.json configurations at full size ---------------------------------------
+
+def _random_device_batch(count, n, seed):
+    gen = torch.Generator(device="cuda").manual_seed(seed)
+    G = torch.randn((count, n, n), generator=gen, device="cuda")
+    P = torch.baddbmm(torch.eye(n, device="cuda").expand(count, n, n), G.transpose(1, 2), G,
+                      alpha=1.0 / n)
+    P = (0.5 * (P + P.transpose(1, 2))).contiguous()
+    return P, torch.randn((count, n), generator=gen, device="cuda")
+
+
+def _sample_against_oracle(orc, res, P, q, beta, picks, **kw):
+    idx = torch.randint(0, P.shape[0], (picks,), generator=torch.Generator().manual_seed(3)).cuda()
+    o = orc.admm(P[idx].cpu().numpy().astype(np.float64), q[idx].cpu().numpy().astype(np.float64),
+                 -beta, beta, **{k: v[idx].cpu().numpy().astype(np.float64) for k, v in kw.items()})
+    ok = nondegenerate(o["margins"]) & (o["status"] == 0)
+    assert ok.mean() > 0.8
+    assert np.array_equal(res["iters"][idx].cpu().numpy()[ok], o["iters"][ok])
+    assert np.array_equal(res["status"][idx].cpu().numpy()[ok], o["status"][ok])
+    zr, zo = res["z"][idx].cpu().numpy()[ok], o["z"][ok].astype(np.float32)
+    b = np.float32(beta)
+    assert np.array_equal(active_set(zr, -b, b), active_set(zo, -b, b))
+    assert rel_err(res["x"][idx].cpu().numpy()[ok].astype(np.float64), o["x"][ok]).max() <= X_TOL
+
+
+def test_full_size_config_n4(qp, orc):
+    """BASELINE configs[1]: 2^20 problems, n = 4."""
+    P, q = _random_device_batch(1 << 20, 4, 2026)
+    r1 = qp.solve_batch(P, q, -0.5, 0.5)
+    r2 = qp.solve_batch(P, q, -0.5, 0.5)
+    torch.cuda.synchronize()
+    for k in r1:
+        assert torch.equal(r1[k], r2[k]), k
+    assert int((r1["status"] != 0).sum()) == 0 and float(r1["z"].abs().max()) <= 0.5
+    _sample_against_oracle(orc, r1, P, q, 0.5, 4000)
+
+
+def test_full_size_config_mpc_n40(qp, orc):
+    """BASELINE configs[3]: 2^18 condensed linear-MPC problems, n = 40 (4096 distinct ones,
+    tiled): copies of one problem must give identical answers wherever they sit in the
+    grid, and a sample must agree with the oracle."""
+    Pm, qm, lbm, ubm = problems.mpc(4096, seed=2026)
+    beta = float(ubm[0, 0])
+    reps = (1 << 18) // 4096
+    P = torch.from_numpy(Pm).cuda().repeat(reps, 1, 1).contiguous()
+    q = torch.from_numpy(qm).cuda().repeat(reps, 1).contiguous()
+    r = qp.solve_batch(P, q, -beta, beta)
+    torch.cuda.synchronize()
+    assert int((r["status"] != 0).sum()) == 0
+    assert float(r["z"].abs().max()) <= beta
+    for k in ("x", "z", "lam", "iters"):
+        v = r[k].reshape(reps, 4096, -1)
+        assert torch.equal(v, v[:1].expand_as(v)), k
+    _sample_against_oracle(orc, r, P, q, beta, 300)
+
+
+def test_full_size_config_warm_n64(qp, orc):
+    """BASELINE configs[4]: 2^16 problems, n = 64, re-solved from the previous solution
+    after a 1 % perturbation of q."""
+    count = 1 << 16
+    P, q = _random_device_batch(count, 64, 2026)
+    first = qp.solve_batch(P, q, -0.5, 0.5)
+    q2 = q + 0.01 * torch.randn(q.shape, device="cuda",
+                                generator=torch.Generator(device="cuda").manual_seed(9))
+    z0, u0 = first["z"].clone(), first["lam"].clone()
+    warm = qp.solve_batch(P, q2, -0.5, 0.5, z0=z0, u0=u0)
+    cold = qp.solve_batch(P, q2, -0.5, 0.5)
+    torch.cuda.synchronize()
+    assert int((warm["status"] != 0).sum()) == 0 and int((cold["status"] != 0).sum()) == 0
+    assert float(warm["iters"].float().mean()) < 0.6 * float(cold["iters"].float().mean())
+    # both runs stop inside the same tolerance ball around the one minimiser
+    assert float((warm["z"] - cold["z"]).abs().max()) <= 2e-2
+    _sample_against_oracle(orc, warm, P, q2, 0.5, 200, z0=z0, u0=u0)
