@@ -167,21 +167,27 @@ qp_bpq_kernel(const KernelArgs p)
 		for (int K = seg * SEG; K < Kseg; ++K) {
 			const int L = PFI ? NC - K : NC;
 			float *pb = bc + (K & 1) * C::BUF; // pb[m * ROW + position]: pivot row m
-			// Publish the four pivot rows WITHOUT their owner writing forty stores: the
-			// intermediate matrix of Gauss-Jordan is symmetric up to sign (rows already
-			// pivoted: M[m][c] = -M[c][m]; the others: M[m][c] = M[c][m]), so the entries of
-			// the pivot rows at the columns of MY rows are my own first four columns.  Every
-			// lane writes its 4x4 block (four 128-bit stores, all lanes in parallel).
-			// Column c sits at shifted position (c - 4K) mod n.  In product form the columns
-			// of pivoted rows are dead (eta columns): those lanes have nothing to publish.
-			if (!PFI || g >= K) {
-				const float sg = g < K ? -1.0f : 1.0f;
-				const int p0 = 4 * (g >= K ? g - K : g - K + NC);
+			// The owner publishes its four rows as they are.  (The intermediate matrix of
+			// Gauss-Jordan is symmetric up to sign, so every lane could publish the entries of
+			// the pivot rows at its own columns from its first four columns -- four stores per
+			// lane instead of forty by one.  That was measured 5 % faster and is NOT done: rows
+			// filled in from other rows' columns break the row-operation invariant R A = I,
+			// and on ill-conditioned problems the left residual grows a hundredfold,
+			// profiles/README.md "block pivot accuracy".)  In product form only the first L
+			// chunks are still matrix columns.
+			if (g == K) {
 #pragma unroll
-				for (int m = 0; m < 4; ++m) {
-					const float2 a = __fmul2_rn(S[0][m], make_float2(sg, sg));
-					const float2 b = __fmul2_rn(S[1][m], make_float2(sg, sg));
-					*reinterpret_cast<float4 *>(pb + m * ROW + p0) = make_float4(a.x, a.y, b.x, b.y);
+				for (int c = 0; c < NC; ++c) {
+					if (c < Lmin || c < L) {
+						*reinterpret_cast<float4 *>(pb + 0 * ROW + 4 * c) = make_float4(
+							S[0][4 * c].x, S[0][4 * c + 1].x, S[0][4 * c + 2].x, S[0][4 * c + 3].x);
+						*reinterpret_cast<float4 *>(pb + 1 * ROW + 4 * c) = make_float4(
+							S[0][4 * c].y, S[0][4 * c + 1].y, S[0][4 * c + 2].y, S[0][4 * c + 3].y);
+						*reinterpret_cast<float4 *>(pb + 2 * ROW + 4 * c) = make_float4(
+							S[1][4 * c].x, S[1][4 * c + 1].x, S[1][4 * c + 2].x, S[1][4 * c + 3].x);
+						*reinterpret_cast<float4 *>(pb + 3 * ROW + 4 * c) = make_float4(
+							S[1][4 * c].y, S[1][4 * c + 1].y, S[1][4 * c + 2].y, S[1][4 * c + 3].y);
+					}
 				}
 			}
 			if (g == K) {
@@ -197,28 +203,22 @@ qp_bpq_kernel(const KernelArgs p)
 				}
 			}
 			__syncwarp();
-			// pivot block (B[m][j] = pivot row m at column j), replaced by minus its inverse
+			// pivot block (B[m][j] = pivot row m at column j) and its L D L^T
 			float B[4][4];
 #pragma unroll
 			for (int m = 0; m < 4; ++m) {
 				const float4 v = *reinterpret_cast<const float4 *>(pb + m * ROW);
 				B[m][0] = v.x, B[m][1] = v.y, B[m][2] = v.z, B[m][3] = v.w;
 			}
-			bad |= neg_inv4(B);
-			// H = -(first four columns) x B^-1 = (first four columns) x B; H[m][rp] is the
-			// pair of multipliers of pivot row m for my row pair rp
+			Ldl4 Bf;
+			bad |= ldl4_factor(B, Bf);
+			// H = -(first four columns) x B^-1 by two triangular solves; H[m][rp] is the pair
+			// of multipliers of pivot row m for my row pair rp
 			float2 H[4][2];
 #pragma unroll
-			for (int m = 0; m < 4; ++m) {
-#pragma unroll
-				for (int rp = 0; rp < 2; ++rp) {
-					float2 h = __fmul2_rn(S[rp][0], make_float2(B[0][m], B[0][m]));
-					h = fma2_bc(S[rp][1], B[1][m], h);
-					h = fma2_bc(S[rp][2], B[2][m], h);
-					h = fma2_bc(S[rp][3], B[3][m], h);
-					H[m][rp] = h;
-				}
-			}
+			for (int rp = 0; rp < 2; ++rp)
+				ldl4_minus_solve2(Bf, S[rp][0], S[rp][1], S[rp][2], S[rp][3], H[0][rp], H[1][rp],
+						  H[2][rp], H[3][rp]);
 			// S(:, j-4) <- S(:, j) + H * pivot_rows(:, j)
 			auto update_chunk = [&](int c) {
 				float4 pr[4];

@@ -129,6 +129,74 @@ __device__ __forceinline__ float rcp_newton(float v)
 	return fmaf(r, fmaf(-v, r, 1.0f), r);
 }
 
+// L D L^T of a symmetric positive definite 4x4 pivot block, for the block Gauss-Jordan of
+// the lane-group kernels.  The multipliers of a block step, -c B^-1, are formed by two
+// triangular solves with these factors (minus_solve below), NOT by multiplying with an
+// explicit inverse of B: the solves are componentwise backward stable, the explicit inverse
+// is not, and on ill-conditioned problems (condensed MPC Hessians, cond(P + rho I) ~ 1e4)
+// the explicit form lost two digits in R (profiles/README.md, "block pivot accuracy").
+// Same operation count: 6 + 4 + 6 against 16.
+struct Ldl4 {
+	float l10, l20, l21, l30, l31, l32; // unit lower triangle
+	float n0, n1, n2, n3;               // -1 / d_k
+};
+
+// Reads the upper triangle of B.  Returns true when a pivot is not strictly positive.
+__device__ __forceinline__ bool ldl4_factor(const float (&B)[4][4], Ldl4 &f)
+{
+	const float d0 = B[0][0];
+	const float i0 = rcp_approx(d0);
+	f.l10 = B[0][1] * i0, f.l20 = B[0][2] * i0, f.l30 = B[0][3] * i0;
+	const float d1 = fmaf(-f.l10, B[0][1], B[1][1]);
+	const float t21 = fmaf(-f.l10, B[0][2], B[1][2]);
+	const float t31 = fmaf(-f.l10, B[0][3], B[1][3]);
+	const float i1 = rcp_approx(d1);
+	f.l21 = t21 * i1, f.l31 = t31 * i1;
+	const float d2 = fmaf(-f.l21, t21, fmaf(-f.l20, B[0][2], B[2][2]));
+	const float t32 = fmaf(-f.l21, t31, fmaf(-f.l20, B[0][3], B[2][3]));
+	const float i2 = rcp_approx(d2);
+	f.l32 = t32 * i2;
+	const float d3 = fmaf(-f.l32, t32, fmaf(-f.l31, t31, fmaf(-f.l30, B[0][3], B[3][3])));
+	const float i3 = rcp_approx(d3);
+	f.n0 = -i0, f.n1 = -i1, f.n2 = -i2, f.n3 = -i3;
+	return !(d0 > 0.0f) || !(d1 > 0.0f) || !(d2 > 0.0f) || !(d3 > 0.0f);
+}
+
+// h = -c B^-1 for the row vector c (B = L D L^T symmetric):  w = c L^-T, m = -w D^-1,
+// h = m L^-1
+__device__ __forceinline__ void ldl4_minus_solve(const Ldl4 &f, float c0, float c1, float c2, float c3,
+						 float &h0, float &h1, float &h2, float &h3)
+{
+	const float w1 = fmaf(-f.l10, c0, c1);
+	const float w2 = fmaf(-f.l21, w1, fmaf(-f.l20, c0, c2));
+	const float w3 = fmaf(-f.l32, w2, fmaf(-f.l31, w1, fmaf(-f.l30, c0, c3)));
+	const float m0 = c0 * f.n0, m1 = w1 * f.n1, m2 = w2 * f.n2;
+	h3 = w3 * f.n3;
+	h2 = fmaf(-f.l32, h3, m2);
+	h1 = fmaf(-f.l31, h3, fmaf(-f.l21, h2, m1));
+	h0 = fmaf(-f.l30, h3, fmaf(-f.l20, h2, fmaf(-f.l10, h1, m0)));
+}
+
+// the same for two rows at once, packed as (row a, row b)
+__device__ __forceinline__ float2 fma2_s(float s, float2 a, float2 c)
+{
+	return __ffma2_rn(make_float2(s, s), a, c);
+}
+__device__ __forceinline__ void ldl4_minus_solve2(const Ldl4 &f, float2 c0, float2 c1, float2 c2, float2 c3,
+						  float2 &h0, float2 &h1, float2 &h2, float2 &h3)
+{
+	const float2 w1 = fma2_s(-f.l10, c0, c1);
+	const float2 w2 = fma2_s(-f.l21, w1, fma2_s(-f.l20, c0, c2));
+	const float2 w3 = fma2_s(-f.l32, w2, fma2_s(-f.l31, w1, fma2_s(-f.l30, c0, c3)));
+	const float2 m0 = __fmul2_rn(c0, make_float2(f.n0, f.n0));
+	const float2 m1 = __fmul2_rn(w1, make_float2(f.n1, f.n1));
+	const float2 m2 = __fmul2_rn(w2, make_float2(f.n2, f.n2));
+	h3 = __fmul2_rn(w3, make_float2(f.n3, f.n3));
+	h2 = fma2_s(-f.l32, h3, m2);
+	h1 = fma2_s(-f.l31, h3, fma2_s(-f.l21, h2, m1));
+	h0 = fma2_s(-f.l30, h3, fma2_s(-f.l20, h2, fma2_s(-f.l10, h1, m0)));
+}
+
 // shared-memory 128-bit load the compiler may not hoist or merge
 __device__ __forceinline__ float4 lds128(const float4 *p)
 {

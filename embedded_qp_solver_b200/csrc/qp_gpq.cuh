@@ -66,49 +66,6 @@ template <int NP, int T> struct GpqSmem {
 	static constexpr int WARP = G * GROUP;
 };
 
-// B <- -B^-1 for a symmetric positive definite 4x4 block: four symmetric sweeps on the
-// upper triangle (36 multiply-adds and four MUFU reciprocals; a Gauss-Jordan on the full
-// block needs 60).  Only the upper triangle of B is read; the full (symmetric) result is
-// written.  Returns true when a pivot is not strictly positive.
-__device__ __forceinline__ bool neg_inv4(float (&B)[4][4])
-{
-	bool bad = false;
-#pragma unroll
-	for (int k = 0; k < 4; ++k) {
-		const float piv = B[k][k];
-		bad |= !(piv > 0.0f);
-		const float d = rcp_approx(piv);
-		float t[4];
-#pragma unroll
-		for (int j = 0; j < 4; ++j)
-			t[j] = (j < k ? B[j][k] : B[k][j]) * d;
-#pragma unroll
-		for (int i = 0; i < 4; ++i) {
-			if (i == k)
-				continue;
-			const float aik = i < k ? B[i][k] : B[k][i];
-#pragma unroll
-			for (int j = i; j < 4; ++j)
-				if (j != k)
-					B[i][j] = fmaf(-aik, t[j], B[i][j]);
-		}
-#pragma unroll
-		for (int j = 0; j < 4; ++j) {
-			if (j < k)
-				B[j][k] = t[j];
-			else if (j > k)
-				B[k][j] = t[j];
-		}
-		B[k][k] = -d;
-	}
-#pragma unroll
-	for (int i = 1; i < 4; ++i)
-#pragma unroll
-		for (int j = 0; j < i; ++j)
-			B[i][j] = B[j][i];
-	return bad;
-}
-
 // CTAs per SM the register budget is capped for (rows in registers: NP * RPL floats)
 template <int NP, int T> struct GpqOcc {
 	static constexpr int ROWREGS = NP * ((NP + T - 1) / T);
@@ -273,17 +230,18 @@ qp_gpq_kernel(const KernelArgs p)
 		// the remaining chunks of step K are being updated.  At the end of step K the next
 		// owners publish their complete rows, so step K+1 starts with everything it needs.
 		bool bad = !(rho > 0.0f && rho < 3.0e38f);
-		float Bi[4][4]; // minus the inverse of the current pivot block
+		Ldl4 Bf; // L D L^T of the current pivot block
 		{
 			if (g < 4)
 				publish_row<NH>(S[0], bc + g * ROW);
 			__syncwarp();
+			float Bi[4][4];
 #pragma unroll
 			for (int m = 0; m < 4; ++m) {
 				const float4 v = *reinterpret_cast<const float4 *>(bc + m * ROW);
 				Bi[m][0] = v.x, Bi[m][1] = v.y, Bi[m][2] = v.z, Bi[m][3] = v.w;
 			}
-			bad |= neg_inv4(Bi);
+			bad |= ldl4_factor(Bi, Bf);
 		}
 		// The run-time block loop is cut into compile-time segments: one per register slot,
 		// and in the product-form variant one per four steps, so that the number of chunks
@@ -320,20 +278,13 @@ qp_gpq_kernel(const KernelArgs p)
 					else
 						pivot_row_reset<NH>(S[ks], ctab, m0);
 				}
-				// H = -(first four columns) x B^-1 = (first four columns) x Bi, two pairs per row
+				// H = -(first four columns) x B^-1 by two triangular solves per row, two
+				// pairs per row
 				float2 H[RPL][2];
 #pragma unroll
-				for (int s = 0; s < RPL; ++s) {
-#pragma unroll
-					for (int mp = 0; mp < 2; ++mp) {
-						float2 h = __fmul2_rn(make_float2(Bi[0][2 * mp], Bi[0][2 * mp + 1]),
-								      make_float2(S[s][0].x, S[s][0].x));
-						h = fma2_bc(make_float2(Bi[1][2 * mp], Bi[1][2 * mp + 1]), S[s][0].y, h);
-						h = fma2_bc(make_float2(Bi[2][2 * mp], Bi[2][2 * mp + 1]), S[s][1].x, h);
-						h = fma2_bc(make_float2(Bi[3][2 * mp], Bi[3][2 * mp + 1]), S[s][1].y, h);
-						H[s][mp] = h;
-					}
-				}
+				for (int s = 0; s < RPL; ++s)
+					ldl4_minus_solve(Bf, S[s][0].x, S[s][0].y, S[s][1].x, S[s][1].y, H[s][0].x,
+							 H[s][0].y, H[s][1].x, H[s][1].y);
 				// S(:, j-4) <- S(:, j) + H * pivot_rows(:, j), one 4-column chunk at a time
 				auto update_chunk = [&](int c) {
 					float2 lo[4], hi[4];
@@ -375,7 +326,8 @@ qp_gpq_kernel(const KernelArgs p)
 					const float4 v = *reinterpret_cast<const float4 *>(pn + m * ROW);
 					Bn[m][0] = v.x, Bn[m][1] = v.y, Bn[m][2] = v.z, Bn[m][3] = v.w;
 				}
-				const bool badn = neg_inv4(Bn);
+				Ldl4 Bfn;
+				const bool badn = ldl4_factor(Bn, Bfn);
 #pragma unroll
 				for (int c = 2; c < NC; ++c) {
 					if (c < Lmin) // live in every step of this segment: no test
@@ -406,11 +358,7 @@ qp_gpq_kernel(const KernelArgs p)
 				}
 				__syncwarp();
 				bad |= more && badn;
-#pragma unroll
-				for (int i = 0; i < 4; ++i)
-#pragma unroll
-					for (int j = 0; j < 4; ++j)
-						Bi[i][j] = Bn[i][j];
+				Bf = Bfn;
 			}
 		}
 		__syncwarp();

@@ -438,7 +438,7 @@ def test_status_codes_every_family(qp):
 def test_kernel_families_agree_on_a_large_batch(qp, n, fams):
     """No sanitizer on this pool: a batch large enough to fill the persistent grid several
     times over (grid-stride loops, ragged tail, every warp slot) solved by each family;
-    the families share no code below the dispatcher except the 4x4 pivot inverse."""
+    the families share no code below the dispatcher except the 4x4 pivot-block factorisation."""
     count = 200_003 if n <= 16 else (60_001 if n <= 40 else 20_001)
     gen = torch.Generator(device="cuda").manual_seed(5 + n)
     G = torch.randn((count, n, n), generator=gen, device="cuda")
@@ -512,7 +512,7 @@ def test_api_misuse_returns_codes_never_exits(qp):
     assert lib.qp_solve_batch(None, C.byref(sol), None) == api.QP_ERR_INVALID
     pb.n, pb.count, pb.mem = 0, 1, api.MEM_DEVICE
     assert lib.qp_solve_batch(C.byref(pb), C.byref(sol), None) == api.QP_ERR_INVALID
-    pb.n = 65
+    pb.n = api.QP_MAX_DIM_BOX + 1
     assert lib.qp_solve_batch(C.byref(pb), C.byref(sol), None) == api.QP_ERR_UNSUPPORTED
     pb.n, pb.P, pb.q = 16, None, None
     assert lib.qp_solve_batch(C.byref(pb), C.byref(sol), None) == api.QP_ERR_INVALID
@@ -655,7 +655,7 @@ def _random_device_batch(count, n, seed):
     return P, torch.randn((count, n), generator=gen, device="cuda")
 
 
-def _sample_against_oracle(orc, res, P, q, beta, picks, **kw):
+def _sample_against_oracle(orc, res, P, q, beta, picks, x_max=X_TOL, **kw):
     idx = torch.randint(0, P.shape[0], (picks,), generator=torch.Generator().manual_seed(3)).cuda()
     o = orc.admm(P[idx].cpu().numpy().astype(np.float64), q[idx].cpu().numpy().astype(np.float64),
                  -beta, beta, **{k: v[idx].cpu().numpy().astype(np.float64) for k, v in kw.items()})
@@ -666,7 +666,8 @@ def _sample_against_oracle(orc, res, P, q, beta, picks, **kw):
     zr, zo = res["z"][idx].cpu().numpy()[ok], o["z"][ok].astype(np.float32)
     b = np.float32(beta)
     assert np.array_equal(active_set(zr, -b, b), active_set(zo, -b, b))
-    assert rel_err(res["x"][idx].cpu().numpy()[ok].astype(np.float64), o["x"][ok]).max() <= X_TOL
+    e = rel_err(res["x"][idx].cpu().numpy()[ok].astype(np.float64), o["x"][ok])
+    assert e.max() <= x_max and (e > X_TOL).mean() <= 0.005
 
 
 def test_full_size_config_n4(qp, orc):
@@ -697,7 +698,10 @@ def test_full_size_config_mpc_n40(qp, orc):
     for k in ("x", "z", "lam", "iters"):
         v = r[k].reshape(reps, 4096, -1)
         assert torch.equal(v, v[:1].expand_as(v)), k
-    _sample_against_oracle(orc, r, P, q, beta, 300)
+    # cond(P + rho I) reaches 1.2e4 on this set: the reference's own algorithm run in binary32
+    # (oracle, dtype=float32) is off by up to 1.1e-4 on the worst problems, and so are the
+    # kernels (tools/mpc_accuracy.py); the bar is 1e-4 on 99.5 % and 2e-4 on all
+    _sample_against_oracle(orc, r, P, q, beta, 300, x_max=2e-4)
 
 
 def test_full_size_config_warm_n64(qp, orc):
@@ -717,3 +721,34 @@ def test_full_size_config_warm_n64(qp, orc):
     # both runs stop inside the same tolerance ball around the one minimiser
     assert float((warm["z"] - cold["z"]).abs().max()) <= 2e-2
     _sample_against_oracle(orc, warm, P, q2, 0.5, 200, z0=z0, u0=u0)
+
+
+def test_ill_conditioned_mpc_set_every_family(qp, orc):
+    """The 4096 condensed-MPC problems (cond up to 1.2e4) through every family that takes
+    n = 40: the x error against the FP64 oracle must stay at the level of the reference
+    algorithm in binary32 (1.1e-4 worst case).  Guards the block Gauss-Jordan: multipliers
+    by L D L^T solves and pivot rows published as they are (an explicit 4x4 inverse or rows
+    rebuilt from columns by symmetry give 1.5e-3 ... 4e-3 here)."""
+    P, q, lb, ub = problems.mpc(4096, seed=2026)
+    beta = float(ub[0, 0])
+    o = orc.admm(P.astype(np.float64), q.astype(np.float64), -beta, beta)
+    tP, tq = dev(P, q)
+    for kern in (qp.KERNEL_BPQ, qp.KERNEL_GPQ, qp.KERNEL_CPQ):
+        r = qp.solve_batch(tP, tq, -beta, beta, options=qp.Options(kernel=kern))
+        torch.cuda.synchronize()
+        same = r["iters"].cpu().numpy() == o["iters"]
+        assert same.mean() > 0.995
+        e = rel_err(r["x"].cpu().numpy().astype(np.float64), o["x"])[same]
+        assert e.max() <= 2e-4 and (e > X_TOL).sum() <= 4, (kern, e.max(), (e > X_TOL).sum())
+    # warm-started re-solve takes the product-form variants (bpq: warm start; gpq: n >= 48 only)
+    z0, u0 = r["z"], r["lam"]
+    q2 = problems.perturb_q(q, seed=3)
+    o2 = orc.admm(P.astype(np.float64), q2.astype(np.float64), -beta, beta,
+                  z0=z0.cpu().numpy().astype(np.float64), u0=u0.cpu().numpy().astype(np.float64))
+    r2 = qp.solve_batch(tP, torch.from_numpy(q2).cuda(), -beta, beta, z0=z0, u0=u0,
+                        options=qp.Options(kernel=qp.KERNEL_BPQ))
+    torch.cuda.synchronize()
+    same = r2["iters"].cpu().numpy() == o2["iters"]
+    assert same.mean() > 0.99
+    e = rel_err(r2["x"].cpu().numpy().astype(np.float64), o2["x"])[same]
+    assert e.max() <= 2e-4 and (e > X_TOL).sum() <= 4, (e.max(), (e > X_TOL).sum())
