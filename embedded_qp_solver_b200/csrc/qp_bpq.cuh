@@ -17,10 +17,11 @@
 //     elimination is FFMA2 with the pair of multipliers (H) in registers and the pivot
 //     value as the scalar broadcast operand;
 //   * a 4x4 pivot block lies in ONE lane, all four register slots, so the block loop needs
-//     no per-slot split.  The pivot rows are published by ALL lanes at once, each writing
-//     the 4x4 block it knows by the (signed) symmetry of the Gauss-Jordan intermediate;
-//     the owner then turns its rows into -I_4 so that the common update produces
-//     B^-1 x (pivot rows) for it;
+//     no per-slot split.  The owner of the next step publishes its rows chunk by chunk
+//     while the current step finishes them (position-major buffer: one 128-bit store per
+//     column), then turns its rows into -I_4 so that the common update produces
+//     B^-1 x (pivot rows) for it.  The multipliers -C B^-1 come from two triangular
+//     solves with the L D L^T of the pivot block, not from an explicit inverse;
 //   * loads, stores and the per-coordinate vectors are 128-bit per lane: lane g reads
 //     P[j][4g..4g+3] (column block of the symmetric P = row block), q/lb/ub/z0/u0[4g..4g+3],
 //     and writes x/z/lambda[4g..4g+3];
@@ -98,7 +99,7 @@ __global__ void __launch_bounds__(BPQ_WARPS * 32, BpqCfg<NP>::MINB)
 qp_bpq_kernel(const KernelArgs p)
 {
 	using C = BpqCfg<NP>;
-	constexpr int T = C::T, G = C::G, ROW = C::ROW;
+	constexpr int T = C::T, G = C::G;
 	constexpr unsigned FULL = 0xffffffffu;
 	__shared__ __align__(16) float sm[BPQ_WARPS * C::GG * C::GROUP];
 	__shared__ float4 ctab[5]; // columns of -I_4, then a zero vector
@@ -160,36 +161,37 @@ qp_bpq_kernel(const KernelArgs p)
 		constexpr int NC = NP / 4;
 		constexpr int SEG = PFI ? 4 : NC;
 		constexpr int NSEG = (NC + SEG - 1) / SEG;
+		// chunk c of my four rows -> the pivot-row buffer (position-major: dst[4 * position + m])
+		auto publish_chunk = [&](float *dst, int c) {
+#pragma unroll
+			for (int t = 0; t < 4; ++t)
+				*reinterpret_cast<float4 *>(dst + 4 * (4 * c + t)) =
+					make_float4(S[0][4 * c + t].x, S[0][4 * c + t].y, S[1][4 * c + t].x, S[1][4 * c + t].y);
+		};
+		if (g == 0) {
+#pragma unroll
+			for (int c = 0; c < NC; ++c)
+				publish_chunk(bc, c);
+		}
 #pragma unroll
 		for (int seg = 0; seg < NSEG; ++seg) {
 		const int Kseg = (seg + 1) * SEG < NC ? (seg + 1) * SEG : NC;
 		const int Lmax = PFI ? NC - seg * SEG : NC, Lmin = PFI ? NC - (Kseg - 1) : NC;
 		for (int K = seg * SEG; K < Kseg; ++K) {
 			const int L = PFI ? NC - K : NC;
-			float *pb = bc + (K & 1) * C::BUF; // pb[m * ROW + position]: pivot row m
-			// The owner publishes its four rows as they are.  (The intermediate matrix of
-			// Gauss-Jordan is symmetric up to sign, so every lane could publish the entries of
-			// the pivot rows at its own columns from its first four columns -- four stores per
-			// lane instead of forty by one.  That was measured 5 % faster and is NOT done: rows
-			// filled in from other rows' columns break the row-operation invariant R A = I,
-			// and on ill-conditioned problems the left residual grows a hundredfold,
-			// profiles/README.md "block pivot accuracy".)  In product form only the first L
-			// chunks are still matrix columns.
-			if (g == K) {
-#pragma unroll
-				for (int c = 0; c < NC; ++c) {
-					if (c < Lmin || c < L) {
-						*reinterpret_cast<float4 *>(pb + 0 * ROW + 4 * c) = make_float4(
-							S[0][4 * c].x, S[0][4 * c + 1].x, S[0][4 * c + 2].x, S[0][4 * c + 3].x);
-						*reinterpret_cast<float4 *>(pb + 1 * ROW + 4 * c) = make_float4(
-							S[0][4 * c].y, S[0][4 * c + 1].y, S[0][4 * c + 2].y, S[0][4 * c + 3].y);
-						*reinterpret_cast<float4 *>(pb + 2 * ROW + 4 * c) = make_float4(
-							S[1][4 * c].x, S[1][4 * c + 1].x, S[1][4 * c + 2].x, S[1][4 * c + 3].x);
-						*reinterpret_cast<float4 *>(pb + 3 * ROW + 4 * c) = make_float4(
-							S[1][4 * c].y, S[1][4 * c + 1].y, S[1][4 * c + 2].y, S[1][4 * c + 3].y);
-					}
-				}
-			}
+			const float *pb = bc + (K & 1) * C::BUF; // pb[4 * position + m]: pivot row m
+			float *pn = bc + ((K + 1) & 1) * C::BUF; // the rows of step K + 1 are collected here
+			const bool nowner = (K + 1 < NC) && (g == K + 1);
+			// The owner of step K + 1 publishes its four rows as they are, chunk by chunk as
+			// step K finishes them, so that the stores overlap step K's arithmetic.  (The
+			// intermediate matrix of Gauss-Jordan is symmetric up to sign, so every lane could
+			// publish the entries of the pivot rows at its own columns from its first four
+			// columns -- four stores per lane instead of forty by one lane.  That was 11 %
+			// faster at n = 40 and is NOT done: rows rebuilt from other rows' columns break the
+			// row-operation invariant R A = I, and on ill-conditioned problems the left
+			// residual grows a hundredfold; profiles/README.md "block pivot accuracy".)  In
+			// product form only the first L chunks are still matrix columns.
+			__syncwarp();
 			if (g == K) {
 				// my four rows become -I_4, so that the common update below produces
 				// B^-1 x (pivot rows) for them (constants from shared memory: one 128-bit
@@ -202,13 +204,12 @@ qp_bpq_kernel(const KernelArgs p)
 					}
 				}
 			}
-			__syncwarp();
 			// pivot block (B[m][j] = pivot row m at column j) and its L D L^T
 			float B[4][4];
 #pragma unroll
-			for (int m = 0; m < 4; ++m) {
-				const float4 v = *reinterpret_cast<const float4 *>(pb + m * ROW);
-				B[m][0] = v.x, B[m][1] = v.y, B[m][2] = v.z, B[m][3] = v.w;
+			for (int j = 0; j < 4; ++j) {
+				const float4 v = *reinterpret_cast<const float4 *>(pb + 4 * j);
+				B[0][j] = v.x, B[1][j] = v.y, B[2][j] = v.z, B[3][j] = v.w;
 			}
 			Ldl4 Bf;
 			bad |= ldl4_factor(B, Bf);
@@ -221,24 +222,27 @@ qp_bpq_kernel(const KernelArgs p)
 						  H[2][rp], H[3][rp]);
 			// S(:, j-4) <- S(:, j) + H * pivot_rows(:, j)
 			auto update_chunk = [&](int c) {
-				float4 pr[4];
+				float4 pr[4]; // pr[t] = the four pivot rows at position 4c + t
 #pragma unroll
-				for (int m = 0; m < 4; ++m)
-					pr[m] = *reinterpret_cast<const float4 *>(pb + m * ROW + 4 * c);
+				for (int t = 0; t < 4; ++t)
+					pr[t] = *reinterpret_cast<const float4 *>(pb + 4 * (4 * c + t));
 #pragma unroll
 				for (int rp = 0; rp < 2; ++rp) {
 					float2 a0 = S[rp][4 * c], a1 = S[rp][4 * c + 1], a2 = S[rp][4 * c + 2],
 					       a3 = S[rp][4 * c + 3];
-#pragma unroll
-					for (int m = 0; m < 4; ++m) {
-						a0 = fma2_bc(H[m][rp], pr[m].x, a0);
-						a1 = fma2_bc(H[m][rp], pr[m].y, a1);
-						a2 = fma2_bc(H[m][rp], pr[m].z, a2);
-						a3 = fma2_bc(H[m][rp], pr[m].w, a3);
-					}
+					a0 = fma2_bc(H[0][rp], pr[0].x, a0), a1 = fma2_bc(H[0][rp], pr[1].x, a1);
+					a2 = fma2_bc(H[0][rp], pr[2].x, a2), a3 = fma2_bc(H[0][rp], pr[3].x, a3);
+					a0 = fma2_bc(H[1][rp], pr[0].y, a0), a1 = fma2_bc(H[1][rp], pr[1].y, a1);
+					a2 = fma2_bc(H[1][rp], pr[2].y, a2), a3 = fma2_bc(H[1][rp], pr[3].y, a3);
+					a0 = fma2_bc(H[2][rp], pr[0].z, a0), a1 = fma2_bc(H[2][rp], pr[1].z, a1);
+					a2 = fma2_bc(H[2][rp], pr[2].z, a2), a3 = fma2_bc(H[2][rp], pr[3].z, a3);
+					a0 = fma2_bc(H[3][rp], pr[0].w, a0), a1 = fma2_bc(H[3][rp], pr[1].w, a1);
+					a2 = fma2_bc(H[3][rp], pr[2].w, a2), a3 = fma2_bc(H[3][rp], pr[3].w, a3);
 					S[rp][4 * c - 4] = a0, S[rp][4 * c - 3] = a1, S[rp][4 * c - 2] = a2,
 						      S[rp][4 * c - 1] = a3;
 				}
+				if (nowner)
+					publish_chunk(pn, c - 1);
 			};
 			auto place_eta = [&](int c) { // chunk c <- H
 #pragma unroll
@@ -257,8 +261,11 @@ qp_bpq_kernel(const KernelArgs p)
 				} else if (c == Lmax && c == L)
 					place_eta(c - 1);
 			}
-			if (Lmax == NC && L == NC)
+			if (Lmax == NC && L == NC) {
 				place_eta(NC - 1);
+				if (!PFI && nowner) // full inverse: the eta columns are matrix columns again
+					publish_chunk(pn, NC - 1);
+			}
 		}
 		}
 		__syncwarp();
