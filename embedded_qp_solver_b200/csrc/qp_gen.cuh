@@ -22,7 +22,8 @@
 //
 // Correctness-first kernel: P + rho A'A, its inverse R and A live in shared memory; lanes
 // own coordinates i = lane, lane + 32 and rows j = lane + 32 k.  A'z and A'u are carried
-// along, so an iteration costs one mat-vec with R, one with A and two with A'.
+// along, so an iteration costs one mat-vec with R, one with A and one pass over A for A'z
+// and A'u together.
 #pragma once
 
 #include "qp_common.cuh"
@@ -122,15 +123,22 @@ __global__ void __launch_bounds__(GEN_WARPS * 32) qp_gen_kernel(const GenArgs a)
 			}
 			o0 = s0, o1 = s1;
 		};
-		// coordinates i0, i1 of A' v for an m-vector in shared memory
-		auto at_times = [&](const float *v, float &o0, float &o1) {
-			float s0 = 0.f, s1 = 0.f;
+		// A' v and A' w in one pass over A
+		auto at_times2 = [&](const float *v, const float *w, float &a0, float &a1, float &b0,
+				     float &b1) {
+			float s0 = 0.f, s1 = 0.f, t0 = 0.f, t1 = 0.f;
 			for (int k = 0; k < m; ++k) {
-				const float vk = v[k];
-				if (h0) s0 = fmaf(As[k * ld + i0], vk, s0);
-				if (h1) s1 = fmaf(As[k * ld + i1], vk, s1);
+				const float vk = v[k], wk = w[k];
+				if (h0) {
+					const float e = As[k * ld + i0];
+					s0 = fmaf(e, vk, s0), t0 = fmaf(e, wk, t0);
+				}
+				if (h1) {
+					const float e = As[k * ld + i1];
+					s1 = fmaf(e, vk, s1), t1 = fmaf(e, wk, t1);
+				}
 			}
-			o0 = s0, o1 = s1;
+			a0 = s0, a1 = s1, b0 = t0, b1 = t1;
 		};
 
 		// A'z and A'u of the starting point
@@ -141,8 +149,7 @@ __global__ void __launch_bounds__(GEN_WARPS * 32) qp_gen_kernel(const GenArgs a)
 				if (lane + 32 * k < m)
 					vm0[lane + 32 * k] = z[k], vm1[lane + 32 * k] = u[k];
 			__syncwarp();
-			at_times(vm0, w1a, w1b);
-			at_times(vm1, w2a, w2b);
+			at_times2(vm0, vm1, w1a, w1b, w2a, w2b);
 			__syncwarp();
 		}
 
@@ -182,8 +189,7 @@ __global__ void __launch_bounds__(GEN_WARPS * 32) qp_gen_kernel(const GenArgs a)
 				}
 				__syncwarp();
 				float n1a, n1b, n2a, n2b;
-				at_times(vm0, n1a, n1b); // A'z
-				at_times(vm1, n2a, n2b); // A'u
+				at_times2(vm0, vm1, n1a, n1b, n2a, n2b); // A'z, A'u
 				const float da = n1a - w1a, db = n1b - w1b;
 				float ss = fmaf(da, da, db * db), nu = fmaf(n2a, n2a, n2b * n2b);
 				w1a = n1a, w1b = n1b, w2a = n2a, w2b = n2b;

@@ -180,7 +180,7 @@ def test_resolving_from_the_solution_is_idempotent(qp):
     assert np.max(np.abs(a["z"] - b["z"])) <= 1e-5
 
 
-@pytest.mark.parametrize("n", [4, 16, 40, 64])
+@pytest.mark.parametrize("n", [4, 16, 40, 64, 100])
 def test_kkt_at_tight_tolerance(qp, n):
     """north_star: KKT residual <= 1e-5 (relative).  With the reference's loose
     reltol = 1e-2 the iterate is not yet a KKT point, so the KKT test runs the
@@ -752,3 +752,34 @@ def test_ill_conditioned_mpc_set_every_family(qp, orc):
     assert same.mean() > 0.99
     e = rel_err(r2["x"].cpu().numpy().astype(np.float64), o2["x"])[same]
     assert e.max() <= 2e-4 and (e > X_TOL).sum() <= 4, (e.max(), (e > X_TOL).sum())
+
+
+# ---- matrix_invert, observed through one iteration ------------------------
+
+@pytest.mark.parametrize("family,n", [("tpq", 16), ("bpq", 40), ("gpq", 40), ("gpq", 64), ("cpq", 100)])
+def test_inverse_against_the_oracles_matrix_invert(qp, orc, family, n):
+    """With z = u = 0 the first x-update is x = -(P + rho I)^-1 q (qp_solvers.c:146-159), so n
+    problems that share P and have q = -e_i return the columns of the inverse the kernel
+    formed: compared with the oracle's matrix_invert (LU with partial pivoting,
+    matrix_ops.c:551-630) and with the reference's own inversion_test property
+    A * invert(A) = I (test/test.c:37-57; 1e-6 there in binary64, cond * 2^-23 here)."""
+    kern = {"tpq": qp.KERNEL_TPQ, "bpq": qp.KERNEL_BPQ, "gpq": qp.KERNEL_GPQ,
+            "cpq": qp.KERNEL_CPQ}[family]
+    for gen, seed in ((problems.wellcond, 31), (problems.mpc if n == 40 else problems.wellcond, 32)):
+        if gen is problems.mpc:
+            P1 = gen(4, seed=seed)[0][3]
+        else:
+            P1 = gen(1, n, seed=seed, beta=0.5)[0][0]
+        A = P1.astype(np.float64) + np.eye(n)
+        Rref, sing = orc.invert(A)
+        assert sing == 0
+        P = np.repeat(P1[None], n, axis=0)
+        q = -np.eye(n, dtype=np.float32)
+        tP, tq = dev(P, q)
+        r = qp.solve_batch(tP, tq, -1e12, 1e12, options=qp.Options(kernel=kern, max_iter=1))
+        torch.cuda.synchronize()
+        R = r["x"].cpu().numpy().astype(np.float64).T          # column i = x of problem i
+        cond = np.linalg.cond(A)
+        scale = np.abs(Rref).max()
+        assert np.abs(R - Rref).max() <= 20 * cond * 2.0 ** -24 * scale, (family, n, cond)
+        assert np.abs(R @ A - np.eye(n)).max() <= 20 * cond * 2.0 ** -24, (family, n, cond)
