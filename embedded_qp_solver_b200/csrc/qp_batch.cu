@@ -563,15 +563,16 @@ bool host_pack_enabled()
 //
 // Packing trades PCIe bytes for host-memory traffic (about 2.1 KB instead of 1.1 KB per
 // problem at n = 16), so it only pays while the host's DRAM is not the shared bottleneck:
-// it is used for at most two GPUs per host -- counting the ranks of a torchrun job
-// (LOCAL_WORLD_SIZE) -- and needs 12 hardware threads per GPU.
+// it is used when ONE GPU is fed from this host -- counting the ranks of a torchrun job
+// (LOCAL_WORLD_SIZE) and the devices of this process -- and needs 12 hardware threads.
+// Measured with two ranks on a 24-thread host: 68.9 M QP/s packed against 92.2 M plain.
 static unsigned host_threads_per_gpu(unsigned gpus_in_this_process)
 {
 	unsigned ranks = 1;
 	if (const char *e = std::getenv("LOCAL_WORLD_SIZE"))
 		ranks = unsigned(std::max(1, std::atoi(e)));
 	const unsigned sharers = std::max(1u, ranks * std::max(1u, gpus_in_this_process));
-	if (sharers > 2)
+	if (sharers > 1)
 		return 0;
 	return std::thread::hardware_concurrency() / sharers;
 }
