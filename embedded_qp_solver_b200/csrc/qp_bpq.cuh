@@ -194,13 +194,19 @@ qp_bpq_kernel(const KernelArgs p)
 			__syncwarp();
 			if (g == K) {
 				// my four rows become -I_4, so that the common update below produces
-				// B^-1 x (pivot rows) for them (constants from shared memory: one 128-bit
-				// load per column)
+				// B^-1 x (pivot rows) for them.  Register moves: the kernel is bound by the
+				// shared-memory pipe, and filling from a constant table in shared memory
+				// (-DQPB_BPQ_LDS_FILL, faster in qp_gpq.cuh) costs 2-4 % here.
 #pragma unroll
 				for (int j = 0; j < NP; ++j) {
 					if (j / 4 < Lmin || j / 4 < L) {
+#ifdef QPB_BPQ_LDS_FILL
 						const float4 c = lds128_volatile(&ctab[j < 4 ? j : 4]);
 						S[0][j] = make_float2(c.x, c.y), S[1][j] = make_float2(c.z, c.w);
+#else
+						S[0][j] = make_float2(j == 0 ? -1.0f : 0.0f, j == 1 ? -1.0f : 0.0f);
+						S[1][j] = make_float2(j == 2 ? -1.0f : 0.0f, j == 3 ? -1.0f : 0.0f);
+#endif
 					}
 				}
 			}
