@@ -783,3 +783,65 @@ def test_inverse_against_the_oracles_matrix_invert(qp, orc, family, n):
         scale = np.abs(Rref).max()
         assert np.abs(R - Rref).max() <= 20 * cond * 2.0 ** -24 * scale, (family, n, cond)
         assert np.abs(R @ A - np.eye(n)).max() <= 20 * cond * 2.0 ** -24, (family, n, cond)
+
+
+# ---- seeded sweep over every dimension and option combination -----------------------------------
+
+@pytest.mark.parametrize("block", range(8))
+def test_sweep_of_dimensions_and_options(qp, orc, block):
+    """Every n from 1 to 128 (16 per block) with a seeded random choice of batch size, box
+    form (scalar / arrays), warm start, over-relaxation, rho (option / per problem) and
+    pointer alignment, against the oracle: catches a shape or option pair that the
+    per-family tests happen not to combine."""
+    rng = np.random.default_rng(900 + block)
+    for n in range(16 * block + 1, 16 * block + 17):
+        count = int(rng.integers(1, 70))
+        P, q, lb, ub = problems.wellcond(count, n, seed=5000 + n, beta=0.5)
+        arrays = bool(rng.integers(0, 2))
+        warm = bool(rng.integers(0, 2))
+        alpha = float(rng.choice([1.0, 1.0, 1.4, 1.7]))
+        per_rho = bool(rng.integers(0, 2))
+        rho = float(rng.choice([0.6, 1.0, 2.0]))
+        misalign = bool(rng.integers(0, 4) == 0)
+        if arrays:
+            lb = (-rng.uniform(0.05, 1.0, (count, n))).astype(np.float32)
+            ub = rng.uniform(0.05, 1.0, (count, n)).astype(np.float32)
+        z0 = u0 = None
+        if warm:
+            z0 = np.clip(rng.normal(0, 0.3, (count, n)), lb, ub).astype(np.float32)
+            u0 = rng.normal(0, 0.1, (count, n)).astype(np.float32)
+        kw64 = {}
+        if warm:
+            kw64 = dict(z0=z0.astype(np.float64), u0=u0.astype(np.float64))
+        o = orc.admm(P.astype(np.float64), q.astype(np.float64), lb.astype(np.float64),
+                     ub.astype(np.float64), rho=rho, alpha=alpha, **kw64)
+
+        def put(a):
+            if a is None:
+                return None
+            t = torch.from_numpy(np.ascontiguousarray(a))
+            if misalign:  # 4-byte aligned only: one float into a larger buffer
+                buf = torch.empty(t.numel() + 1, dtype=t.dtype, device="cuda")
+                v = buf[1:].view(t.shape)
+                v.copy_(t)
+                return v
+            return t.cuda()
+
+        kw = dict(options=qp.Options(rho=rho, alpha=alpha))
+        if per_rho:
+            kw["rho"] = torch.full((count,), rho, device="cuda")
+        if arrays:
+            r = qp.solve_batch(put(P), put(q), put(lb), put(ub), z0=put(z0), u0=put(u0), **kw)
+        else:
+            r = qp.solve_batch(put(P), put(q), -0.5, 0.5, z0=put(z0), u0=put(u0), **kw)
+        torch.cuda.synchronize()
+        what = dict(n=n, count=count, arrays=arrays, warm=warm, alpha=alpha, rho=rho,
+                    per_rho=per_rho, misalign=misalign)
+        ok = nondegenerate(o["margins"]) & (o["status"] == 0)
+        assert np.array_equal(r["status"].cpu().numpy()[ok], o["status"][ok]), what
+        assert np.array_equal(r["iters"].cpu().numpy()[ok], o["iters"][ok]), what
+        if ok.any():
+            e = rel_err(r["x"].cpu().numpy()[ok].astype(np.float64), o["x"][ok])
+            assert e.max() <= X_TOL, (what, e.max())
+            lam = r["lam"].cpu().numpy()[ok]
+            assert np.max(np.abs(lam - rho * o["u"][ok])) <= 2e-3, what
