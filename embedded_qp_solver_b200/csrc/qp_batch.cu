@@ -1257,25 +1257,38 @@ extern "C" int qp_gradient_batch(const qp_batch *pb, const float *x0, unsigned i
 // ----------------------------------------------------------------------------------------
 // general rows l <= A x <= u (qp_gen.cuh)
 // ----------------------------------------------------------------------------------------
-static int launch_gen(const GenArgs &a, int dev, cudaStream_t st)
+template <int T> static int launch_gen_t(const GenArgs &a, int dev, cudaStream_t st)
 {
-	const size_t smem = GEN_WARPS * gen_smem_floats_per_warp(a.n, a.m) * sizeof(float);
-	const size_t smem_max = GEN_WARPS * gen_smem_floats_per_warp(QP_MAX_DIM, QP_MAX_ROWS) * sizeof(float);
+	constexpr int G = 32 / T;
+	const size_t smem = GEN_WARPS * G * gen_smem_floats_per_group(a.n, a.m, T) * sizeof(float);
+	// the largest problem this group width takes: n = 2T, m = 4T
+	const size_t smem_max = GEN_WARPS * G * gen_smem_floats_per_group(2 * T, 4 * T, T) * sizeof(float);
 	static bool attr_done[64] = {};
 	if (!attr_done[dev]) {
-		QP_CUDA(cudaFuncSetAttribute(qp_gen_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+		QP_CUDA(cudaFuncSetAttribute(qp_gen_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
 					     int(smem_max)));
 		attr_done[dev] = true;
 	}
 	int per_sm = 1;
-	QP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, qp_gen_kernel, GEN_WARPS * 32, smem));
+	QP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, qp_gen_kernel<T>, GEN_WARPS * 32, smem));
 	per_sm = std::max(1, per_sm);
-	const unsigned long long need = (a.count + GEN_WARPS - 1) / GEN_WARPS;
+	const unsigned long long per_cta = GEN_WARPS * G;
+	const unsigned long long need = (a.count + per_cta - 1) / per_cta;
 	const unsigned long long grid =
 		std::max(1ull, std::min((unsigned long long)dev_sms(dev) * per_sm, need));
-	qp_gen_kernel<<<dim3((unsigned)grid), dim3(GEN_WARPS * 32), smem, st>>>(a);
+	qp_gen_kernel<T><<<dim3((unsigned)grid), dim3(GEN_WARPS * 32), smem, st>>>(a);
 	QP_CUDA(cudaGetLastError());
 	return QP_OK;
+}
+
+static int launch_gen(const GenArgs &a, int dev, cudaStream_t st)
+{
+	switch (gen_lanes(a.n, a.m)) {
+	case 4:  return launch_gen_t<4>(a, dev, st);
+	case 8:  return launch_gen_t<8>(a, dev, st);
+	case 16: return launch_gen_t<16>(a, dev, st);
+	}
+	return launch_gen_t<32>(a, dev, st);
 }
 
 extern "C" int qp_solve_general_batch(const qp_general_batch *pb, const qp_general_solution *sol,

@@ -50,9 +50,11 @@ def test_identity_rows_reproduce_the_reference_golden_vectors(qp, name):
     assert rel_err(b["x"][ok].astype(np.float64), r["x"][ok].astype(np.float64)).max() <= X_TOL
 
 
-@pytest.mark.parametrize("n,m", [(4, 8), (16, 32), (5, 3), (40, 80), (64, 128), (33, 70)])
+@pytest.mark.parametrize("n,m", [(4, 8), (16, 32), (5, 3), (40, 80), (64, 128), (33, 70),
+                                 (8, 16), (9, 16), (24, 48), (20, 64), (32, 65), (1, 1)])
 def test_general_rows_against_the_numpy_restatement(qp, n, m):
-    count = 40 if n <= 16 else 10
+    # counts that leave the last warp's groups ragged (4, 8, 16 or 32 lanes per problem)
+    count = 43 if n <= 16 else 11
     P, q, _, _ = problems.wellcond(count, n, seed=2000 + n)
     A, l, u = random_rows(count, n, m, seed=n)
     o = general_np.admm_general_batch(P, q, A, l, u)
