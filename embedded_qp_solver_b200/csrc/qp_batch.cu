@@ -17,6 +17,7 @@
 //                  No collective anywhere: problems are independent.
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <cstdlib>
 #include <functional>
@@ -448,8 +449,15 @@ public:
 		done_.wait(lk, [this] { return pending_ == 0; }); // a previous call that returned early
 		body_ = std::move(body);
 		pending_ = unsigned(workers_.size());
+		t0_ = std::chrono::steady_clock::now();
 		++gen_;
 		cv_.notify_all();
+	}
+	// seconds from start() to the last worker's return, of the call that finished last
+	double last_seconds()
+	{
+		std::lock_guard<std::mutex> lk(mu_);
+		return last_s_;
 	}
 	void wait()
 	{
@@ -474,8 +482,10 @@ private:
 				body_(id, unsigned(workers_.size()));
 			{
 				std::lock_guard<std::mutex> lk(mu_);
-				if (--pending_ == 0)
+				if (--pending_ == 0) {
+					last_s_ = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0_).count();
 					done_.notify_all();
+				}
 			}
 		}
 	}
@@ -486,6 +496,8 @@ private:
 	unsigned pending_ = 0;
 	unsigned long gen_ = 0;
 	bool stop_ = false;
+	std::chrono::steady_clock::time_point t0_;
+	double last_s_ = 0.0;
 };
 
 // upper triangle (row-major, i <= j) of `count` n x n matrices, `pk` floats apart.
@@ -556,6 +568,16 @@ bool host_pack_enabled()
 	return on;
 }
 
+// QPB200_HOST_PACK=2: pack regardless of the timing (measurements)
+bool host_pack_forced()
+{
+	static const bool on = [] {
+		const char *e = std::getenv("QPB200_HOST_PACK");
+		return e && e[0] == '2';
+	}();
+	return on;
+}
+
 } // namespace
 
 // One core packs ~10 GB/s and the copy engine wants ~85 GB/s of it: with fewer than 12
@@ -577,9 +599,13 @@ static unsigned host_threads_per_gpu(unsigned gpus_in_this_process)
 	return std::thread::hardware_concurrency() / sharers;
 }
 
+// set when a workspace of this process gave packing up (see run_shard)
+static std::atomic<bool> g_pack_given_up{false};
+
 extern "C" int qp_host_path_packs(uint32_t n)
 {
-	return host_pack_enabled() && (n == 8 || n == 12 || n == 16) && host_threads_per_gpu(1) >= 12;
+	return host_pack_enabled() && !g_pack_given_up.load() && (n == 8 || n == 12 || n == 16) &&
+	       host_threads_per_gpu(1) >= 12;
 }
 
 // ----------------------------------------------------------------------------------------
@@ -599,15 +625,22 @@ struct Slot {
 	float *hpk = nullptr;  // packed upper triangles of P (pinned), n = 8, 12, 16
 	cudaStream_t stream = nullptr;
 	cudaEvent_t done = nullptr;
+	cudaEvent_t t0 = nullptr, t1 = nullptr; // around the copy of the packed triangles
 	// bookkeeping of the chunk in flight
 	size_t first = 0, cnt = 0;
 	bool busy = false;
+	bool timed = false; // t0, t1 were recorded for the chunk in flight
 };
 
 struct DeviceCtx {
 	int dev = 0;
 	Slot slot[DEPTH];
 	HostPool *pool = nullptr; // packing workers of this device's shard
+	// host-side packing is given up for this workspace when the workers turn out slower
+	// than the copy engine would be on the full matrices (a slow or busy host)
+	bool pack_off = false;
+	unsigned slow_chunks = 0;     // consecutive chunks whose packing took longer than that
+	double h2d_bytes_per_s = 0.0; // measured on the packed copies
 };
 
 struct qp_workspace {
@@ -668,6 +701,10 @@ void free_ctx(DeviceCtx &c)
 		cudaFreeHost(s.hpk);
 		if (s.done)
 			cudaEventDestroy(s.done);
+		if (s.t0)
+			cudaEventDestroy(s.t0);
+		if (s.t1)
+			cudaEventDestroy(s.t1);
 		if (s.stream)
 			cudaStreamDestroy(s.stream);
 		s = Slot();
@@ -702,6 +739,8 @@ int alloc_ctx(DeviceCtx &c, uint32_t n, size_t chunk)
 		s.diters = s.dstatus + chunk;
 		QP_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
 		QP_CUDA(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+		QP_CUDA(cudaEventCreate(&s.t0));
+		QP_CUDA(cudaEventCreate(&s.t1));
 	}
 	return QP_OK;
 }
@@ -737,6 +776,12 @@ int run_shard(qp_workspace *ws, DeviceCtx &ctx, const qp_batch &pb, const qp_bat
 		if (!s.busy)
 			return QP_OK;
 		QP_CUDA(cudaEventSynchronize(s.done));
+		if (s.timed) {
+			float ms = 0.0f;
+			if (cudaEventElapsedTime(&ms, s.t0, s.t1) == cudaSuccess && ms > 0.0f)
+				ctx.h2d_bytes_per_s = double(s.cnt) * tpq_packed_stride(int(n)) * 4.0 / (ms * 1e-3);
+			s.timed = false;
+		}
 		if (!pin_out) {
 			const size_t c = s.cnt, f = s.first;
 			const float *h = s.hout;
@@ -758,11 +803,11 @@ int run_shard(qp_workspace *ws, DeviceCtx &ctx, const qp_batch &pb, const qp_bat
 
 	// pack the upper triangles of P on the host when the thread-per-QP kernel will run
 	const unsigned tpg = host_threads_per_gpu(unsigned(ws->devs.size()));
-	const bool pack = qp_host_path_packs(n) && tpg >= 12 &&
+	const bool pack0 = !ctx.pack_off && qp_host_path_packs(n) && tpg >= 12 &&
 			  (opt.kernel == QP_KERNEL_AUTO || opt.kernel == QP_KERNEL_TPQ) &&
 			  ((pb.lb == nullptr) == (pb.ub == nullptr)) && ((pb.z0 == nullptr) == (pb.u0 == nullptr));
 	const int pk = tpq_packed_stride(int(n));
-	if (pack && !ctx.pool)
+	if (pack0 && !ctx.pool)
 		// one core moves ~10 GB/s; PCIe wants ~85 GB/s of packing traffic: use the cores
 		ctx.pool = new HostPool(std::min(32u, tpg - 1));
 
@@ -784,19 +829,40 @@ int run_shard(qp_workspace *ws, DeviceCtx &ctx, const qp_batch &pb, const qp_bat
 		});
 		return QP_OK;
 	};
-	if (pack && lo < hi) {
+	bool next_packed = false; // the chunk about to be enqueued has been (is being) packed
+	if (pack0 && lo < hi) {
 		int rc = start_pack(0, lo);
 		if (rc != QP_OK)
 			return rc;
+		next_packed = true;
 	}
 
 	size_t k = 0;
 	for (size_t first = lo; first < hi; first += chunk, ++k) {
 		Slot &s = ctx.slot[k % DEPTH];
 		int rc = QP_OK;
+		const bool pack = next_packed;
 		if (pack) {
 			ctx.pool->wait(); // chunk k is packed (its slot was retired by start_pack)
-			if (first + chunk < hi)
+			// Packing pays while it takes less time than the copy engine would need for
+			// the full matrices of the same chunk; on a slow or busy host it does not
+			// (measured: 40.7 M QP/s packed where the plain copy gives 49 M).
+			if (!host_pack_forced() && ctx.h2d_bytes_per_s > 0.0 && std::min(chunk, hi - first) == chunk) {
+				if (std::getenv("QPB200_DEBUG"))
+					std::fprintf(stderr, "qpb200: pack %.3f ms, full copy %.3f ms at %.1f GB/s\n",
+						     ctx.pool->last_seconds() * 1e3,
+						     double(chunk) * n * n * 4.0 / ctx.h2d_bytes_per_s * 1e3,
+						     ctx.h2d_bytes_per_s * 1e-9);
+				const double t_full = double(chunk) * n * n * 4.0 / ctx.h2d_bytes_per_s;
+				// eight chunks in a row, so that one preempted worker does not decide
+				ctx.slow_chunks = ctx.pool->last_seconds() > 1.15 * t_full ? ctx.slow_chunks + 1 : 0;
+				if (ctx.slow_chunks >= 8) {
+					ctx.pack_off = true;
+					g_pack_given_up.store(true);
+				}
+			}
+			next_packed = !ctx.pack_off && first + chunk < hi;
+			if (next_packed)
 				rc = start_pack(k + 1, first + chunk);
 		} else {
 			rc = retire(s);
@@ -818,8 +884,12 @@ int run_shard(qp_workspace *ws, DeviceCtx &ctx, const qp_batch &pb, const qp_bat
 		} ins[] = { { pb.P, s.dP, size_t(n) * n }, { pb.q, s.dq, n },  { pb.lb, s.dlb, n },
 			    { pb.ub, s.dub, n },           { pb.z0, s.dz0, n }, { pb.u0, s.du0, n },
 			    { pb.rho, s.drho, 1 } };
-		if (pack)
+		if (pack) {
+			QP_CUDA(cudaEventRecord(s.t0, st));
 			QP_CUDA(cudaMemcpyAsync(s.dP, s.hpk, c * size_t(pk) * 4, cudaMemcpyHostToDevice, st));
+			QP_CUDA(cudaEventRecord(s.t1, st));
+			s.timed = true;
+		}
 		if (pin_in) {
 			for (const In &i : ins)
 				if (i.src && !(pack && i.src == pb.P))

@@ -293,9 +293,11 @@ int qp_problem_file_read(const char *path, size_t first, size_t count,
 			 uint32_t n, double *P, double *q);
 
 /* 1 when the QP_MEM_HOST path packs the upper triangles of P on the host before the copy
- * (n = 8, 12, 16, at least 12 hardware threads, QPB200_HOST_PACK != 0): P is symmetric and
- * the kernels read only its upper triangle, so 544 instead of 1 024 bytes per problem cross
- * PCIe at n = 16. */
+ * (n = 8, 12, 16, one GPU fed from this host, at least 12 hardware threads,
+ * QPB200_HOST_PACK != 0): P is symmetric and the kernels read only its upper triangle, so
+ * 544 instead of 1 024 bytes per problem cross PCIe at n = 16.  The library times the
+ * packing against the copy engine and gives it up for the rest of the process when the
+ * host turns out too slow for it to pay; the answer then turns to 0. */
 int qp_host_path_packs(uint32_t n);
 
 /* Diagnostics. */
