@@ -568,12 +568,23 @@ bool host_pack_enabled()
 	return on;
 }
 
-// QPB200_HOST_PACK=2: pack regardless of the timing (measurements)
+// QPB200_HOST_PACK=2: pack regardless of the timing (measurements);
+// QPB200_HOST_PACK=3: give packing up after three chunks regardless of the timing (tests of
+// the switch in the middle of a call)
 bool host_pack_forced()
 {
 	static const bool on = [] {
 		const char *e = std::getenv("QPB200_HOST_PACK");
 		return e && e[0] == '2';
+	}();
+	return on;
+}
+
+bool host_pack_test_switch()
+{
+	static const bool on = [] {
+		const char *e = std::getenv("QPB200_HOST_PACK");
+		return e && e[0] == '3';
 	}();
 	return on;
 }
@@ -847,6 +858,10 @@ int run_shard(qp_workspace *ws, DeviceCtx &ctx, const qp_batch &pb, const qp_bat
 			// Packing pays while it takes less time than the copy engine would need for
 			// the full matrices of the same chunk; on a slow or busy host it does not
 			// (measured: 40.7 M QP/s packed where the plain copy gives 49 M).
+			if (host_pack_test_switch() && k >= 2) {
+				ctx.pack_off = true;
+				g_pack_given_up.store(true);
+			}
 			if (!host_pack_forced() && ctx.h2d_bytes_per_s > 0.0 && std::min(chunk, hi - first) == chunk) {
 				if (std::getenv("QPB200_DEBUG"))
 					std::fprintf(stderr, "qpb200: pack %.3f ms, full copy %.3f ms at %.1f GB/s\n",

@@ -845,3 +845,32 @@ def test_sweep_of_dimensions_and_options(qp, orc, block):
             assert e.max() <= X_TOL, (what, e.max())
             lam = r["lam"].cpu().numpy()[ok]
             assert np.max(np.abs(lam - rho * o["u"][ok])) <= 2e-3, what
+
+
+def test_host_path_switching_from_packed_to_plain_copies_in_mid_call(qp):
+    """The host path gives the host-side packing of upper triangles up when the host is too
+    slow for it (qp_batch.cu, run_shard).  QPB200_HOST_PACK=3 forces that switch after three
+    chunks; the answers must not depend on it.  The variable is read once per process."""
+    import subprocess
+    import sys
+    code = r"""
+import numpy as np, torch, sys
+sys.path.insert(0, %r)
+import embedded_qp_solver_b200 as qp
+from embedded_qp_solver_b200 import problems
+P, q, lb, ub = problems.wellcond(120000, 16, seed=77, beta=0.5)
+packs_before = qp.host_path_packs(16)
+h = qp.solve_batch(P, q, -0.5, 0.5)
+d = qp.solve_batch(torch.from_numpy(P).cuda(), torch.from_numpy(q).cuda(), -0.5, 0.5)
+torch.cuda.synchronize()
+for k in h:
+    assert np.array_equal(np.asarray(h[k]), d[k].cpu().numpy()), k
+print("OK", int(packs_before), int(qp.host_path_packs(16)))
+""" % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, QPB200_HOST_PACK="3")
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    tag, before, after = r.stdout.split()[-3:]
+    assert tag == "OK"
+    if before == "1":          # this host packs: the switch must have happened
+        assert after == "0"
