@@ -464,6 +464,11 @@ public:
 		std::unique_lock<std::mutex> lk(mu_);
 		done_.wait(lk, [this] { return pending_ == 0; });
 	}
+	bool idle()
+	{
+		std::lock_guard<std::mutex> lk(mu_);
+		return pending_ == 0;
+	}
 
 private:
 	void loop(unsigned id)
@@ -633,7 +638,6 @@ struct Slot {
 	// pinned staging (allocated on first use with pageable caller memory)
 	float *hin = nullptr;  // P | q | lb | ub | z0 | u0 | rho
 	float *hout = nullptr; // x | z | lam | status | iters
-	float *hpk = nullptr;  // packed upper triangles of P (pinned), n = 8, 12, 16
 	cudaStream_t stream = nullptr;
 	cudaEvent_t done = nullptr;
 	cudaEvent_t t0 = nullptr, t1 = nullptr; // around the copy of the packed triangles
@@ -647,6 +651,11 @@ struct DeviceCtx {
 	int dev = 0;
 	Slot slot[DEPTH];
 	HostPool *pool = nullptr; // packing workers of this device's shard
+	// two pinned buffers of packed upper triangles (n = 8, 12, 16), filled in turn by the
+	// pool; hpk_free[b] fires when the copy engine has read buffer b
+	float *hpk[2] = { nullptr, nullptr };
+	cudaEvent_t hpk_free[2] = { nullptr, nullptr };
+	bool hpk_busy[2] = { false, false };
 	// host-side packing is given up for this workspace when the workers turn out slower
 	// than the copy engine would be on the full matrices (a slow or busy host)
 	bool pack_off = false;
@@ -709,7 +718,6 @@ void free_ctx(DeviceCtx &c)
 		cudaFree(s.dP);
 		cudaFreeHost(s.hin);
 		cudaFreeHost(s.hout);
-		cudaFreeHost(s.hpk);
 		if (s.done)
 			cudaEventDestroy(s.done);
 		if (s.t0)
@@ -722,6 +730,14 @@ void free_ctx(DeviceCtx &c)
 	}
 	delete c.pool;
 	c.pool = nullptr;
+	for (int b = 0; b < 2; ++b) {
+		cudaFreeHost(c.hpk[b]);
+		c.hpk[b] = nullptr;
+		if (c.hpk_free[b])
+			cudaEventDestroy(c.hpk_free[b]);
+		c.hpk_free[b] = nullptr;
+		c.hpk_busy[b] = false;
+	}
 	cudaSetDevice(prev);
 }
 
@@ -822,17 +838,35 @@ int run_shard(qp_workspace *ws, DeviceCtx &ctx, const qp_batch &pb, const qp_bat
 		// one core moves ~10 GB/s; PCIe wants ~85 GB/s of packing traffic: use the cores
 		ctx.pool = new HostPool(std::min(32u, tpg - 1));
 
-	// packing of chunk k+1 runs on the pool while this thread enqueues chunk k
-	auto start_pack = [&](size_t kk, size_t first) -> int {
-		Slot &s = ctx.slot[kk % DEPTH];
-		int rc = retire(s);
-		if (rc != QP_OK)
-			return rc;
-		if (!s.hpk)
-			QP_CUDA(cudaMallocHost(&s.hpk, chunk * size_t(pk) * 4));
-		const size_t c = std::min(chunk, hi - first);
-		const float *src = pb.P + first * size_t(n) * n;
-		float *dst = s.hpk;
+	// Chunk scheduling.  The pool packs one chunk at a time, taken from the FRONT of the shard.
+	// Each time a slot is free this thread enqueues the packed chunk if the pool has finished
+	// it, and otherwise a plain chunk (full matrices) taken from the BACK of the shard: the
+	// host cores and the copy engine are both kept busy, and the mix of packed and plain
+	// chunks follows their relative speed (a fast host packs almost everything, a slow one
+	// almost nothing).  Without packing the chunks go front to back.
+	size_t front = lo, back = hi;
+	struct {
+		size_t first = 0, cnt = 0;
+		int buf = 0;
+		bool inflight = false;
+	} job;
+	int pbuf = 0;
+	auto begin_pack = [&]() -> int {
+		if (!pack0 || ctx.pack_off || front >= back)
+			return QP_OK;
+		const size_t c = std::min(chunk, back - front);
+		if (!ctx.hpk[pbuf]) {
+			QP_CUDA(cudaMallocHost(&ctx.hpk[pbuf], chunk * size_t(pk) * 4));
+			QP_CUDA(cudaEventCreateWithFlags(&ctx.hpk_free[pbuf], cudaEventDisableTiming));
+		} else if (ctx.hpk_busy[pbuf]) {
+			QP_CUDA(cudaEventSynchronize(ctx.hpk_free[pbuf]));
+			ctx.hpk_busy[pbuf] = false;
+		}
+		job.first = front, job.cnt = c, job.buf = pbuf, job.inflight = true;
+		front += c;
+		pbuf ^= 1;
+		const float *src = pb.P + job.first * size_t(n) * n;
+		float *dst = ctx.hpk[job.buf];
 		const int nn = int(n), pkk = pk;
 		ctx.pool->start([=](unsigned part, unsigned parts) {
 			const size_t a = c * part / parts, b = c * (part + 1) / parts;
@@ -840,54 +874,60 @@ int run_shard(qp_workspace *ws, DeviceCtx &ctx, const qp_batch &pb, const qp_bat
 		});
 		return QP_OK;
 	};
-	bool next_packed = false; // the chunk about to be enqueued has been (is being) packed
-	if (pack0 && lo < hi) {
-		int rc = start_pack(0, lo);
+	{
+		int rc = begin_pack();
 		if (rc != QP_OK)
 			return rc;
-		next_packed = true;
 	}
 
 	size_t k = 0;
-	for (size_t first = lo; first < hi; first += chunk, ++k) {
+	while (job.inflight || front < back) {
 		Slot &s = ctx.slot[k % DEPTH];
-		int rc = QP_OK;
-		const bool pack = next_packed;
-		if (pack) {
-			ctx.pool->wait(); // chunk k is packed (its slot was retired by start_pack)
+		int rc = retire(s);
+		if (rc != QP_OK) {
+			if (job.inflight)
+				ctx.pool->wait();
+			return rc;
+		}
+		bool pack = false;
+		size_t first = 0, c = 0;
+		int buf = 0;
+		if (job.inflight && (front >= back || ctx.pool->idle())) {
+			ctx.pool->wait();
+			pack = true, first = job.first, c = job.cnt, buf = job.buf;
+			job.inflight = false;
 			// Packing pays while it takes less time than the copy engine would need for
 			// the full matrices of the same chunk; on a slow or busy host it does not
-			// (measured: 40.7 M QP/s packed where the plain copy gives 49 M).
+			// (bench pinned to four cores: 27 M QP/s with packing forced, 49 M without).
 			if (host_pack_test_switch() && k >= 2) {
 				ctx.pack_off = true;
 				g_pack_given_up.store(true);
 			}
-			if (!host_pack_forced() && ctx.h2d_bytes_per_s > 0.0 && std::min(chunk, hi - first) == chunk) {
+			if (!host_pack_forced() && ctx.h2d_bytes_per_s > 0.0 && c == chunk) {
+				const double t_full = double(chunk) * n * n * 4.0 / ctx.h2d_bytes_per_s;
 				if (std::getenv("QPB200_DEBUG"))
 					std::fprintf(stderr, "qpb200: pack %.3f ms, full copy %.3f ms at %.1f GB/s\n",
-						     ctx.pool->last_seconds() * 1e3,
-						     double(chunk) * n * n * 4.0 / ctx.h2d_bytes_per_s * 1e3,
+						     ctx.pool->last_seconds() * 1e3, t_full * 1e3,
 						     ctx.h2d_bytes_per_s * 1e-9);
-				const double t_full = double(chunk) * n * n * 4.0 / ctx.h2d_bytes_per_s;
 				// eight chunks in a row, so that one preempted worker does not decide
-				ctx.slow_chunks = ctx.pool->last_seconds() > 1.15 * t_full ? ctx.slow_chunks + 1 : 0;
+				ctx.slow_chunks = ctx.pool->last_seconds() > 2.0 * t_full ? ctx.slow_chunks + 1 : 0;
 				if (ctx.slow_chunks >= 8) {
 					ctx.pack_off = true;
 					g_pack_given_up.store(true);
 				}
 			}
-			next_packed = !ctx.pack_off && first + chunk < hi;
-			if (next_packed)
-				rc = start_pack(k + 1, first + chunk);
+			rc = begin_pack();
+			if (rc != QP_OK)
+				return rc;
+		} else if (job.inflight) {
+			c = std::min(chunk, back - front); // the pool is busy: a plain chunk from the back
+			first = back - c;
+			back -= c;
 		} else {
-			rc = retire(s);
+			c = std::min(chunk, back - front); // no packing: front to back
+			first = front;
+			front += c;
 		}
-		if (rc != QP_OK) {
-			if (pack)
-				ctx.pool->wait();
-			return rc;
-		}
-		const size_t c = std::min(chunk, hi - first);
 		s.first = first, s.cnt = c;
 		cudaStream_t st = s.stream;
 
@@ -901,8 +941,10 @@ int run_shard(qp_workspace *ws, DeviceCtx &ctx, const qp_batch &pb, const qp_bat
 			    { pb.rho, s.drho, 1 } };
 		if (pack) {
 			QP_CUDA(cudaEventRecord(s.t0, st));
-			QP_CUDA(cudaMemcpyAsync(s.dP, s.hpk, c * size_t(pk) * 4, cudaMemcpyHostToDevice, st));
+			QP_CUDA(cudaMemcpyAsync(s.dP, ctx.hpk[buf], c * size_t(pk) * 4, cudaMemcpyHostToDevice, st));
 			QP_CUDA(cudaEventRecord(s.t1, st));
+			QP_CUDA(cudaEventRecord(ctx.hpk_free[buf], st));
+			ctx.hpk_busy[buf] = true;
 			s.timed = true;
 		}
 		if (pin_in) {
@@ -982,6 +1024,7 @@ int run_shard(qp_workspace *ws, DeviceCtx &ctx, const qp_batch &pb, const qp_bat
 		}
 		QP_CUDA(cudaEventRecord(s.done, st));
 		s.busy = true;
+		++k;
 	}
 	// drain in issue order
 	for (size_t d = 0; d < DEPTH; ++d) {
