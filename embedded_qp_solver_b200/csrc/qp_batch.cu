@@ -651,11 +651,13 @@ struct DeviceCtx {
 	int dev = 0;
 	Slot slot[DEPTH];
 	HostPool *pool = nullptr; // packing workers of this device's shard
-	// two pinned buffers of packed upper triangles (n = 8, 12, 16), filled in turn by the
-	// pool; hpk_free[b] fires when the copy engine has read buffer b
-	float *hpk[2] = { nullptr, nullptr };
-	cudaEvent_t hpk_free[2] = { nullptr, nullptr };
-	bool hpk_busy[2] = { false, false };
+	// pinned buffers of packed upper triangles (n = 8, 12, 16), filled in turn by the pool
+	// (one being filled, one filled and waiting, one being read by the copy engine);
+	// hpk_free[b] fires when the copy engine has read buffer b
+	static constexpr int NPK = 3;
+	float *hpk[NPK] = { nullptr, nullptr, nullptr };
+	cudaEvent_t hpk_free[NPK] = { nullptr, nullptr, nullptr };
+	bool hpk_busy[NPK] = { false, false, false };
 	// host-side packing is given up for this workspace when the workers turn out slower
 	// than the copy engine would be on the full matrices (a slow or busy host)
 	bool pack_off = false;
@@ -730,7 +732,7 @@ void free_ctx(DeviceCtx &c)
 	}
 	delete c.pool;
 	c.pool = nullptr;
-	for (int b = 0; b < 2; ++b) {
+	for (int b = 0; b < DeviceCtx::NPK; ++b) {
 		cudaFreeHost(c.hpk[b]);
 		c.hpk[b] = nullptr;
 		if (c.hpk_free[b])
@@ -838,33 +840,42 @@ int run_shard(qp_workspace *ws, DeviceCtx &ctx, const qp_batch &pb, const qp_bat
 		// one core moves ~10 GB/s; PCIe wants ~85 GB/s of packing traffic: use the cores
 		ctx.pool = new HostPool(std::min(32u, tpg - 1));
 
-	// Chunk scheduling.  The pool packs one chunk at a time, taken from the FRONT of the shard.
-	// Each time a slot is free this thread enqueues the packed chunk if the pool has finished
-	// it, and otherwise a plain chunk (full matrices) taken from the BACK of the shard: the
-	// host cores and the copy engine are both kept busy, and the mix of packed and plain
-	// chunks follows their relative speed (a fast host packs almost everything, a slow one
-	// almost nothing).  Without packing the chunks go front to back.
+	// Chunk scheduling.  The pool packs one chunk at a time, taken from the FRONT of the shard,
+	// and goes straight on to the next one (a finished chunk waits in `ready`).  Each time a
+	// slot is free this thread enqueues the waiting packed chunk if there is one, and
+	// otherwise a plain chunk (full matrices) taken from the BACK of the shard: the host
+	// cores and the copy engine are both kept busy, and the mix of packed and plain chunks
+	// follows their relative speed (a fast host packs almost everything, a slow one almost
+	// nothing).  While it waits for a slot this thread polls the pool, so that the next
+	// chunk is started as soon as the previous one is packed.  Without packing the chunks
+	// go front to back.
 	size_t front = lo, back = hi;
-	struct {
+	struct Job {
 		size_t first = 0, cnt = 0;
 		int buf = 0;
-		bool inflight = false;
-	} job;
+		bool valid = false;
+	} job, ready; // being packed; packed and waiting for a slot
 	int pbuf = 0;
+	// non-blocking: starts the next chunk if there is one and a buffer is free
 	auto begin_pack = [&]() -> int {
-		if (!pack0 || ctx.pack_off || front >= back)
+		if (!pack0 || ctx.pack_off || job.valid || front >= back)
 			return QP_OK;
-		const size_t c = std::min(chunk, back - front);
 		if (!ctx.hpk[pbuf]) {
 			QP_CUDA(cudaMallocHost(&ctx.hpk[pbuf], chunk * size_t(pk) * 4));
 			QP_CUDA(cudaEventCreateWithFlags(&ctx.hpk_free[pbuf], cudaEventDisableTiming));
 		} else if (ctx.hpk_busy[pbuf]) {
-			QP_CUDA(cudaEventSynchronize(ctx.hpk_free[pbuf]));
+			const cudaError_t e = cudaEventQuery(ctx.hpk_free[pbuf]);
+			if (e == cudaErrorNotReady)
+				return QP_OK; // the copy engine still reads it: try again later
+			QP_CUDA(e);
 			ctx.hpk_busy[pbuf] = false;
 		}
-		job.first = front, job.cnt = c, job.buf = pbuf, job.inflight = true;
+		if (ready.valid && ready.buf == pbuf)
+			return QP_OK;
+		const size_t c = std::min(chunk, back - front);
+		job.first = front, job.cnt = c, job.buf = pbuf, job.valid = true;
 		front += c;
-		pbuf ^= 1;
+		pbuf = (pbuf + 1) % DeviceCtx::NPK;
 		const float *src = pb.P + job.first * size_t(n) * n;
 		float *dst = ctx.hpk[job.buf];
 		const int nn = int(n), pkk = pk;
@@ -874,6 +885,31 @@ int run_shard(qp_workspace *ws, DeviceCtx &ctx, const qp_batch &pb, const qp_bat
 		});
 		return QP_OK;
 	};
+	// moves a finished chunk to `ready` and keeps the pool going
+	auto pump = [&]() -> int {
+		if (job.valid && !ready.valid && ctx.pool->idle()) {
+			ctx.pool->wait();
+			ready = job;
+			job.valid = false;
+			// Packing pays while it takes less time than about twice what the copy engine
+			// needs for the full matrices of the same chunk; on a hopelessly slow or busy
+			// host it only takes memory bandwidth away from the copies.
+			if (!host_pack_forced() && ctx.h2d_bytes_per_s > 0.0 && ready.cnt == chunk) {
+				const double t_full = double(chunk) * n * n * 4.0 / ctx.h2d_bytes_per_s;
+				if (std::getenv("QPB200_DEBUG"))
+					std::fprintf(stderr, "qpb200: pack %.3f ms, full copy %.3f ms at %.1f GB/s\n",
+						     ctx.pool->last_seconds() * 1e3, t_full * 1e3,
+						     ctx.h2d_bytes_per_s * 1e-9);
+				// eight chunks in a row, so that one preempted worker does not decide
+				ctx.slow_chunks = ctx.pool->last_seconds() > 3.0 * t_full ? ctx.slow_chunks + 1 : 0;
+				if (ctx.slow_chunks >= 8) {
+					ctx.pack_off = true;
+					g_pack_given_up.store(true);
+				}
+			}
+		}
+		return begin_pack();
+	};
 	{
 		int rc = begin_pack();
 		if (rc != QP_OK)
@@ -881,48 +917,41 @@ int run_shard(qp_workspace *ws, DeviceCtx &ctx, const qp_batch &pb, const qp_bat
 	}
 
 	size_t k = 0;
-	while (job.inflight || front < back) {
+	while (job.valid || ready.valid || front < back) {
 		Slot &s = ctx.slot[k % DEPTH];
-		int rc = retire(s);
+		int rc = QP_OK;
+		// wait for the slot; meanwhile keep the pool fed
+		while (rc == QP_OK && s.busy && (job.valid || front < back) && pack0 && !ctx.pack_off &&
+		       cudaEventQuery(s.done) == cudaErrorNotReady) {
+			rc = pump();
+			std::this_thread::sleep_for(std::chrono::microseconds(20));
+		}
+		if (rc == QP_OK)
+			rc = retire(s);
+		if (rc == QP_OK)
+			rc = pump();
 		if (rc != QP_OK) {
-			if (job.inflight)
+			if (job.valid)
 				ctx.pool->wait();
 			return rc;
+		}
+		if (host_pack_test_switch() && k >= 3 && !ctx.pack_off) {
+			ctx.pack_off = true;
+			g_pack_given_up.store(true);
 		}
 		bool pack = false;
 		size_t first = 0, c = 0;
 		int buf = 0;
-		if (job.inflight && (front >= back || ctx.pool->idle())) {
-			ctx.pool->wait();
-			pack = true, first = job.first, c = job.cnt, buf = job.buf;
-			job.inflight = false;
-			// Packing pays while it takes less time than the copy engine would need for
-			// the full matrices of the same chunk; on a slow or busy host it does not
-			// (bench pinned to four cores: 27 M QP/s with packing forced, 49 M without).
-			if (host_pack_test_switch() && k >= 2) {
-				ctx.pack_off = true;
-				g_pack_given_up.store(true);
-			}
-			if (!host_pack_forced() && ctx.h2d_bytes_per_s > 0.0 && c == chunk) {
-				const double t_full = double(chunk) * n * n * 4.0 / ctx.h2d_bytes_per_s;
-				if (std::getenv("QPB200_DEBUG"))
-					std::fprintf(stderr, "qpb200: pack %.3f ms, full copy %.3f ms at %.1f GB/s\n",
-						     ctx.pool->last_seconds() * 1e3, t_full * 1e3,
-						     ctx.h2d_bytes_per_s * 1e-9);
-				// eight chunks in a row, so that one preempted worker does not decide
-				ctx.slow_chunks = ctx.pool->last_seconds() > 2.0 * t_full ? ctx.slow_chunks + 1 : 0;
-				if (ctx.slow_chunks >= 8) {
-					ctx.pack_off = true;
-					g_pack_given_up.store(true);
-				}
-			}
-			rc = begin_pack();
-			if (rc != QP_OK)
-				return rc;
-		} else if (job.inflight) {
+		if (ready.valid) {
+			pack = true, first = ready.first, c = ready.cnt, buf = ready.buf;
+			ready.valid = false;
+		} else if (job.valid && front < back) {
 			c = std::min(chunk, back - front); // the pool is busy: a plain chunk from the back
 			first = back - c;
 			back -= c;
+		} else if (job.valid) {
+			ctx.pool->wait(); // nothing else left to send: wait for the last packed chunk
+			continue;
 		} else {
 			c = std::min(chunk, back - front); // no packing: front to back
 			first = front;
