@@ -603,20 +603,30 @@ bool host_pack_test_switch()
 // problem at n = 16), so it only pays while the host's DRAM is not the shared bottleneck:
 // it is used when ONE GPU is fed from this host -- counting the ranks of a torchrun job
 // (LOCAL_WORLD_SIZE) and the devices of this process -- and needs 12 hardware threads.
-// Measured with two ranks on a 24-thread host: 68.9 M QP/s packed against 92.2 M plain.
+// Measured with two ranks on a 24-thread host: 68.9 M QP/s packed against 92.2 M plain, and
+// with the greedy mix of packed and plain chunks (QPB200_HOST_PACK=2 lifts this rule)
+// 85-88 M against 93 M plain.
 static unsigned host_threads_per_gpu(unsigned gpus_in_this_process)
 {
 	unsigned ranks = 1;
 	if (const char *e = std::getenv("LOCAL_WORLD_SIZE"))
 		ranks = unsigned(std::max(1, std::atoi(e)));
 	const unsigned sharers = std::max(1u, ranks * std::max(1u, gpus_in_this_process));
-	if (sharers > 1)
+	if (sharers > 1 && !host_pack_forced())
 		return 0;
 	return std::thread::hardware_concurrency() / sharers;
 }
 
 // set when a workspace of this process gave packing up (see run_shard)
 static std::atomic<bool> g_pack_given_up{false};
+
+// bytes the QP_MEM_HOST path has handed to the copy engine (host to device) in this process
+static std::atomic<unsigned long long> g_h2d_bytes{0};
+
+extern "C" unsigned long long qp_host_path_h2d_bytes(void)
+{
+	return g_h2d_bytes.load();
+}
 
 extern "C" int qp_host_path_packs(uint32_t n)
 {
@@ -968,6 +978,13 @@ int run_shard(qp_workspace *ws, DeviceCtx &ctx, const qp_batch &pb, const qp_bat
 		} ins[] = { { pb.P, s.dP, size_t(n) * n }, { pb.q, s.dq, n },  { pb.lb, s.dlb, n },
 			    { pb.ub, s.dub, n },           { pb.z0, s.dz0, n }, { pb.u0, s.du0, n },
 			    { pb.rho, s.drho, 1 } };
+		{
+			size_t wire = pack ? c * size_t(pk) * 4 : 0;
+			for (const In &i : ins)
+				if (i.src && !(pack && i.src == pb.P))
+					wire += c * i.per * 4;
+			g_h2d_bytes.fetch_add(wire);
+		}
 		if (pack) {
 			QP_CUDA(cudaEventRecord(s.t0, st));
 			QP_CUDA(cudaMemcpyAsync(s.dP, ctx.hpk[buf], c * size_t(pk) * 4, cudaMemcpyHostToDevice, st));

@@ -299,6 +299,10 @@ int qp_problem_file_read(const char *path, size_t first, size_t count,
  * packing against the copy engine and gives it up for the rest of the process when the
  * host turns out too slow for it to pay; the answer then turns to 0. */
 int qp_host_path_packs(uint32_t n);
+/* Bytes the QP_MEM_HOST path has handed to the copy engine (host to device) since the
+ * process started: packed and plain chunks are mixed as the host keeps up, so this, not
+ * the answer above, says what crossed PCIe. */
+unsigned long long qp_host_path_h2d_bytes(void);
 
 /* Diagnostics. */
 const char *qp_last_error(void);      /* text of the last QP_ERR_CUDA, per thread */
