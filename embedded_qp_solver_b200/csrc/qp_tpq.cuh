@@ -327,7 +327,7 @@ qp_tpq_kernel(const KernelArgs p)
 		int my_iters = int(p.max_iter);
 		int my_status = QP_STATUS_MAX_ITER;
 		unsigned it = 0;
-		bool active = valid && !bad && p.max_iter > 0;
+		const bool active = valid && !bad && p.max_iter > 0;
 		const float alpha = p.alpha;
 		const float rho2 = rho * rho, relrho = p.reltol * rho;
 
@@ -338,8 +338,12 @@ qp_tpq_kernel(const KernelArgs p)
 		for (int k = 0; k < NQ; ++k)
 			qn[k] = lds128(&priv_vec4[k * 32 + lane]);
 
-		while (__any_sync(FULL, active)) {
-			if (active) {
+		// The body holds no warp-wide operation, so lanes simply leave the loop when their
+		// problem is done and wait for the others at the __syncwarp() behind it (no vote,
+		// no per-lane flag to test: ~10 instructions less per iteration).
+		bool conv = false;
+		if (active) {
+			do {
 				// admm_update_x (:146-159): y = rho (z - u) - q ; x = (P + rho I)^-1 y
 #pragma unroll
 				for (int k = 0; k < NQ; ++k) {
@@ -389,24 +393,25 @@ qp_tpq_kernel(const KernelArgs p)
 					}
 				}
 				++it;
+				// (n <= 8 has the registers to keep q: loaded once before the loop)
+				if (N > 8) {
 #pragma unroll
-				for (int k = 0; k < NQ; ++k)
-					qn[k] = lds128(&priv_vec4[k * 32 + lane]);
+					for (int k = 0; k < NQ; ++k)
+						qn[k] = lds128(&priv_vec4[k * 32 + lane]);
+				}
 				// admm_eps_pri (:233-243), admm_eps_dual (:245-253), stop test (:308):
 				//   ||x-z|| < eps_pri  and  rho ||z-z_old|| < eps_dual,
 				// compared as squares so that only the two norms inside the thresholds
 				// need a square root (MUFU.SQRT, no branches)
 				const float eps_pri = fmaf(p.reltol, sqrt_approx(fmaxf(nx, nz)), p.eps_abs);
 				const float eps_dual = fmaf(relrho, sqrt_approx(nu), p.eps_abs);
-				const bool conv = (rr < eps_pri * eps_pri) && (rho2 * ss < eps_dual * eps_dual);
-				if (conv) {
-					my_status = QP_STATUS_CONVERGED;
-					my_iters = int(it);
-					active = false;
-				} else if (it >= p.max_iter) {
-					active = false;
-				}
-			}
+				conv = (rr < eps_pri * eps_pri) && (rho2 * ss < eps_dual * eps_dual);
+			} while (!conv && it < p.max_iter);
+		}
+		__syncwarp();
+		if (conv) {
+			my_status = QP_STATUS_CONVERGED;
+			my_iters = int(it);
 		}
 
 		// ---- results ---------------------------------------------------------------
