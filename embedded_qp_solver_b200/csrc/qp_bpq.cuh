@@ -299,7 +299,7 @@ qp_bpq_kernel(const KernelArgs p)
 		// ---- ADMM iterations (qp_solvers.c:284-310) -----------------------------------------
 		int status = QP_STATUS_MAX_ITER;
 		unsigned it = 0;
-		bool active = valid && !bad && p.max_iter > 0; // uniform inside a group
+		const bool active = valid && !bad && p.max_iter > 0; // uniform inside a group
 		// x = R y for my four rows, y broadcast from shared memory (full-inverse variant)
 		auto publish_y = [&](float *yb) {
 			*reinterpret_cast<float4 *>(yb + 4 * g) =
@@ -363,12 +363,14 @@ qp_bpq_kernel(const KernelArgs p)
 			return conv != 0;
 		};
 
+		// Every warp-wide operation of the loops below names only the lanes of the group
+		// (am), so a group simply leaves its loop when its problem is done and waits for
+		// the other groups at the __syncwarp() behind it: no ballot, no flag to test.
+		const unsigned am = (((1u << T) - 1u) << gbase);
+		bool conv = false;
 		if constexpr (PFI) {
-		for (;;) {
-			const unsigned am = __ballot_sync(FULL, active);
-			if (am == 0u)
-				break;
-			if (active) {
+		if (active) {
+			do {
 				// admm_update_x (:146-159): y = rho (z - u) - q ; x = R y with
 				// R = E_{NC-1} ... E_0: E_K maps the four pivot entries v_P (all in lane K
 				// of the group) to B^-1 v_P and adds H_K v_P to every other entry; H_K
@@ -396,13 +398,8 @@ qp_bpq_kernel(const KernelArgs p)
 				rr = ring.sum(rr, am), ss = ring.sum(ss, am), nx = ring.sum(nx, am);
 				nz = ring.sum(nz, am), nu = ring.sum(nu, am);
 				++it;
-				if (converged(rr, ss, nx, nz, nu, am)) {
-					status = QP_STATUS_CONVERGED;
-					active = false;
-				} else if (it >= p.max_iter) {
-					active = false;
-				}
-			}
+				conv = converged(rr, ss, nx, nz, nu, am);
+			} while (!conv && it < p.max_iter);
 		}
 		} else {
 		// Full inverse.  The loop is software-pipelined: the mat-vec of the NEXT iteration is
@@ -411,19 +408,11 @@ qp_bpq_kernel(const KernelArgs p)
 		// chains overlap the FMAs instead of heading a serial chain of ~300 cycles per
 		// iteration.  One mat-vec per problem is wasted (the one after convergence).
 		float xr[4] = { 0.f, 0.f, 0.f, 0.f };
-		{
-			const unsigned am = __ballot_sync(FULL, active);
-			if (active) {
-				publish_y(bc);
-				__syncwarp(am);
-				matvec(bc, xr);
-			}
-		}
-		for (;;) {
-			const unsigned am = __ballot_sync(FULL, active);
-			if (am == 0u)
-				break;
-			if (active) {
+		if (active) {
+			publish_y(bc);
+			__syncwarp(am);
+			matvec(bc, xr);
+			do {
 				float rr, ss, nx, nz, nu;
 				elementwise(xr, rr, ss, nx, nz, nu);
 				++it;
@@ -433,16 +422,13 @@ qp_bpq_kernel(const KernelArgs p)
 				rr = ring.sum(rr, am), ss = ring.sum(ss, am), nx = ring.sum(nx, am);
 				nz = ring.sum(nz, am), nu = ring.sum(nu, am);
 				matvec(yb, xr);
-				if (converged(rr, ss, nx, nz, nu, am)) {
-					status = QP_STATUS_CONVERGED;
-					active = false;
-				} else if (it >= p.max_iter) {
-					active = false;
-				}
-			}
+				conv = converged(rr, ss, nx, nz, nu, am);
+			} while (!conv && it < p.max_iter);
 		}
 		}
 		__syncwarp();
+		if (conv)
+			status = QP_STATUS_CONVERGED;
 
 		// ---- results ---------------------------------------------------------------------------
 		float nf = fmaf(x[0], 0.0f, fmaf(x[1], 0.0f, fmaf(x[2], 0.0f, x[3] * 0.0f)));

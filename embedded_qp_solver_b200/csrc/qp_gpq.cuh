@@ -382,7 +382,7 @@ qp_gpq_kernel(const KernelArgs p)
 		// ---- ADMM iterations (qp_solvers.c:284-310) -----------------------------------------
 		int status = QP_STATUS_MAX_ITER;
 		unsigned it = 0;
-		bool active = valid && !bad && p.max_iter > 0; // uniform inside a group
+		const bool active = valid && !bad && p.max_iter > 0; // uniform inside a group
 		// element-wise part of one iteration with x = xr: admm_update_x_hat (:161-174),
 		// _z (:176-190), _u (:192-203) and the five partial sums of squares (:205-253)
 		auto elementwise = [&](const float (&xr)[RPL], float &rr, float &ss, float &nx, float &nz,
@@ -422,12 +422,14 @@ qp_gpq_kernel(const KernelArgs p)
 			return (rr < eps_pri * eps_pri) && (rho2 * ss < eps_dual * eps_dual);
 		};
 
+		// Every warp-wide operation of the loops below names only the lanes of the group
+		// (am), so a group simply leaves its loop when its problem is done and waits for
+		// the other groups at the __syncwarp() behind it: no ballot, no flag to test.
+		const unsigned am = (T == 32) ? FULL : (((1u << (T & 31)) - 1u) << (lane & ~(T - 1)));
+		bool conv = false;
 		if constexpr (PFI) {
-		for (;;) {
-			const unsigned am = __ballot_sync(FULL, active);
-			if (am == 0u)
-				break;
-			if (active) {
+		if (active) {
+			do {
 				// admm_update_x (:146-159): y = rho (z - u) - q ; x = R y.
 				// R is held in product form, R = E_{NC-1} ... E_0: apply the block eta
 				// transformations one after the other.  E_K maps the four pivot entries
@@ -457,13 +459,8 @@ qp_gpq_kernel(const KernelArgs p)
 				elementwise(xr, rr, ss, nx, nz, nu);
 				reduce5(rr, ss, nx, nz, nu, am);
 				++it;
-				if (converged(rr, ss, nx, nz, nu)) {
-					status = QP_STATUS_CONVERGED;
-					active = false;
-				} else if (it >= p.max_iter) {
-					active = false;
-				}
-			}
+				conv = converged(rr, ss, nx, nz, nu);
+			} while (!conv && it < p.max_iter);
 		}
 		} else {
 		// Full inverse: x = R y is a register-resident mat-vec with y broadcast from shared
@@ -503,19 +500,11 @@ qp_gpq_kernel(const KernelArgs p)
 #pragma unroll
 		for (int s = 0; s < RPL; ++s)
 			xr[s] = 0.0f;
-		{
-			const unsigned am = __ballot_sync(FULL, active);
-			if (active) {
-				publish_y(bc);
-				__syncwarp(am);
-				matvec(bc, xr);
-			}
-		}
-		for (;;) {
-			const unsigned am = __ballot_sync(FULL, active);
-			if (am == 0u)
-				break;
-			if (active) {
+		if (active) {
+			publish_y(bc);
+			__syncwarp(am);
+			matvec(bc, xr);
+			do {
 				float rr, ss, nx, nz, nu;
 				elementwise(xr, rr, ss, nx, nz, nu);
 				++it;
@@ -524,16 +513,13 @@ qp_gpq_kernel(const KernelArgs p)
 				__syncwarp(am);
 				reduce5(rr, ss, nx, nz, nu, am);
 				matvec(yb, xr);
-				if (converged(rr, ss, nx, nz, nu)) {
-					status = QP_STATUS_CONVERGED;
-					active = false;
-				} else if (it >= p.max_iter) {
-					active = false;
-				}
-			}
+				conv = converged(rr, ss, nx, nz, nu);
+			} while (!conv && it < p.max_iter);
 		}
 		}
 		__syncwarp();
+		if (conv)
+			status = QP_STATUS_CONVERGED;
 
 		// ---- results ---------------------------------------------------------------------------
 		float nf = 0.0f;
