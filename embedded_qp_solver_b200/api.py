@@ -81,7 +81,7 @@ ABI_SYMBOLS = [
     "qp_device_count", "qp_kernel_for", "qp_probe_fp32_tflops", "qp_probe_hbm_gbs",
     "qp_newton_batch", "qp_newton_qf",
     "qp_problem_file_write", "qp_problem_file_count", "qp_problem_file_read",
-    "qp_solve_general_batch", "qp_host_path_packs", "qp_host_path_h2d_bytes", "qp_gradient_batch", "qp_gradient_qf",
+    "qp_solve_general_batch", "qp_host_path_packs", "qp_host_path_h2d_bytes", "qp_host_pack_upper", "qp_gradient_batch", "qp_gradient_qf",
 ]
 
 _lib = None
@@ -159,6 +159,8 @@ def load_library(path: Optional[str] = None):
     lib.qp_solve_general_batch.restype = C.c_int
     lib.qp_host_path_packs.argtypes = [C.c_uint32]
     lib.qp_host_path_packs.restype = C.c_int
+    lib.qp_host_pack_upper.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint32, C.c_int]
+    lib.qp_host_pack_upper.restype = C.c_int
     lib.qp_host_path_h2d_bytes.argtypes = []
     lib.qp_host_path_h2d_bytes.restype = C.c_ulonglong
     lib.qp_last_error.restype = C.c_char_p

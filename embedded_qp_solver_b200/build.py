@@ -11,7 +11,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "lib", "libqpb200.so")
-SOURCES = [os.path.join(CSRC, "qp_batch.cu"), os.path.join(CSRC, "qp_file.cpp")]
+SOURCES = [os.path.join(CSRC, "qp_batch.cu"), os.path.join(CSRC, "qp_file.cpp"),
+           os.path.join(CSRC, "qp_hostpack.cpp")]
 HEADERS = [os.path.join(CSRC, f) for f in ("qp_common.cuh", "qp_tpq.cuh", "qp_gpq.cuh", "qp_bpq.cuh", "qp_cpq.cuh", "qp_newton.cuh", "qp_gen.cuh")] + [
     os.path.join(os.path.dirname(HERE), "include", "qp_batch.h")]
 

@@ -48,6 +48,11 @@
 
 using namespace qpb;
 
+namespace qpb { // qp_hostpack.cpp
+bool hostpack_have_avx512();
+void hostpack_upper16_avx512(const float *P, float *out, size_t count);
+}
+
 // ----------------------------------------------------------------------------------------
 // errors
 // ----------------------------------------------------------------------------------------
@@ -554,9 +559,17 @@ template <int N> void pack_upper_n(const float *P, float *out, size_t count, int
 #endif
 }
 
-void pack_upper(const float *P, float *out, size_t count, int n)
+// wide: -1 = AVX-512 when the CPU has it (QPB200_HOST_PACK_SSE=1 keeps the 128-bit version,
+// for measurements), 0 = 128-bit, 1 = AVX-512 (the caller has checked the CPU)
+void pack_upper(const float *P, float *out, size_t count, int n, int wide = -1)
 {
 	const int pk = tpq_packed_stride(n);
+	// n = 16 with AVX-512 (qp_hostpack.cpp): about twice the rate per core
+	static const bool have = qpb::hostpack_have_avx512() && !std::getenv("QPB200_HOST_PACK_SSE");
+	if (n == 16 && pk == 136 && (wide < 0 ? have : wide > 0)) {
+		qpb::hostpack_upper16_avx512(P, out, count);
+		return;
+	}
 	switch (n) {
 	case 8:  pack_upper_n<8>(P, out, count, pk); break;
 	case 12: pack_upper_n<12>(P, out, count, pk); break;
@@ -626,6 +639,16 @@ static std::atomic<unsigned long long> g_h2d_bytes{0};
 extern "C" unsigned long long qp_host_path_h2d_bytes(void)
 {
 	return g_h2d_bytes.load();
+}
+
+extern "C" int qp_host_pack_upper(const float *P, float *out, size_t count, uint32_t n, int wide)
+{
+	if (!P || !out || !(n == 8 || n == 12 || n == 16) || (reinterpret_cast<uintptr_t>(out) & 15u))
+		return QP_ERR_INVALID;
+	if (wide > 0 && !qpb::hostpack_have_avx512())
+		return QP_ERR_UNSUPPORTED; // no AVX-512 on this CPU
+	pack_upper(P, out, count, int(n), wide);
+	return QP_OK;
 }
 
 extern "C" int qp_host_path_packs(uint32_t n)

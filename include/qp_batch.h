@@ -303,6 +303,12 @@ int qp_host_path_packs(uint32_t n);
  * process started: packed and plain chunks are mixed as the host keeps up, so this, not
  * the answer above, says what crossed PCIe. */
 unsigned long long qp_host_path_h2d_bytes(void);
+/* The packing step of that path on its own (tests, measurements; no GPU involved): the
+ * row-major upper triangles of `count` n x n matrices (n = 8, 12, 16), records
+ * (n (n + 1) / 2 rounded up to a multiple of 4) floats apart, `out` 16-byte aligned.
+ * wide: 0 = 128-bit moves, 1 = AVX-512 (QP_ERR_UNSUPPORTED without it, n = 16 only),
+ * -1 = what the host path itself would use. */
+int qp_host_pack_upper(const float *P, float *out, size_t count, uint32_t n, int wide);
 
 /* Diagnostics. */
 const char *qp_last_error(void);      /* text of the last QP_ERR_CUDA, per thread */

@@ -124,3 +124,41 @@ int main(void) {
     offs = [int(v) for v in out[7:]]
     assert offs == [api.qp_batch.count.offset, api.qp_batch.z0.offset, api.qp_options.stream.offset,
                     api.qp_options.kernel.offset, api.qp_general_batch.A.offset]
+
+
+@pytest.mark.parametrize("n", [8, 12, 16])
+def test_host_packing_of_upper_triangles(n):
+    """The packing step of the QP_MEM_HOST path (no GPU involved): record layout, and the
+    AVX-512 version (n = 16, when this CPU has it) bit for bit equal to the 128-bit one,
+    from even and odd record offsets and for odd counts."""
+    import numpy as np
+    from embedded_qp_solver_b200.api import load_library, QP_OK
+    lib = load_library()
+    rng = np.random.default_rng(n)
+    count = 37
+    P = rng.standard_normal((count, n, n)).astype(np.float32)
+    pk = (n * (n + 1) // 2 + 3) // 4 * 4
+    iu = np.triu_indices(n)
+    want = np.zeros((count, pk), np.float32)
+    want[:, : len(iu[0])] = P[:, iu[0], iu[1]]
+
+    def run(first, cnt, wide):
+        raw = np.full(count * pk + 32, np.nan, np.float32)
+        off = (-raw.ctypes.data // 4) % 16  # 64-byte aligned start of record 0
+        out = raw[off: off + count * pk].reshape(count, pk)
+        rc = lib.qp_host_pack_upper(P[first:].ctypes.data, out[first:].ctypes.data, cnt, n, wide)
+        # nothing outside the records asked for is written
+        assert np.isnan(out[:first]).all() and np.isnan(out[first + cnt:]).all()
+        assert np.isnan(raw[:off]).all() and np.isnan(raw[off + count * pk:]).all()
+        return rc, out[first: first + cnt].copy()
+
+    rc, got = run(0, count, 0)
+    assert rc == QP_OK and np.array_equal(got, want)
+    rc, got = run(0, count, -1)
+    assert rc == QP_OK and np.array_equal(got, want)
+    if n == 16:
+        for first, cnt in [(0, count), (1, count - 1), (1, 6), (2, 5), (3, 1), (0, 0)]:
+            rc, got = run(first, cnt, 1)
+            if rc != QP_OK:
+                pytest.skip("no AVX-512 on this CPU")
+            assert np.array_equal(got, want[first: first + cnt]), (first, cnt)
