@@ -51,6 +51,7 @@ using namespace qpb;
 namespace qpb { // qp_hostpack.cpp
 bool hostpack_have_avx512();
 void hostpack_upper16_avx512(const float *P, float *out, size_t count);
+void hostpack_upper16_avx512_cached(const float *P, float *out, size_t count);
 }
 
 // ----------------------------------------------------------------------------------------
@@ -560,14 +561,22 @@ template <int N> void pack_upper_n(const float *P, float *out, size_t count, int
 }
 
 // wide: -1 = AVX-512 when the CPU has it (QPB200_HOST_PACK_SSE=1 keeps the 128-bit version,
-// for measurements), 0 = 128-bit, 1 = AVX-512 (the caller has checked the CPU)
+// for measurements), 0 = 128-bit, 1 = AVX-512 with ordinary stores, 2 = AVX-512 with
+// non-temporal stores (the caller has checked the CPU)
 void pack_upper(const float *P, float *out, size_t count, int n, int wide = -1)
 {
 	const int pk = tpq_packed_stride(n);
 	// n = 16 with AVX-512 (qp_hostpack.cpp): about twice the rate per core
 	static const bool have = qpb::hostpack_have_avx512() && !std::getenv("QPB200_HOST_PACK_SSE");
 	if (n == 16 && pk == 136 && (wide < 0 ? have : wide > 0)) {
-		qpb::hostpack_upper16_avx512(P, out, count);
+		// ordinary stores straight into the staging buffer beat the non-temporal ones by
+		// ~5 % end to end with the 512-bit moves (65 M against 61 M QP/s; with the 128-bit
+		// version it is the other way round); QPB200_PACK_NT=1 keeps the non-temporal ones
+		static const bool nt = std::getenv("QPB200_PACK_NT") != nullptr;
+		if (wide < 0 ? !nt : wide == 1)
+			qpb::hostpack_upper16_avx512_cached(P, out, count);
+		else
+			qpb::hostpack_upper16_avx512(P, out, count);
 		return;
 	}
 	switch (n) {

@@ -306,8 +306,8 @@ unsigned long long qp_host_path_h2d_bytes(void);
 /* The packing step of that path on its own (tests, measurements; no GPU involved): the
  * row-major upper triangles of `count` n x n matrices (n = 8, 12, 16), records
  * (n (n + 1) / 2 rounded up to a multiple of 4) floats apart, `out` 16-byte aligned.
- * wide: 0 = 128-bit moves, 1 = AVX-512 (QP_ERR_UNSUPPORTED without it, n = 16 only),
- * -1 = what the host path itself would use. */
+ * wide: 0 = 128-bit moves, 1 = AVX-512 with ordinary stores, 2 = AVX-512 with non-temporal
+ * stores (QP_ERR_UNSUPPORTED without AVX-512; n = 16 only), -1 = what the host path uses. */
 int qp_host_pack_upper(const float *P, float *out, size_t count, uint32_t n, int wide);
 
 /* Diagnostics. */

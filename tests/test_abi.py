@@ -157,8 +157,9 @@ def test_host_packing_of_upper_triangles(n):
     rc, got = run(0, count, -1)
     assert rc == QP_OK and np.array_equal(got, want)
     if n == 16:
-        for first, cnt in [(0, count), (1, count - 1), (1, 6), (2, 5), (3, 1), (0, 0)]:
-            rc, got = run(first, cnt, 1)
-            if rc != QP_OK:
-                pytest.skip("no AVX-512 on this CPU")
-            assert np.array_equal(got, want[first: first + cnt]), (first, cnt)
+        for wide in (1, 2):
+            for first, cnt in [(0, count), (1, count - 1), (1, 6), (2, 5), (3, 1), (0, 0)]:
+                rc, got = run(first, cnt, wide)
+                if rc != QP_OK:
+                    pytest.skip("no AVX-512 on this CPU")
+                assert np.array_equal(got, want[first: first + cnt]), (wide, first, cnt)
