@@ -185,7 +185,7 @@ def parse():
     ap.add_argument("--beta", type=float, default=0.5)
     ap.add_argument("--seed", type=int, default=2026)
     ap.add_argument("--cpu-sample", type=int, default=400_000)
-    ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 10)")
+    ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 20)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     return ap.parse_args()
@@ -289,9 +289,9 @@ def run_ours(args, rank, local_rank, world):
         hout.update({k: torch.empty(count, dtype=torch.int32).pin_memory()
                      for k in ("status", "iters")})
         hopts = qp.Options(device=local_rank)
-        for _ in range(2):
+        for _ in range(max(3, min(args.warmup, 5))):
             qp.solve_batch(hP, hq, -args.beta, args.beta, options=hopts, out=hout)
-        ksteps = args.e2e_steps or min(args.steps, 10)
+        ksteps = args.e2e_steps or min(args.steps, 20)
         barrier()
         wire0 = qp.host_path_h2d_bytes()
         t0 = time.perf_counter()
