@@ -874,3 +874,29 @@ print("OK", int(packs_before), int(qp.host_path_packs(16)))
     assert tag == "OK"
     if before == "1":          # this host packs: the switch must have happened
         assert after == "0"
+
+
+@pytest.mark.parametrize("family,n", [("tpq", 4), ("tpq", 16), ("bpq", 24), ("bpq", 40), ("gpq", 40),
+                                      ("gpq", 64), ("cpq", 100)])
+@pytest.mark.parametrize("cap", [1, 9, 10])
+def test_iteration_cap_in_the_middle_of_a_warp(qp, orc, family, n, cap):
+    """The lanes (tpq) or lane groups (bpq, gpq) of a warp leave the iteration loop on their
+    own: with the cap at the typical iteration count some problems of every warp converge
+    and their neighbours run into the cap (qp_solvers.c:284 loop bound); status, iteration
+    count and iterate must match the oracle run with the same cap, problem by problem."""
+    count = 333
+    P, q, lb, ub = problems.wellcond(count, n, seed=4200 + n, beta=0.5)
+    o = orc.admm(P.astype(np.float64), q.astype(np.float64), lb.astype(np.float64),
+                 ub.astype(np.float64), max_iter=cap)
+    kern = getattr(qp, "KERNEL_" + family.upper())
+    r = solve_dev(qp, P, q, lb, ub, options=qp.Options(kernel=kern, max_iter=cap))
+    # (with the cap at 1 nothing is near its stop test: every problem runs into the cap)
+    ok = nondegenerate(o["margins"]) if cap > 1 else np.ones(count, bool)
+    assert ok.sum() > count // 2
+    if cap >= 9:
+        assert (o["status"] == 0).any() and (o["status"] == 1).any()
+    assert np.array_equal(r["status"][ok], o["status"][ok])
+    assert np.array_equal(r["iters"][ok], o["iters"][ok])
+    e = rel_err(r["x"][ok].astype(np.float64), o["x"][ok])
+    assert e.max() <= X_TOL, e.max()
+    assert np.max(np.abs(r["z"][ok] - o["z"][ok])) <= 1e-4
