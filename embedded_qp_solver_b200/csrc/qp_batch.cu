@@ -879,8 +879,16 @@ int run_shard(qp_workspace *ws, DeviceCtx &ctx, const qp_batch &pb, const qp_bat
 			  ((pb.lb == nullptr) == (pb.ub == nullptr)) && ((pb.z0 == nullptr) == (pb.u0 == nullptr));
 	const int pk = tpq_packed_stride(int(n));
 	if (pack0 && !ctx.pool)
-		// one core moves ~10 GB/s; PCIe wants ~85 GB/s of packing traffic: use the cores
-		ctx.pool = new HostPool(std::min(32u, tpg - 1));
+	{
+		// three quarters of the hardware threads: the path is bound by the host's memory
+		// system, and the enqueueing thread and the driver's own threads want cores too
+		// (16-thread host, 2^20 problems at n = 16: 4 workers 63 M, 8 65 M, 12 70 M,
+		// 15 68 M QP/s end to end)
+		unsigned workers = std::min(32u, tpg - tpg / 4);
+		if (const char *e = std::getenv("QPB200_PACK_THREADS")) // measurements
+			workers = unsigned(std::max(1, std::min(64, std::atoi(e))));
+		ctx.pool = new HostPool(workers);
+	}
 
 	// Chunk scheduling.  The pool packs one chunk at a time, taken from the FRONT of the shard,
 	// and goes straight on to the next one (a finished chunk waits in `ready`).  Each time a
