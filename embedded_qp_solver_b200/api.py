@@ -28,6 +28,8 @@ QP_OK, QP_ERR_INVALID, QP_ERR_UNSUPPORTED, QP_ERR_CUDA, QP_ERR_NO_DEVICE = 0, -1
 QP_ERR_IO = -5
 MEM_HOST, MEM_DEVICE = 0, 1
 KERNEL_AUTO, KERNEL_TPQ, KERNEL_GPQ, KERNEL_BPQ, KERNEL_CPQ = 0, 1, 2, 3, 4
+SCHEDULE_AUTO, SCHEDULE_SINGLE, SCHEDULE_LEVELS = 0, 1, 2
+P_DENSE, P_UPPER = 0, 1
 
 _fp = C.POINTER(C.c_float)
 _ip = C.POINTER(C.c_int32)
@@ -37,7 +39,8 @@ class qp_batch(C.Structure):
     _fields_ = [("n", C.c_uint32), ("mem", C.c_uint32), ("count", C.c_size_t),
                 ("P", C.c_void_p), ("q", C.c_void_p), ("lb", C.c_void_p), ("ub", C.c_void_p),
                 ("lb_scalar", C.c_float), ("ub_scalar", C.c_float),
-                ("z0", C.c_void_p), ("u0", C.c_void_p), ("rho", C.c_void_p)]
+                ("z0", C.c_void_p), ("u0", C.c_void_p), ("rho", C.c_void_p),
+                ("p_layout", C.c_uint32), ("reserved", C.c_uint32)]
 
 
 class qp_batch_solution(C.Structure):
@@ -60,7 +63,7 @@ class qp_options(C.Structure):
     _fields_ = [("rho", C.c_float), ("alpha", C.c_float), ("abstol", C.c_float),
                 ("reltol", C.c_float), ("max_iter", C.c_uint32), ("device_mask", C.c_uint32),
                 ("device", C.c_int32), ("stream", C.c_void_p), ("chunk", C.c_uint32),
-                ("kernel", C.c_uint32)]
+                ("kernel", C.c_uint32), ("schedule", C.c_uint32), ("reserved", C.c_uint32)]
 
 
 class qp_ref_matrix(C.Structure):
@@ -82,6 +85,7 @@ ABI_SYMBOLS = [
     "qp_newton_batch", "qp_newton_qf",
     "qp_problem_file_write", "qp_problem_file_count", "qp_problem_file_read",
     "qp_solve_general_batch", "qp_host_path_packs", "qp_host_path_h2d_bytes", "qp_host_pack_upper", "qp_gradient_batch", "qp_gradient_qf",
+    "qp_packed_stride", "qp_probe_copy_seconds",
 ]
 
 _lib = None
@@ -163,6 +167,10 @@ def load_library(path: Optional[str] = None):
     lib.qp_host_pack_upper.restype = C.c_int
     lib.qp_host_path_h2d_bytes.argtypes = []
     lib.qp_host_path_h2d_bytes.restype = C.c_ulonglong
+    lib.qp_packed_stride.argtypes = [C.c_uint32]
+    lib.qp_packed_stride.restype = C.c_size_t
+    lib.qp_probe_copy_seconds.argtypes = [C.c_int, C.c_size_t, C.c_size_t, C.c_int, C.c_size_t, C.c_int]
+    lib.qp_probe_copy_seconds.restype = C.c_double
     lib.qp_last_error.restype = C.c_char_p
     lib.qp_device_count.restype = C.c_int
     lib.qp_kernel_for.argtypes = [C.c_uint32, C.c_int]
@@ -189,11 +197,12 @@ class Options:
     stream: int = 0
     chunk: int = 0
     kernel: int = 0   # KERNEL_AUTO / KERNEL_TPQ / KERNEL_GPQ / KERNEL_BPQ / KERNEL_CPQ
+    schedule: int = 0  # SCHEDULE_AUTO / SCHEDULE_SINGLE / SCHEDULE_LEVELS
 
     def to_c(self) -> qp_options:
         return qp_options(self.rho, self.alpha, self.abstol, self.reltol, int(self.max_iter),
                           int(self.device_mask), int(self.device), C.c_void_p(self.stream or None),
-                          int(self.chunk), int(self.kernel))
+                          int(self.chunk), int(self.kernel), int(self.schedule), 0)
 
 
 def _is_torch(t) -> bool:
@@ -219,7 +228,7 @@ def _as_f32(a, shape, what):
 
 def solve_batch(P, q, lb=None, ub=None, z0=None, u0=None, options: Optional[Options] = None,
                 out: Optional[dict] = None, workspace: Optional["Workspace"] = None,
-                want=("x", "z", "lam", "status", "iters"), rho=None) -> dict:
+                want=("x", "z", "lam", "status", "iters"), rho=None, p_layout: int = P_DENSE) -> dict:
     """Solve ``count`` box QPs: the batched replacement of a loop of the
     reference's ``admm(x0, iterations, qf)`` (qp_solvers.c:255-319).
 
@@ -227,6 +236,8 @@ def solve_batch(P, q, lb=None, ub=None, z0=None, u0=None, options: Optional[Opti
     scalar, or None (= -/+1e12, the reference's host box, config.h:29-30).
     rho: None (``options.rho`` for every problem, the reference's RHO_ADMM) or
     an array [count] of per-problem penalties.
+    p_layout=P_UPPER: P is [count, packed_stride(n)], the row-major upper triangle of every
+    matrix (``pack_upper``), n = 8, 12, 16.
     CUDA torch tensors take the device path (kernel launched on the current
     torch stream, no synchronisation, outputs are torch tensors on that
     device); numpy arrays / CPU tensors take the host path (copies, sharded
@@ -234,16 +245,23 @@ def solve_batch(P, q, lb=None, ub=None, z0=None, u0=None, options: Optional[Opti
     """
     lib = load_library()
     opt = options or Options()
-    count, n = int(P.shape[0]), int(P.shape[1])
-    if tuple(P.shape) != (count, n, n):
-        raise ValueError("P must be [count, n, n]")
-    hP, aP, dev = _as_f32(P, (count, n, n), "P")
+    count = int(P.shape[0])
+    if p_layout == P_UPPER:
+        n = int(q.shape[1])
+        pshape = (count, packed_stride(n))
+    else:
+        n = int(P.shape[1])
+        pshape = (count, n, n)
+    if tuple(P.shape) != pshape:
+        raise ValueError(f"P must be {pshape}")
+    hP, aP, dev = _as_f32(P, pshape, "P")
     hq, aq, dq = _as_f32(q, (count, n), "q")
     if dq != dev:
         raise ValueError("P and q must live on the same side (host or device)")
 
     pb = qp_batch()
     pb.n, pb.count = n, count
+    pb.p_layout = int(p_layout)
     pb.mem = MEM_DEVICE if dev else MEM_HOST
     pb.P, pb.q = aP, aq
     pb.lb_scalar, pb.ub_scalar = -1e12, 1e12
@@ -565,6 +583,33 @@ def admm_many(qfs, iterations: int, lb: float = -1e12, ub: float = 1e12):
     if rc != QP_OK:
         raise QpError(rc, "qp_admm_qf_batch")
     return x, st, it
+
+
+def packed_stride(n: int) -> int:
+    """Floats per problem of a P_UPPER batch (``qp_packed_stride``)."""
+    return int(load_library().qp_packed_stride(n))
+
+
+def pack_upper(P) -> np.ndarray:
+    """[count, n, n] -> [count, packed_stride(n)]: the row-major upper triangle of each
+    matrix, zero padded (the P_UPPER layout).  numpy, any n the layout takes."""
+    P = np.asarray(P, dtype=np.float32)
+    count, n = P.shape[0], P.shape[1]
+    iu = np.triu_indices(n)
+    out = np.zeros((count, packed_stride(n)), np.float32)
+    out[:, :len(iu[0])] = P[:, iu[0], iu[1]]
+    return out
+
+
+def probe_copy_seconds(h2d_bytes: int, d2h_bytes: int, device: int = -1, pinned: bool = True,
+                       piece_bytes: int = 0, repeats: int = 3) -> float:
+    """Seconds to move those bytes both ways at once with no kernel in between
+    (``qp_probe_copy_seconds``): the ceiling of the host-memory path."""
+    t = float(load_library().qp_probe_copy_seconds(device, h2d_bytes, d2h_bytes, int(pinned),
+                                                   piece_bytes, repeats))
+    if t < 0:
+        raise QpError(int(t), "qp_probe_copy_seconds")
+    return t
 
 
 def host_path_h2d_bytes() -> int:

@@ -2,12 +2,13 @@
 //
 // Replaces, for a whole batch, the reference's per-problem call
 //   struct _matrix *admm(x0, iterations, qf)     /root/reference/qp_solvers/qp_solvers.c:255-319
-// and the static slab pools behind it (/root/reference/kmalloc/kmalloc.c:37-66) with a
-// preallocated device workspace.
+// and the static slab pools behind it (/root/reference/kmalloc/kmalloc.c:37-66) with
+// preallocated device workspaces.  The kernels live in one translation unit per family
+// (k_tpq.cu, k_bpq.cu, k_gpq.cu, k_cpq.cu, k_aux.cu; qp_internal.h declares their launchers).
 //
 // Two data paths:
 //   QP_MEM_DEVICE  arrays already in HBM: pick the kernel for n, launch it on the
-//                  caller's stream, return without synchronising.  No allocation.
+//                  caller's stream, return without synchronising.
 //   QP_MEM_HOST    arrays in host memory: the batch is split into contiguous shards,
 //                  one per GPU in device_mask (one host thread per GPU), and every
 //                  shard into chunks that flow through a DEPTH-deep ring of
@@ -24,6 +25,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -32,19 +34,7 @@
 #include <xmmintrin.h>
 #endif
 
-#include "qp_bpq.cuh"
-#include "qp_cpq.cuh"
-#include "qp_gen.cuh"
-#include "qp_gpq.cuh"
-#include "qp_newton.cuh"
-#include "qp_tpq.cuh"
-
-#ifndef QPB_BPQ_PFI_FROM
-#define QPB_BPQ_PFI_FROM 24
-#endif
-#ifndef QPB_GPQ_PFI_FROM
-#define QPB_GPQ_PFI_FROM 48
-#endif
+#include "qp_internal.h"
 
 using namespace qpb;
 
@@ -57,16 +47,9 @@ void hostpack_upper16_avx512_cached(const float *P, float *out, size_t count);
 // ----------------------------------------------------------------------------------------
 // errors
 // ----------------------------------------------------------------------------------------
-static thread_local std::string g_err;
-
-#define QP_CUDA(call)                                                                          \
-	do {                                                                                   \
-		cudaError_t e_ = (call);                                                       \
-		if (e_ != cudaSuccess) {                                                       \
-			g_err = std::string(#call) + ": " + cudaGetErrorString(e_);            \
-			return QP_ERR_CUDA;                                                    \
-		}                                                                              \
-	} while (0)
+namespace qpb {
+thread_local std::string g_err;
+}
 
 extern "C" const char *qp_last_error(void)
 {
@@ -78,7 +61,7 @@ extern "C" int qp_device_count(void)
 	int n = 0;
 	if (cudaGetDeviceCount(&n) != cudaSuccess)
 		return 0;
-	return n;
+	return std::min(n, MAX_DEVICES);
 }
 
 extern "C" void qp_options_default(qp_options *o)
@@ -96,187 +79,59 @@ extern "C" void qp_options_default(qp_options *o)
 	o->stream = nullptr;
 	o->chunk = 0;
 	o->kernel = QP_KERNEL_AUTO;
+	o->schedule = QP_SCHEDULE_AUTO;
+}
+
+extern "C" size_t qp_packed_stride(uint32_t n)
+{
+	return size_t(tpq_packed_stride(int(n)));
 }
 
 // ----------------------------------------------------------------------------------------
 // kernel selection and launch
 // ----------------------------------------------------------------------------------------
-namespace {
-
-struct DevInfo {
-	int sms = 0;
-	bool ok = false;
-};
-DevInfo g_dev[64];
-std::mutex g_dev_mu;
+namespace qpb {
 
 int dev_sms(int dev)
 {
-	std::lock_guard<std::mutex> lk(g_dev_mu);
-	if (!g_dev[dev].ok) {
+	static std::atomic<int> sms[MAX_DEVICES];
+	int v = sms[dev].load(std::memory_order_acquire);
+	if (!v) {
 		cudaDeviceProp pr;
 		if (cudaGetDeviceProperties(&pr, dev) != cudaSuccess)
 			return 0;
-		g_dev[dev].sms = pr.multiProcessorCount;
-		g_dev[dev].ok = true;
+		v = pr.multiProcessorCount;
+		sms[dev].store(v, std::memory_order_release);
 	}
-	return g_dev[dev].sms;
+	return v;
 }
 
-inline bool aligned16(const void *p)
+int resolve_device(int dev)
 {
-	return (reinterpret_cast<uintptr_t>(p) & 15u) == 0;
+	if (dev >= 0)
+		return dev < qp_device_count() ? dev : -1;
+	int cur = 0;
+	if (cudaGetDevice(&cur) != cudaSuccess)
+		return -1;
+	return cur < MAX_DEVICES ? cur : -1;
 }
 
-bool tpq_eligible(const KernelArgs &a)
+bool family_has_levels(int family, int n)
 {
-	const int n = a.n;
-	if (!(n == 4 || n == 8 || n == 12 || n == 16))
-		return false;
-	if ((a.lb == nullptr) != (a.ub == nullptr))
-		return false;
-	if ((a.z0 == nullptr) != (a.u0 == nullptr))
-		return false;
-	const void *ptrs[] = { a.P, a.q, a.lb, a.ub, a.z0, a.u0, a.x, a.z, a.lam };
-	for (const void *p : ptrs)
-		if (p && !aligned16(p))
-			return false;
-	return true;
+	return family == QP_KERNEL_TPQ || (family == QP_KERNEL_BPQ && n >= 8);
 }
 
-template <int N, bool B, bool W, bool R, bool PK>
-int launch_tpq(const KernelArgs &a, int dev, cudaStream_t st)
-{
-	using L = TpqLayout<N, B, W>;
-	using Cfg = TpqCfg<N, B, W>;
-	auto kern = qp_tpq_kernel<N, B, W, R, PK>;
-	static bool attr_done[64] = {};
-	if (!attr_done[dev]) {
-		QP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-					     int(L::BYTES)));
-		attr_done[dev] = true;
-	}
-	const unsigned long long nbatch = (a.count + 31ull) / 32ull;
-	unsigned long long grid = (unsigned long long)dev_sms(dev) * Cfg::MINB;
-	// every warp of a CTA should have a batch to work on
-	const unsigned long long need = (nbatch + Cfg::WARPS - 1) / Cfg::WARPS;
-	grid = std::max(1ull, std::min(grid, need));
-	kern<<<dim3((unsigned)grid), dim3(Cfg::WARPS * 32), L::BYTES, st>>>(a);
-	QP_CUDA(cudaGetLastError());
-	return QP_OK;
-}
+} // namespace qpb
 
-template <int N, bool PK> int launch_tpq_v(const KernelArgs &a, int dev, cudaStream_t st)
-{
-	const bool b = a.lb != nullptr, w = a.z0 != nullptr;
-	if (a.alpha != 1.0f) { // over-relaxation: separate instantiation, not a branch in the loop
-		if (b && w)
-			return launch_tpq<N, true, true, true, PK>(a, dev, st);
-		if (b)
-			return launch_tpq<N, true, false, true, PK>(a, dev, st);
-		if (w)
-			return launch_tpq<N, false, true, true, PK>(a, dev, st);
-		return launch_tpq<N, false, false, true, PK>(a, dev, st);
-	}
-	if (b && w)
-		return launch_tpq<N, true, true, false, PK>(a, dev, st);
-	if (b)
-		return launch_tpq<N, true, false, false, PK>(a, dev, st);
-	if (w)
-		return launch_tpq<N, false, true, false, PK>(a, dev, st);
-	return launch_tpq<N, false, false, false, PK>(a, dev, st);
-}
-
-// packed upper triangles arrive only from the host path, for n = 8, 12, 16
-template <int N> int launch_tpq_n(const KernelArgs &a, int dev, cudaStream_t st)
-{
-	if constexpr (N >= 8) {
-		if (a.p_packed)
-			return launch_tpq_v<N, true>(a, dev, st);
-	}
-	return launch_tpq_v<N, false>(a, dev, st);
-}
-
-template <int NP, bool PFI> int launch_gpq_form(const KernelArgs &a, int dev, cudaStream_t st)
-{
-	constexpr int T = GpqLanes<NP>::T; // lanes per QP; 32 / T problems per warp
-	auto kern = qp_gpq_kernel<NP, T, PFI>;
-	static int per_sm[64] = {};
-	if (!per_sm[dev]) {
-		int b = 0;
-		QP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, kern, GPQ_WARPS * 32, 0));
-		per_sm[dev] = std::max(1, b);
-	}
-	constexpr unsigned long long per_cta = GPQ_WARPS * (32 / T);
-	const unsigned long long need = (a.count + per_cta - 1) / per_cta;
-	unsigned long long grid = (unsigned long long)dev_sms(dev) * per_sm[dev];
-	grid = std::max(1ull, std::min(grid, need));
-	kern<<<dim3((unsigned)grid), dim3(GPQ_WARPS * 32), 0, st>>>(a);
-	QP_CUDA(cudaGetLastError());
-	return QP_OK;
-}
-
-template <int NP> int launch_gpq(const KernelArgs &a, int dev, cudaStream_t st)
-{
-	// n >= 48: the elimination dominates up to ~20-30 iterations: always the product form
-	if constexpr (NP >= QPB_GPQ_PFI_FROM)
-		return launch_gpq_form<NP, true>(a, dev, st);
-	else
-		return launch_gpq_form<NP, false>(a, dev, st);
-}
-
-bool bpq_eligible(const KernelArgs &a)
-{
-	const int n = a.n;
-	if (n % 8 != 0 || n > 40)
-		return false;
-	const void *ptrs[] = { a.P, a.q, a.lb, a.ub, a.z0, a.u0, a.x, a.z, a.lam };
-	for (const void *p : ptrs)
-		if (p && !aligned16(p))
-			return false;
-	return true;
-}
-
-template <int NP, bool PFI> int launch_bpq_form(const KernelArgs &a, int dev, cudaStream_t st)
-{
-	auto kern = qp_bpq_kernel<NP, PFI>;
-	static int per_sm[64] = {};
-	if (!per_sm[dev]) {
-		int b = 0;
-		QP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, kern, BPQ_WARPS * 32, 0));
-		per_sm[dev] = std::max(1, b);
-	}
-	constexpr unsigned long long per_cta = BPQ_WARPS * BpqCfg<NP>::G;
-	const unsigned long long need = (a.count + per_cta - 1) / per_cta;
-	unsigned long long grid = (unsigned long long)dev_sms(dev) * per_sm[dev];
-	grid = std::max(1ull, std::min(grid, need));
-	kern<<<dim3((unsigned)grid), dim3(BPQ_WARPS * 32), 0, st>>>(a);
-	QP_CUDA(cudaGetLastError());
-	return QP_OK;
-}
-
-template <int NP> int launch_bpq(const KernelArgs &a, int dev, cudaStream_t st)
-{
-	if constexpr (NP >= QPB_BPQ_PFI_FROM) {
-		if (a.z0 != nullptr)
-			return launch_bpq_form<NP, true>(a, dev, st);
-	}
-	return launch_bpq_form<NP, false>(a, dev, st);
-}
-
-template <int TT> int launch_cpq(const KernelArgs &a, int dev, cudaStream_t st)
-{
-	const unsigned long long grid = std::min<unsigned long long>(a.count, 2ull * dev_sms(dev));
-	qp_cpq_kernel<TT><<<dim3((unsigned)grid), dim3(CPQ_THREADS), 0, st>>>(a);
-	QP_CUDA(cudaGetLastError());
-	return QP_OK;
-}
+namespace {
 
 // which kernel family solves this batch (QP_KERNEL_*), 0 = none
 int pick_kernel(const KernelArgs &a, uint32_t forced)
 {
 	const bool t = tpq_eligible(a), b = bpq_eligible(a), g = a.n >= 1 && a.n <= QP_MAX_DIM;
 	const bool c = a.n >= 1 && a.n <= QP_MAX_DIM_BOX;
+	if (a.p_packed) // packed upper triangles: the thread-per-QP kernels only
+		return (t && a.n >= 8 && (forced == QP_KERNEL_AUTO || forced == QP_KERNEL_TPQ)) ? QP_KERNEL_TPQ : 0;
 	switch (forced) {
 	case QP_KERNEL_TPQ: return t ? QP_KERNEL_TPQ : 0;
 	case QP_KERNEL_BPQ: return b ? QP_KERNEL_BPQ : 0;
@@ -292,54 +147,111 @@ int pick_kernel(const KernelArgs &a, uint32_t forced)
 	return g ? QP_KERNEL_GPQ : 0;
 }
 
-int launch_solver(const KernelArgs &a, int dev, cudaStream_t st, uint32_t forced = QP_KERNEL_AUTO)
+// ---- scratch of the level scheduler: one grow-only arena per device -----------------------
+//
+// A launch with levels needs a counter block, two index lists, the saved (z, u, iterations)
+// of evicted problems and, for qp_bpq.cuh, their inverses.  The arena belongs to the library
+// (the reference's pools are static too, kmalloc/kmalloc.c:37-42); launches that use it are
+// chained by an event, so callers on different streams of one device never share it in time.
+struct DevArena {
+	std::mutex mu;
+	char *base = nullptr;
+	size_t bytes = 0;
+	cudaEvent_t last = nullptr; // recorded behind the latest launch that used the arena
+};
+DevArena g_arena[MAX_DEVICES];
+
+struct LevelPolicy {
+	unsigned cmin0, grow, thr, max_level;
+};
+
+// QPB200_LEVELS="cmin0,grow,thr,max_level" overrides the defaults (measurements)
+LevelPolicy level_policy(int family, int n)
+{
+	LevelPolicy pol;
+	if (family == QP_KERNEL_TPQ)
+		pol = { 16u, 2u, 12u, 6u }; // evict at <= 12 lanes after 16, 64, 256, ... iterations
+	else
+		pol = { 16u, 1u, unsigned(n / 4), 9u }; // bpq: when one group of n/4 lanes is left
+	if (const char *e = std::getenv("QPB200_LEVELS")) {
+		unsigned a = 0, b = 0, c = 0, d = 0;
+		if (std::sscanf(e, "%u,%u,%u,%u", &a, &b, &c, &d) == 4 && a > 0 && d > 0) {
+			pol.cmin0 = a, pol.grow = b, pol.max_level = std::min(d, unsigned(LEV_SLOTS - 2));
+			if (c > 0)
+				pol.thr = c;
+		}
+	}
+	return pol;
+}
+
+size_t up256(size_t v)
+{
+	return (v + 255) / 256 * 256;
+}
+
+// Solve one device-resident batch on `dev`, stream `st` (the device is current).
+int launch_solver(KernelArgs a, int dev, cudaStream_t st, uint32_t forced, uint32_t schedule)
 {
 	if (a.count == 0)
 		return QP_OK;
-	switch (pick_kernel(a, forced)) {
-	case QP_KERNEL_TPQ:
-		switch (a.n) {
-		case 4:  return launch_tpq_n<4>(a, dev, st);
-		case 8:  return launch_tpq_n<8>(a, dev, st);
-		case 12: return launch_tpq_n<12>(a, dev, st);
-		case 16: return launch_tpq_n<16>(a, dev, st);
-		}
-		break;
-	case QP_KERNEL_BPQ:
-		switch (a.n) {
-		case 8:  return launch_bpq<8>(a, dev, st);
-		case 16: return launch_bpq<16>(a, dev, st);
-		case 24: return launch_bpq<24>(a, dev, st);
-		case 32: return launch_bpq<32>(a, dev, st);
-		case 40: return launch_bpq<40>(a, dev, st);
-		}
-		break;
-	case QP_KERNEL_GPQ:
-		switch ((a.n + 7) / 8 * 8) {
-		case 8:  return launch_gpq<8>(a, dev, st);
-		case 16: return launch_gpq<16>(a, dev, st);
-		case 24: return launch_gpq<24>(a, dev, st);
-		case 32: return launch_gpq<32>(a, dev, st);
-		case 40: return launch_gpq<40>(a, dev, st);
-		case 48: return launch_gpq<48>(a, dev, st);
-		case 56: return launch_gpq<56>(a, dev, st);
-		case 64: return launch_gpq<64>(a, dev, st);
-		}
-		break;
-	case QP_KERNEL_CPQ:
-		switch ((a.n + 15) / 16) {
-		case 1: return launch_cpq<1>(a, dev, st);
-		case 2: return launch_cpq<2>(a, dev, st);
-		case 3: return launch_cpq<3>(a, dev, st);
-		case 4: return launch_cpq<4>(a, dev, st);
-		case 5: return launch_cpq<5>(a, dev, st);
-		case 6: return launch_cpq<6>(a, dev, st);
-		case 7: return launch_cpq<7>(a, dev, st);
-		case 8: return launch_cpq<8>(a, dev, st);
-		}
-		break;
+	const int fam = pick_kernel(a, forced);
+	if (!fam)
+		return QP_ERR_UNSUPPORTED;
+	bool levels = false;
+	if (family_has_levels(fam, a.n) && a.count < 0xfffff000ull) {
+		if (schedule == QP_SCHEDULE_LEVELS)
+			levels = a.max_iter > 16;
+		else if (schedule == QP_SCHEDULE_AUTO)
+			levels = a.max_iter > 64 && a.count >= 4096;
 	}
-	return QP_ERR_UNSUPPORTED;
+	auto launch = [&]() -> int {
+		switch (fam) {
+		case QP_KERNEL_TPQ: return launch_tpq_family(a, dev, st);
+		case QP_KERNEL_BPQ: return launch_bpq_family(a, dev, st);
+		case QP_KERNEL_GPQ: return launch_gpq_family(a, dev, st);
+		case QP_KERNEL_CPQ: return launch_cpq_family(a, dev, st);
+		}
+		return QP_ERR_UNSUPPORTED;
+	};
+	if (!levels)
+		return launch();
+
+	DevArena &ar = g_arena[dev];
+	std::lock_guard<std::mutex> lk(ar.mu);
+	const size_t c = size_t(a.count), n = size_t(a.n);
+	const bool want_R = fam == QP_KERNEL_BPQ;
+	const size_t o_list0 = up256(LEV_CTR_WORDS * 4), o_list1 = o_list0 + up256(c * 4),
+		     o_its = o_list1 + up256(c * 4), o_zs = o_its + up256(c * 4),
+		     o_us = o_zs + up256(c * n * 4), o_R = o_us + up256(c * n * 4),
+		     need = o_R + (want_R ? up256(c * n * n * 4) : 0);
+	if (!ar.last)
+		QP_CUDA(cudaEventCreateWithFlags(&ar.last, cudaEventDisableTiming));
+	if (ar.bytes < need) {
+		QP_CUDA(cudaEventSynchronize(ar.last)); // nobody is using the old one any more
+		if (ar.base)
+			cudaFree(ar.base);
+		ar.base = nullptr, ar.bytes = 0;
+		QP_CUDA(cudaMalloc(&ar.base, need));
+		ar.bytes = need;
+		// the kernels leave the counter block zero behind them; it starts zero
+		QP_CUDA(cudaMemset(ar.base, 0, o_list0));
+	}
+	QP_CUDA(cudaStreamWaitEvent(st, ar.last, 0));
+	const LevelPolicy pol = level_policy(fam, a.n);
+	a.lev.ctr = reinterpret_cast<unsigned *>(ar.base);
+	a.lev.list[1] = reinterpret_cast<unsigned *>(ar.base + o_list0); // level 1 reads list[1]
+	a.lev.list[0] = reinterpret_cast<unsigned *>(ar.base + o_list1);
+	a.lev.its = reinterpret_cast<int *>(ar.base + o_its);
+	a.lev.zs = reinterpret_cast<float *>(ar.base + o_zs);
+	a.lev.us = reinterpret_cast<float *>(ar.base + o_us);
+	a.lev.Rs = want_R ? reinterpret_cast<float *>(ar.base + o_R) : nullptr;
+	a.lev.cmin0 = pol.cmin0, a.lev.grow = pol.grow, a.lev.thr = pol.thr,
+	a.lev.max_level = pol.max_level;
+	const int rc = launch();
+	if (rc != QP_OK)
+		return rc;
+	QP_CUDA(cudaEventRecord(ar.last, st));
+	return QP_OK;
 }
 
 int check_problem(const qp_batch *pb, const qp_batch_solution *sol)
@@ -352,6 +264,10 @@ int check_problem(const qp_batch *pb, const qp_batch_solution *sol)
 		return QP_ERR_UNSUPPORTED;
 	if (pb->mem != QP_MEM_HOST && pb->mem != QP_MEM_DEVICE)
 		return QP_ERR_INVALID;
+	if (pb->p_layout != QP_P_DENSE && pb->p_layout != QP_P_UPPER)
+		return QP_ERR_INVALID;
+	if (pb->p_layout == QP_P_UPPER && !(pb->n == 8 || pb->n == 12 || pb->n == 16))
+		return QP_ERR_UNSUPPORTED;
 	if (pb->count && (!pb->P || !pb->q))
 		return QP_ERR_INVALID;
 	return QP_OK;
@@ -365,12 +281,14 @@ int check_options(const qp_options &o)
 		return QP_ERR_INVALID;
 	if (!(o.abstol >= 0.0f) || !(o.reltol >= 0.0f))
 		return QP_ERR_INVALID;
+	if (o.schedule > QP_SCHEDULE_LEVELS)
+		return QP_ERR_INVALID;
 	return QP_OK;
 }
 
 KernelArgs make_args(const qp_batch &pb, const qp_batch_solution &sol, const qp_options &o)
 {
-	KernelArgs a;
+	KernelArgs a = {};
 	a.P = pb.P, a.q = pb.q, a.lb = pb.lb, a.ub = pb.ub, a.z0 = pb.z0, a.u0 = pb.u0;
 	a.x = sol.x, a.z = sol.z, a.lam = sol.lambda, a.status = sol.status, a.iters = sol.iters;
 	a.count = pb.count;
@@ -382,39 +300,8 @@ KernelArgs make_args(const qp_batch &pb, const qp_batch_solution &sol, const qp_
 	a.eps_abs = float(std::sqrt(double(pb.n)) * double(o.abstol));
 	a.reltol = o.reltol;
 	a.max_iter = o.max_iter;
-	a.p_packed = 0;
+	a.p_packed = pb.p_layout == QP_P_UPPER ? 1 : 0;
 	return a;
-}
-
-struct DeviceGuard {
-	int prev = -1;
-	bool changed = false;
-	int enter(int dev)
-	{
-		if (cudaGetDevice(&prev) != cudaSuccess)
-			return QP_ERR_NO_DEVICE;
-		if (dev != prev) {
-			if (cudaSetDevice(dev) != cudaSuccess)
-				return QP_ERR_NO_DEVICE;
-			changed = true;
-		}
-		return QP_OK;
-	}
-	~DeviceGuard()
-	{
-		if (changed)
-			cudaSetDevice(prev);
-	}
-};
-
-int resolve_device(int dev)
-{
-	if (dev >= 0)
-		return dev < qp_device_count() ? dev : -1;
-	int cur = 0;
-	if (cudaGetDevice(&cur) != cudaSuccess)
-		return -1;
-	return cur;
 }
 
 } // namespace
@@ -707,11 +594,18 @@ struct DeviceCtx {
 	double h2d_bytes_per_s = 0.0; // measured on the packed copies
 };
 
+// `cap` is the capacity of a slot in problems: every buffer is laid out for it, and it only
+// grows.  A call cuts its shards into chunks of any size up to cap, so batches of different
+// sizes share one workspace without reallocation.
 struct qp_workspace {
 	uint32_t n = 0;
-	size_t chunk = 0; // problems per slot
+	size_t cap = 0;
 	std::vector<DeviceCtx> devs;
-	std::mutex mu;
+	std::mutex mu; // held for the whole of a solve
+	// default-workspace cache (qp_solve_batch): key and age
+	uint32_t key_mask = 0;
+	int key_dev = -1;
+	unsigned long stamp = 0;
 };
 
 namespace {
@@ -756,6 +650,8 @@ void free_ctx(DeviceCtx &c)
 	int prev = 0;
 	cudaGetDevice(&prev);
 	cudaSetDevice(c.dev);
+	if (c.pool)
+		c.pool->wait();
 	for (Slot &s : c.slot) {
 		if (s.stream)
 			cudaStreamSynchronize(s.stream);
@@ -785,34 +681,56 @@ void free_ctx(DeviceCtx &c)
 	cudaSetDevice(prev);
 }
 
-int alloc_ctx(DeviceCtx &c, uint32_t n, size_t chunk)
+int alloc_ctx(DeviceCtx &c, uint32_t n, size_t cap)
 {
 	DeviceGuard g;
 	if (g.enter(c.dev) != QP_OK)
 		return QP_ERR_NO_DEVICE;
 	for (Slot &s : c.slot) {
 		// one allocation per slot, carved up (all offsets are multiples of 16 bytes
-		// because chunk is a multiple of 32)
-		const size_t fl = chunk * (in_floats(n) + out_floats(n));
+		// because cap is a multiple of 32)
+		const size_t fl = cap * (in_floats(n) + out_floats(n));
 		float *base = nullptr;
 		QP_CUDA(cudaMalloc(&base, fl * 4));
 		s.dP = base;
-		s.dq = s.dP + chunk * n * n;
-		s.dlb = s.dq + chunk * n;
-		s.dub = s.dlb + chunk * n;
-		s.dz0 = s.dub + chunk * n;
-		s.du0 = s.dz0 + chunk * n;
-		s.drho = s.du0 + chunk * n;
-		s.dx = s.drho + chunk;
-		s.dz = s.dx + chunk * n;
-		s.dlam = s.dz + chunk * n;
-		s.dstatus = reinterpret_cast<int32_t *>(s.dlam + chunk * n);
-		s.diters = s.dstatus + chunk;
+		s.dq = s.dP + cap * n * n;
+		s.dlb = s.dq + cap * n;
+		s.dub = s.dlb + cap * n;
+		s.dz0 = s.dub + cap * n;
+		s.du0 = s.dz0 + cap * n;
+		s.drho = s.du0 + cap * n;
+		s.dx = s.drho + cap;
+		s.dz = s.dx + cap * n;
+		s.dlam = s.dz + cap * n;
+		s.dstatus = reinterpret_cast<int32_t *>(s.dlam + cap * n);
+		s.diters = s.dstatus + cap;
 		QP_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
 		QP_CUDA(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
 		QP_CUDA(cudaEventCreate(&s.t0));
 		QP_CUDA(cudaEventCreate(&s.t1));
 	}
+	return QP_OK;
+}
+
+// (re)allocate every device context of ws for a slot capacity of `cap` problems.  On failure
+// the workspace is left empty (cap = 0), never half built.
+int resize_workspace(qp_workspace *ws, size_t cap)
+{
+	cap = (cap + 31) / 32 * 32;
+	for (DeviceCtx &c : ws->devs)
+		free_ctx(c);
+	ws->cap = 0;
+	for (DeviceCtx &c : ws->devs) {
+		const int rc = alloc_ctx(c, ws->n, cap);
+		if (rc != QP_OK) {
+			const std::string keep = g_err;
+			for (DeviceCtx &d : ws->devs)
+				free_ctx(d);
+			g_err = keep;
+			return rc;
+		}
+	}
+	ws->cap = cap;
 	return QP_OK;
 }
 
@@ -828,15 +746,33 @@ bool is_pinned(const void *p)
 	return at.type == cudaMemoryTypeHost;
 }
 
-// One GPU's share of a host-memory solve: chunks [lo, hi) of the batch.
-int run_shard(qp_workspace *ws, DeviceCtx &ctx, const qp_batch &pb, const qp_batch_solution &sol,
-	      const qp_options &opt, size_t lo, size_t hi)
+// After a failure in the middle of a shard: nothing of this call may stay in flight, because
+// the streams, the packing workers and the pinned buffers would go on touching the caller's
+// arrays after the call has returned (and the next call on the workspace would retire the
+// stale chunks into ITS caller's arrays).
+void quiesce(DeviceCtx &ctx)
 {
-	DeviceGuard g;
-	if (g.enter(ctx.dev) != QP_OK)
-		return QP_ERR_NO_DEVICE;
+	if (ctx.pool)
+		ctx.pool->wait();
+	for (Slot &s : ctx.slot) {
+		if (s.stream)
+			cudaStreamSynchronize(s.stream);
+		s.busy = false, s.timed = false;
+	}
+	for (bool &b : ctx.hpk_busy)
+		b = false;
+	cudaGetLastError();
+}
+
+// One GPU's share of a host-memory solve: problems [lo, hi) of the batch in chunks of `chunk`.
+int run_shard_body(qp_workspace *ws, DeviceCtx &ctx, const qp_batch &pb, const qp_batch_solution &sol,
+		   const qp_options &opt, size_t lo, size_t hi, size_t chunk)
+{
 	const uint32_t n = pb.n;
-	const size_t chunk = ws->chunk;
+	const size_t cap = ws->cap;
+	const bool upper_in = pb.p_layout == QP_P_UPPER; // the caller's P is packed already
+	const int pk = tpq_packed_stride(int(n));
+	const size_t p_per = upper_in ? size_t(pk) : size_t(n) * n; // floats of P per problem
 	const bool pin_in = is_pinned(pb.P) && is_pinned(pb.q) && is_pinned(pb.lb) &&
 			    is_pinned(pb.ub) && is_pinned(pb.z0) && is_pinned(pb.u0) &&
 			    is_pinned(pb.rho);
@@ -850,7 +786,7 @@ int run_shard(qp_workspace *ws, DeviceCtx &ctx, const qp_batch &pb, const qp_bat
 		if (s.timed) {
 			float ms = 0.0f;
 			if (cudaEventElapsedTime(&ms, s.t0, s.t1) == cudaSuccess && ms > 0.0f)
-				ctx.h2d_bytes_per_s = double(s.cnt) * tpq_packed_stride(int(n)) * 4.0 / (ms * 1e-3);
+				ctx.h2d_bytes_per_s = double(s.cnt) * pk * 4.0 / (ms * 1e-3);
 			s.timed = false;
 		}
 		if (!pin_out) {
@@ -859,14 +795,14 @@ int run_shard(qp_workspace *ws, DeviceCtx &ctx, const qp_batch &pb, const qp_bat
 			if (sol.x)
 				std::memcpy(sol.x + f * n, h, c * n * 4);
 			if (sol.z)
-				std::memcpy(sol.z + f * n, h + chunk * n, c * n * 4);
+				std::memcpy(sol.z + f * n, h + cap * n, c * n * 4);
 			if (sol.lambda)
-				std::memcpy(sol.lambda + f * n, h + 2 * chunk * n, c * n * 4);
-			const int32_t *hi32 = reinterpret_cast<const int32_t *>(h + 3 * chunk * n);
+				std::memcpy(sol.lambda + f * n, h + 2 * cap * n, c * n * 4);
+			const int32_t *hi32 = reinterpret_cast<const int32_t *>(h + 3 * cap * n);
 			if (sol.status)
 				std::memcpy(sol.status + f, hi32, c * 4);
 			if (sol.iters)
-				std::memcpy(sol.iters + f, hi32 + chunk, c * 4);
+				std::memcpy(sol.iters + f, hi32 + cap, c * 4);
 		}
 		s.busy = false;
 		return QP_OK;
@@ -874,10 +810,9 @@ int run_shard(qp_workspace *ws, DeviceCtx &ctx, const qp_batch &pb, const qp_bat
 
 	// pack the upper triangles of P on the host when the thread-per-QP kernel will run
 	const unsigned tpg = host_threads_per_gpu(unsigned(ws->devs.size()));
-	const bool pack0 = !ctx.pack_off && qp_host_path_packs(n) && tpg >= 12 &&
+	const bool pack0 = !upper_in && !ctx.pack_off && qp_host_path_packs(n) && tpg >= 12 &&
 			  (opt.kernel == QP_KERNEL_AUTO || opt.kernel == QP_KERNEL_TPQ) &&
 			  ((pb.lb == nullptr) == (pb.ub == nullptr)) && ((pb.z0 == nullptr) == (pb.u0 == nullptr));
-	const int pk = tpq_packed_stride(int(n));
 	if (pack0 && !ctx.pool)
 	{
 		// three quarters of the hardware threads: the path is bound by the host's memory
@@ -911,7 +846,7 @@ int run_shard(qp_workspace *ws, DeviceCtx &ctx, const qp_batch &pb, const qp_bat
 		if (!pack0 || ctx.pack_off || job.valid || front >= back)
 			return QP_OK;
 		if (!ctx.hpk[pbuf]) {
-			QP_CUDA(cudaMallocHost(&ctx.hpk[pbuf], chunk * size_t(pk) * 4));
+			QP_CUDA(cudaMallocHost(&ctx.hpk[pbuf], cap * size_t(pk) * 4));
 			QP_CUDA(cudaEventCreateWithFlags(&ctx.hpk_free[pbuf], cudaEventDisableTiming));
 		} else if (ctx.hpk_busy[pbuf]) {
 			const cudaError_t e = cudaEventQuery(ctx.hpk_free[pbuf]);
@@ -980,11 +915,8 @@ int run_shard(qp_workspace *ws, DeviceCtx &ctx, const qp_batch &pb, const qp_bat
 			rc = retire(s);
 		if (rc == QP_OK)
 			rc = pump();
-		if (rc != QP_OK) {
-			if (job.valid)
-				ctx.pool->wait();
+		if (rc != QP_OK)
 			return rc;
-		}
 		if (host_pack_test_switch() && k >= 3 && !ctx.pack_off) {
 			ctx.pack_off = true;
 			g_pack_given_up.store(true);
@@ -1015,8 +947,8 @@ int run_shard(qp_workspace *ws, DeviceCtx &ctx, const qp_batch &pb, const qp_bat
 			const float *src;
 			float *dst;
 			size_t per;
-		} ins[] = { { pb.P, s.dP, size_t(n) * n }, { pb.q, s.dq, n },  { pb.lb, s.dlb, n },
-			    { pb.ub, s.dub, n },           { pb.z0, s.dz0, n }, { pb.u0, s.du0, n },
+		} ins[] = { { pb.P, s.dP, p_per },   { pb.q, s.dq, n },   { pb.lb, s.dlb, n },
+			    { pb.ub, s.dub, n },     { pb.z0, s.dz0, n }, { pb.u0, s.du0, n },
 			    { pb.rho, s.drho, 1 } };
 		{
 			size_t wire = pack ? c * size_t(pk) * 4 : 0;
@@ -1040,7 +972,7 @@ int run_shard(qp_workspace *ws, DeviceCtx &ctx, const qp_batch &pb, const qp_bat
 								cudaMemcpyHostToDevice, st));
 		} else {
 			if (!s.hin)
-				QP_CUDA(cudaMallocHost(&s.hin, chunk * in_floats(n) * 4));
+				QP_CUDA(cudaMallocHost(&s.hin, cap * in_floats(n) * 4));
 			size_t off = 0;
 			for (const In &i : ins) {
 				if (i.src && !(pack && i.src == pb.P)) {
@@ -1048,7 +980,7 @@ int run_shard(qp_workspace *ws, DeviceCtx &ctx, const qp_batch &pb, const qp_bat
 					QP_CUDA(cudaMemcpyAsync(i.dst, s.hin + off, c * i.per * 4,
 								cudaMemcpyHostToDevice, st));
 				}
-				off += chunk * i.per;
+				off += cap * (i.src == pb.P ? size_t(n) * n : i.per);
 			}
 		}
 
@@ -1060,14 +992,14 @@ int run_shard(qp_workspace *ws, DeviceCtx &ctx, const qp_batch &pb, const qp_bat
 		dpb.lb = pb.lb ? s.dlb : nullptr, dpb.ub = pb.ub ? s.dub : nullptr;
 		dpb.z0 = pb.z0 ? s.dz0 : nullptr, dpb.u0 = pb.u0 ? s.du0 : nullptr;
 		dpb.rho = pb.rho ? s.drho : nullptr;
+		dpb.p_layout = (pack || upper_in) ? QP_P_UPPER : QP_P_DENSE;
 		qp_batch_solution dsol;
 		dsol.x = sol.x ? s.dx : nullptr, dsol.z = sol.z ? s.dz : nullptr;
 		dsol.lambda = sol.lambda ? s.dlam : nullptr;
 		dsol.status = sol.status ? s.dstatus : nullptr;
 		dsol.iters = sol.iters ? s.diters : nullptr;
-		KernelArgs ka = make_args(dpb, dsol, opt);
-		ka.p_packed = pack ? 1 : 0;
-		rc = launch_solver(ka, ctx.dev, st, pack ? uint32_t(QP_KERNEL_TPQ) : opt.kernel);
+		rc = launch_solver(make_args(dpb, dsol, opt), ctx.dev, st,
+				   pack ? uint32_t(QP_KERNEL_TPQ) : opt.kernel, opt.schedule);
 		if (rc != QP_OK)
 			return rc;
 
@@ -1090,22 +1022,22 @@ int run_shard(qp_workspace *ws, DeviceCtx &ctx, const qp_batch &pb, const qp_bat
 							cudaMemcpyDeviceToHost, st));
 		} else {
 			if (!s.hout)
-				QP_CUDA(cudaMallocHost(&s.hout, chunk * out_floats(n) * 4));
+				QP_CUDA(cudaMallocHost(&s.hout, cap * out_floats(n) * 4));
 			float *h = s.hout;
 			if (sol.x)
 				QP_CUDA(cudaMemcpyAsync(h, s.dx, c * n * 4, cudaMemcpyDeviceToHost, st));
 			if (sol.z)
-				QP_CUDA(cudaMemcpyAsync(h + chunk * n, s.dz, c * n * 4,
+				QP_CUDA(cudaMemcpyAsync(h + cap * n, s.dz, c * n * 4,
 							cudaMemcpyDeviceToHost, st));
 			if (sol.lambda)
-				QP_CUDA(cudaMemcpyAsync(h + 2 * chunk * n, s.dlam, c * n * 4,
+				QP_CUDA(cudaMemcpyAsync(h + 2 * cap * n, s.dlam, c * n * 4,
 							cudaMemcpyDeviceToHost, st));
-			int32_t *hi32 = reinterpret_cast<int32_t *>(h + 3 * chunk * n);
+			int32_t *hi32 = reinterpret_cast<int32_t *>(h + 3 * cap * n);
 			if (sol.status)
 				QP_CUDA(cudaMemcpyAsync(hi32, s.dstatus, c * 4, cudaMemcpyDeviceToHost,
 							st));
 			if (sol.iters)
-				QP_CUDA(cudaMemcpyAsync(hi32 + chunk, s.diters, c * 4,
+				QP_CUDA(cudaMemcpyAsync(hi32 + cap, s.diters, c * 4,
 							cudaMemcpyDeviceToHost, st));
 		}
 		QP_CUDA(cudaEventRecord(s.done, st));
@@ -1119,6 +1051,76 @@ int run_shard(qp_workspace *ws, DeviceCtx &ctx, const qp_batch &pb, const qp_bat
 			return rc;
 	}
 	return QP_OK;
+}
+
+int run_shard(qp_workspace *ws, DeviceCtx &ctx, const qp_batch &pb, const qp_batch_solution &sol,
+	      const qp_options &opt, size_t lo, size_t hi, size_t chunk)
+{
+	DeviceGuard g;
+	if (g.enter(ctx.dev) != QP_OK)
+		return QP_ERR_NO_DEVICE;
+	const int rc = run_shard_body(ws, ctx, pb, sol, opt, lo, hi, chunk);
+	if (rc != QP_OK) {
+		const std::string keep = g_err;
+		quiesce(ctx);
+		g_err = keep;
+	}
+	return rc;
+}
+
+// chunk size of a call: the caller's, else ~32 MB of input, never more than the slots hold
+size_t call_chunk(const qp_workspace *ws, const qp_batch &pb, const qp_options &opt)
+{
+	const size_t nd = std::max<size_t>(1, ws->devs.size());
+	size_t c = opt.chunk ? (size_t(opt.chunk) + 31) / 32 * 32
+			     : choose_chunk(pb.n, (pb.count + nd - 1) / nd);
+	return std::min(c, ws->cap);
+}
+
+// the solve itself; ws->mu is held by the caller
+int solve_host_locked(qp_workspace *ws, const qp_batch &pb, const qp_batch_solution &sol,
+		      const qp_options &opt)
+{
+	if (ws->cap == 0)
+		return QP_ERR_INVALID;
+	const size_t chunk = call_chunk(ws, pb, opt);
+	const size_t nd = ws->devs.size();
+	if (nd == 1)
+		return run_shard(ws, ws->devs[0], pb, sol, opt, 0, pb.count, chunk);
+
+	// contiguous shards, remainder to the first devices: one host thread per
+	// GPU, results land in the caller's arrays at the shard's offset (the "host-side gather")
+	std::vector<int> rcs(nd, QP_OK);
+	std::vector<std::string> errs(nd);
+	std::vector<std::thread> th;
+	const size_t base = pb.count / nd, rem = pb.count % nd;
+	size_t lo = 0;
+	for (size_t i = 0; i < nd; ++i) {
+		const size_t hi = lo + base + (i < rem ? 1 : 0);
+		if (hi > lo)
+			th.emplace_back([&, i, lo, hi] {
+				rcs[i] = run_shard(ws, ws->devs[i], pb, sol, opt, lo, hi, chunk);
+				errs[i] = g_err;
+			});
+		lo = hi;
+	}
+	for (std::thread &t : th)
+		t.join();
+	for (size_t i = 0; i < nd; ++i)
+		if (rcs[i] != QP_OK) {
+			g_err = errs[i];
+			return rcs[i];
+		}
+	return QP_OK;
+}
+
+int resolve_options(const qp_options *opt_in, qp_options &opt)
+{
+	if (opt_in)
+		opt = *opt_in;
+	else
+		qp_options_default(&opt);
+	return check_options(opt);
 }
 
 } // namespace
@@ -1135,18 +1137,14 @@ extern "C" int qp_workspace_create(uint32_t n, size_t max_count, uint32_t device
 		return QP_ERR_NO_DEVICE;
 	qp_workspace *ws = new qp_workspace;
 	ws->n = n;
-	const size_t per_dev = (std::max<size_t>(max_count, 1) + devs.size() - 1) / devs.size();
-	ws->chunk = choose_chunk(n, per_dev);
 	ws->devs.resize(devs.size());
-	for (size_t i = 0; i < devs.size(); ++i) {
+	for (size_t i = 0; i < devs.size(); ++i)
 		ws->devs[i].dev = devs[i];
-		int rc = alloc_ctx(ws->devs[i], n, ws->chunk);
-		if (rc != QP_OK) {
-			std::string keep = g_err;
-			qp_workspace_destroy(ws);
-			g_err = keep;
-			return rc;
-		}
+	const size_t per_dev = (std::max<size_t>(max_count, 1) + devs.size() - 1) / devs.size();
+	const int rc = resize_workspace(ws, choose_chunk(n, per_dev));
+	if (rc != QP_OK) {
+		delete ws;
+		return rc;
 	}
 	*out = ws;
 	return QP_OK;
@@ -1156,8 +1154,11 @@ extern "C" void qp_workspace_destroy(qp_workspace *ws)
 {
 	if (!ws)
 		return;
-	for (DeviceCtx &c : ws->devs)
-		free_ctx(c);
+	{
+		std::lock_guard<std::mutex> lk(ws->mu); // a solve still running on it finishes first
+		for (DeviceCtx &c : ws->devs)
+			free_ctx(c);
+	}
 	delete ws;
 }
 
@@ -1168,11 +1169,7 @@ extern "C" int qp_solve_batch_ws(qp_workspace *ws, const qp_batch *pb,
 	if (rc != QP_OK)
 		return rc;
 	qp_options opt;
-	if (opt_in)
-		opt = *opt_in;
-	else
-		qp_options_default(&opt);
-	rc = check_options(opt);
+	rc = resolve_options(opt_in, opt);
 	if (rc != QP_OK)
 		return rc;
 	if (pb->count == 0)
@@ -1185,48 +1182,71 @@ extern "C" int qp_solve_batch_ws(qp_workspace *ws, const qp_batch *pb,
 		DeviceGuard g;
 		if (g.enter(dev) != QP_OK)
 			return QP_ERR_NO_DEVICE;
-		return launch_solver(make_args(*pb, *sol, opt), dev,
-				     static_cast<cudaStream_t>(opt.stream), opt.kernel);
+		return launch_solver(make_args(*pb, *sol, opt), dev, static_cast<cudaStream_t>(opt.stream),
+				     opt.kernel, opt.schedule);
 	}
 
 	if (!ws || ws->n != pb->n)
 		return QP_ERR_INVALID;
 	std::lock_guard<std::mutex> lk(ws->mu);
-	const size_t nd = ws->devs.size();
-	if (nd == 1)
-		return run_shard(ws, ws->devs[0], *pb, *sol, opt, 0, pb->count);
-
-	// contiguous shards, remainder to the first devices
-	std::vector<int> rcs(nd, QP_OK);
-	std::vector<std::string> errs(nd);
-	std::vector<std::thread> th;
-	const size_t base = pb->count / nd, rem = pb->count % nd;
-	size_t lo = 0;
-	for (size_t i = 0; i < nd; ++i) {
-		const size_t hi = lo + base + (i < rem ? 1 : 0);
-		if (hi > lo)
-			th.emplace_back([&, i, lo, hi] {
-				rcs[i] = run_shard(ws, ws->devs[i], *pb, *sol, opt, lo, hi);
-				errs[i] = g_err;
-			});
-		lo = hi;
+	// an explicit chunk larger than the slots: grow (the capacity never shrinks)
+	const size_t want = opt.chunk ? (size_t(opt.chunk) + 31) / 32 * 32 : 0;
+	if (want > ws->cap) {
+		rc = resize_workspace(ws, want);
+		if (rc != QP_OK)
+			return rc;
 	}
-	for (std::thread &t : th)
-		t.join();
-	for (size_t i = 0; i < nd; ++i)
-		if (rcs[i] != QP_OK) {
-			g_err = errs[i];
-			return rcs[i];
+	return solve_host_locked(ws, *pb, *sol, opt);
+}
+
+// Default workspaces of qp_solve_batch(): a small cache keyed by (n, device set, device).
+// An entry is handed out as a shared_ptr and its mutex is held for the whole solve, so a
+// second host thread with another shape gets another entry and a thread with the same shape
+// waits its turn -- nobody's streams and pinned buffers are freed under a running solve.  The
+// slot capacity of an entry only grows: alternating batch sizes reuse the same buffers.
+namespace {
+
+struct WsDeleter {
+	void operator()(qp_workspace *ws) const { qp_workspace_destroy(ws); }
+};
+std::vector<std::shared_ptr<qp_workspace>> g_cache;
+std::mutex g_cache_mu;
+unsigned long g_cache_clock = 0;
+constexpr size_t CACHE_ENTRIES = 6;
+
+int default_workspace(uint32_t n, uint32_t mask, int dev, std::shared_ptr<qp_workspace> &out)
+{
+	std::lock_guard<std::mutex> lk(g_cache_mu);
+	for (auto &e : g_cache)
+		if (e->n == n && e->key_mask == mask && e->key_dev == dev) {
+			e->stamp = ++g_cache_clock;
+			out = e;
+			return QP_OK;
 		}
+	std::vector<int> devs = mask_devices(mask, dev);
+	if (devs.empty())
+		return QP_ERR_NO_DEVICE;
+	if (g_cache.size() >= CACHE_ENTRIES) {
+		// drop the least recently used entry nobody holds (its owner frees it otherwise)
+		size_t victim = g_cache.size();
+		for (size_t i = 0; i < g_cache.size(); ++i)
+			if (g_cache[i].use_count() == 1 &&
+			    (victim == g_cache.size() || g_cache[i]->stamp < g_cache[victim]->stamp))
+				victim = i;
+		if (victim < g_cache.size())
+			g_cache.erase(g_cache.begin() + victim);
+	}
+	std::shared_ptr<qp_workspace> ws(new qp_workspace, WsDeleter());
+	ws->n = n, ws->key_mask = mask, ws->key_dev = dev, ws->stamp = ++g_cache_clock;
+	ws->devs.resize(devs.size());
+	for (size_t i = 0; i < devs.size(); ++i)
+		ws->devs[i].dev = devs[i];
+	g_cache.push_back(ws); // empty (cap = 0): sized under its own mutex by the first solve
+	out = ws;
 	return QP_OK;
 }
 
-// default workspace kept by qp_solve_batch(): rebuilt when the shape, the device set or
-// the needed capacity changes
-static qp_workspace *g_default_ws = nullptr;
-static uint32_t g_default_mask = 0;
-static int g_default_dev = -1;
-static std::mutex g_default_mu;
+} // namespace
 
 extern "C" int qp_solve_batch(const qp_batch *pb, const qp_batch_solution *sol,
 			      const qp_options *opt_in)
@@ -1238,82 +1258,31 @@ extern "C" int qp_solve_batch(const qp_batch *pb, const qp_batch_solution *sol,
 		return qp_solve_batch_ws(nullptr, pb, sol, opt_in);
 
 	qp_options opt;
-	if (opt_in)
-		opt = *opt_in;
-	else
-		qp_options_default(&opt);
+	rc = resolve_options(opt_in, opt);
+	if (rc != QP_OK)
+		return rc;
 	const int dev = resolve_device(opt.device);
 	if (dev < 0)
 		return QP_ERR_NO_DEVICE;
-	qp_workspace *ws = nullptr;
-	{
-		std::lock_guard<std::mutex> lk(g_default_mu);
-		const size_t ndev = std::max<size_t>(1, mask_devices(opt.device_mask, dev).size());
-		const size_t want =
-			opt.chunk ? (size_t(opt.chunk) + 31) / 32 * 32
-				  : choose_chunk(pb->n, (pb->count + ndev - 1) / ndev);
-		if (g_default_ws &&
-		    (g_default_ws->n != pb->n || g_default_mask != opt.device_mask ||
-		     g_default_dev != dev || g_default_ws->chunk != want)) {
-			qp_workspace_destroy(g_default_ws);
-			g_default_ws = nullptr;
-		}
-		if (!g_default_ws) {
-			DeviceGuard g;
-			if (g.enter(dev) != QP_OK)
-				return QP_ERR_NO_DEVICE;
-			rc = qp_workspace_create(pb->n, pb->count, opt.device_mask, &g_default_ws);
-			if (rc != QP_OK)
-				return rc;
-			if (opt.chunk && g_default_ws->chunk != want) {
-				// honour an explicit chunk size
-				for (DeviceCtx &c : g_default_ws->devs)
-					free_ctx(c);
-				g_default_ws->chunk = want;
-				for (DeviceCtx &c : g_default_ws->devs) {
-					rc = alloc_ctx(c, pb->n, want);
-					if (rc != QP_OK)
-						return rc;
-				}
-			}
-			g_default_mask = opt.device_mask;
-			g_default_dev = dev;
-		}
-		ws = g_default_ws;
+	std::shared_ptr<qp_workspace> ws;
+	rc = default_workspace(pb->n, opt.device_mask, dev, ws);
+	if (rc != QP_OK)
+		return rc;
+	std::lock_guard<std::mutex> lk(ws->mu);
+	const size_t nd = ws->devs.size();
+	const size_t want = opt.chunk ? (size_t(opt.chunk) + 31) / 32 * 32
+				      : choose_chunk(pb->n, (pb->count + nd - 1) / nd);
+	if (want > ws->cap) {
+		rc = resize_workspace(ws.get(), want);
+		if (rc != QP_OK)
+			return rc;
 	}
-	return qp_solve_batch_ws(ws, pb, sol, &opt);
+	return solve_host_locked(ws.get(), *pb, *sol, opt);
 }
 
 // ----------------------------------------------------------------------------------------
 // objective evaluation (quadratic_form_eval, /root/reference/qp_solvers/qp.c:9-27)
 // ----------------------------------------------------------------------------------------
-__global__ void qp_eval_kernel(const float *__restrict__ P, const float *__restrict__ q,
-			       const float *__restrict__ x, float r, float *__restrict__ f, int n,
-			       unsigned long long count)
-{
-	const int lane = threadIdx.x & 31;
-	const unsigned long long w = (blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x) >> 5;
-	const unsigned long long nw = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
-	for (unsigned long long c = w; c < count; c += nw) {
-		const float *Pc = P + c * (unsigned long long)n * n;
-		const float *xc = x + c * (unsigned long long)n;
-		const float *qc = q + c * (unsigned long long)n;
-		float quad = 0.0f, lin = 0.0f;
-		// lane j accumulates column j: sum_i x_i P_ij, then times x_j (P symmetric or not)
-		for (int j = lane; j < n; j += 32) {
-			float t = 0.0f;
-			for (int i = 0; i < n; ++i)
-				t = fmaf(xc[i], Pc[(unsigned long long)i * n + j], t);
-			quad = fmaf(t, xc[j], quad);
-			lin = fmaf(qc[j], xc[j], lin);
-		}
-		quad = warp_sum(quad);
-		lin = warp_sum(lin);
-		if (lane == 0)
-			f[c] = fmaf(0.5f, quad, lin) + r;
-	}
-}
-
 extern "C" int qp_eval_batch(const qp_batch *pb, const float *x, float r, float *f,
 			     const qp_options *opt_in)
 {
@@ -1333,12 +1302,8 @@ extern "C" int qp_eval_batch(const qp_batch *pb, const float *x, float r, float 
 	if (g.enter(dev) != QP_OK)
 		return QP_ERR_NO_DEVICE;
 	const size_t n = pb->n, c = pb->count;
-	const unsigned grid = (unsigned)std::min<size_t>((c + 7) / 8, size_t(dev_sms(dev)) * 8);
 	if (pb->mem == QP_MEM_DEVICE) {
-		qp_eval_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(opt.stream)>>>(
-			pb->P, pb->q, x, r, f, int(n), c);
-		QP_CUDA(cudaGetLastError());
-		return QP_OK;
+		return launch_eval(pb->P, pb->q, x, r, f, int(n), c, dev, static_cast<cudaStream_t>(opt.stream));
 	}
 	float *d = nullptr;
 	QP_CUDA(cudaMalloc(&d, (c * n * n + 2 * c * n + c) * 4));
@@ -1348,13 +1313,14 @@ extern "C" int qp_eval_batch(const qp_batch *pb, const float *x, float r, float 
 		e = cudaMemcpy(dq, pb->q, c * n * 4, cudaMemcpyHostToDevice);
 	if (e == cudaSuccess)
 		e = cudaMemcpy(dx, x, c * n * 4, cudaMemcpyHostToDevice);
-	if (e == cudaSuccess) {
-		qp_eval_kernel<<<grid, 256>>>(dP, dq, dx, r, df, int(n), c);
-		e = cudaGetLastError();
-	}
+	int lrc = QP_OK;
 	if (e == cudaSuccess)
+		lrc = launch_eval(dP, dq, dx, r, df, int(n), c, dev, nullptr);
+	if (e == cudaSuccess && lrc == QP_OK)
 		e = cudaMemcpy(f, df, c * 4, cudaMemcpyDeviceToHost);
 	cudaFree(d);
+	if (lrc != QP_OK)
+		return lrc;
 	if (e != cudaSuccess) {
 		g_err = std::string("qp_eval_batch: ") + cudaGetErrorString(e);
 		return QP_ERR_CUDA;
@@ -1365,28 +1331,6 @@ extern "C" int qp_eval_batch(const qp_batch *pb, const float *x, float r, float 
 // ----------------------------------------------------------------------------------------
 // batched Newton (newton_method_with_line_search, /root/reference/qp_solvers/qp_solvers.c:103-144)
 // ----------------------------------------------------------------------------------------
-static int launch_newton(const NewtonArgs &a, int dev, cudaStream_t st)
-{
-	const size_t smem = NEWTON_WARPS * newton_smem_floats_per_warp(a.n) * sizeof(float);
-	static size_t attr_done[64] = {};
-	if (attr_done[dev] < smem) {
-		QP_CUDA(cudaFuncSetAttribute(qp_newton_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-					     int(NEWTON_WARPS * newton_smem_floats_per_warp(QP_MAX_DIM) *
-						 sizeof(float))));
-		attr_done[dev] = NEWTON_WARPS * newton_smem_floats_per_warp(QP_MAX_DIM) * sizeof(float);
-	}
-	int per_sm = 1;
-	QP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, qp_newton_kernel,
-							      NEWTON_WARPS * 32, smem));
-	per_sm = std::max(1, per_sm);
-	const unsigned long long need = (a.count + NEWTON_WARPS - 1) / NEWTON_WARPS;
-	const unsigned long long grid =
-		std::max(1ull, std::min((unsigned long long)dev_sms(dev) * per_sm, need));
-	qp_newton_kernel<<<dim3((unsigned)grid), dim3(NEWTON_WARPS * 32), smem, st>>>(a);
-	QP_CUDA(cudaGetLastError());
-	return QP_OK;
-}
-
 static int descent_batch(int gradient, const qp_batch *pb, const float *x0, unsigned iterations,
 			 float *x, int32_t *status, int32_t *steps, float *f, float r,
 			 const qp_options *opt_in)
@@ -1471,40 +1415,6 @@ extern "C" int qp_gradient_batch(const qp_batch *pb, const float *x0, unsigned i
 // ----------------------------------------------------------------------------------------
 // general rows l <= A x <= u (qp_gen.cuh)
 // ----------------------------------------------------------------------------------------
-template <int T> static int launch_gen_t(const GenArgs &a, int dev, cudaStream_t st)
-{
-	constexpr int G = 32 / T;
-	const size_t smem = GEN_WARPS * G * gen_smem_floats_per_group(a.n, a.m, T) * sizeof(float);
-	// the largest problem this group width takes: n = 2T, m = 4T
-	const size_t smem_max = GEN_WARPS * G * gen_smem_floats_per_group(2 * T, 4 * T, T) * sizeof(float);
-	static bool attr_done[64] = {};
-	if (!attr_done[dev]) {
-		QP_CUDA(cudaFuncSetAttribute(qp_gen_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-					     int(smem_max)));
-		attr_done[dev] = true;
-	}
-	int per_sm = 1;
-	QP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, qp_gen_kernel<T>, GEN_WARPS * 32, smem));
-	per_sm = std::max(1, per_sm);
-	const unsigned long long per_cta = GEN_WARPS * G;
-	const unsigned long long need = (a.count + per_cta - 1) / per_cta;
-	const unsigned long long grid =
-		std::max(1ull, std::min((unsigned long long)dev_sms(dev) * per_sm, need));
-	qp_gen_kernel<T><<<dim3((unsigned)grid), dim3(GEN_WARPS * 32), smem, st>>>(a);
-	QP_CUDA(cudaGetLastError());
-	return QP_OK;
-}
-
-static int launch_gen(const GenArgs &a, int dev, cudaStream_t st)
-{
-	switch (gen_lanes(a.n, a.m)) {
-	case 4:  return launch_gen_t<4>(a, dev, st);
-	case 8:  return launch_gen_t<8>(a, dev, st);
-	case 16: return launch_gen_t<16>(a, dev, st);
-	}
-	return launch_gen_t<32>(a, dev, st);
-}
-
 extern "C" int qp_solve_general_batch(const qp_general_batch *pb, const qp_general_solution *sol,
 				      const qp_options *opt_in)
 {
@@ -1745,108 +1655,77 @@ extern "C" const char *qp_kernel_for(uint32_t n, int al16)
 }
 
 // ----------------------------------------------------------------------------------------
-// roofline probes
+// pure-copy ceiling of the host-memory path
 // ----------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) qp_probe_fma_kernel(float *out, int iters, float a, float b)
+extern "C" double qp_probe_copy_seconds(int device, size_t h2d_bytes, size_t d2h_bytes, int pinned,
+					size_t piece_bytes, int repeats)
 {
-	float v[8];
-#pragma unroll
-	for (int k = 0; k < 8; ++k)
-		v[k] = float(threadIdx.x + k);
-	for (int i = 0; i < iters; ++i) {
-#pragma unroll
-		for (int r = 0; r < 8; ++r) {
-#pragma unroll
-			for (int k = 0; k < 8; ++k)
-				v[k] = fmaf(v[k], a, b);
+	const int dev = resolve_device(device);
+	if (dev < 0)
+		return double(QP_ERR_NO_DEVICE);
+	DeviceGuard g;
+	if (g.enter(dev) != QP_OK)
+		return double(QP_ERR_NO_DEVICE);
+	const size_t piece = piece_bytes ? piece_bytes : (32ull << 20);
+	char *din = nullptr, *dout = nullptr, *hin = nullptr, *hout = nullptr;
+	cudaStream_t s0 = nullptr, s1 = nullptr;
+	double best = -1.0;
+	bool ok = cudaMalloc(&din, std::max<size_t>(h2d_bytes, 16)) == cudaSuccess &&
+		  cudaMalloc(&dout, std::max<size_t>(d2h_bytes, 16)) == cudaSuccess &&
+		  cudaStreamCreateWithFlags(&s0, cudaStreamNonBlocking) == cudaSuccess &&
+		  cudaStreamCreateWithFlags(&s1, cudaStreamNonBlocking) == cudaSuccess;
+	if (ok && pinned)
+		ok = cudaMallocHost(&hin, std::max<size_t>(h2d_bytes, 16)) == cudaSuccess &&
+		     cudaMallocHost(&hout, std::max<size_t>(d2h_bytes, 16)) == cudaSuccess;
+	else if (ok) {
+		hin = static_cast<char *>(std::malloc(std::max<size_t>(h2d_bytes, 16)));
+		hout = static_cast<char *>(std::malloc(std::max<size_t>(d2h_bytes, 16)));
+		ok = hin && hout;
+	}
+	if (ok) {
+		std::memset(hin, 1, h2d_bytes);
+		std::memset(hout, 0, d2h_bytes);
+		cudaMemset(dout, 2, d2h_bytes);
+		for (int r = 0; r < std::max(1, repeats) + 1 && ok; ++r) {
+			cudaDeviceSynchronize();
+			const auto t0 = std::chrono::steady_clock::now();
+			size_t a = 0, b = 0;
+			while ((a < h2d_bytes || b < d2h_bytes) && ok) {
+				if (a < h2d_bytes) {
+					const size_t c = std::min(piece, h2d_bytes - a);
+					ok = cudaMemcpyAsync(din + a, hin + a, c, cudaMemcpyHostToDevice, s0) == cudaSuccess;
+					a += c;
+				}
+				if (b < d2h_bytes && ok) {
+					// the results are about a sixth of the inputs: keep the two directions in step
+					const size_t c = std::min(std::max<size_t>(piece * d2h_bytes / std::max<size_t>(h2d_bytes, 1), 1 << 16),
+								  d2h_bytes - b);
+					ok = cudaMemcpyAsync(hout + b, dout + b, c, cudaMemcpyDeviceToHost, s1) == cudaSuccess;
+					b += c;
+				}
+			}
+			ok = ok && cudaStreamSynchronize(s0) == cudaSuccess && cudaStreamSynchronize(s1) == cudaSuccess;
+			const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+			if (ok && r > 0)
+				best = best < 0.0 ? dt : std::min(best, dt);
 		}
 	}
-	float s = 0.0f;
-#pragma unroll
-	for (int k = 0; k < 8; ++k)
-		s += v[k];
-	if (s == 12345.678f)
-		out[0] = s;
-}
-
-extern "C" double qp_probe_fp32_tflops(int device, int repeats)
-{
-	const int dev = resolve_device(device);
-	if (dev < 0)
-		return 0.0;
-	DeviceGuard g;
-	if (g.enter(dev) != QP_OK)
-		return 0.0;
-	float *d = nullptr;
-	if (cudaMalloc(&d, 256) != cudaSuccess)
-		return 0.0;
-	const int sms = dev_sms(dev);
-	const int iters = 4096;
-	const dim3 grid(sms * 8), block(256);
-	cudaEvent_t e0, e1;
-	cudaEventCreate(&e0);
-	cudaEventCreate(&e1);
-	double best = 0.0;
-	for (int r = 0; r < std::max(1, repeats) + 1; ++r) {
-		cudaEventRecord(e0);
-		qp_probe_fma_kernel<<<grid, block>>>(d, iters, 0.999f, 0.001f);
-		cudaEventRecord(e1);
-		cudaEventSynchronize(e1);
-		float ms = 0;
-		cudaEventElapsedTime(&ms, e0, e1);
-		const double flops = 2.0 * 64.0 * iters * double(grid.x) * block.x;
-		if (r > 0 && ms > 0)
-			best = std::max(best, flops / (ms * 1e-3) / 1e12);
+	if (!ok) {
+		g_err = std::string("qp_probe_copy_seconds: ") + cudaGetErrorString(cudaGetLastError());
+		best = double(QP_ERR_CUDA);
 	}
-	cudaEventDestroy(e0);
-	cudaEventDestroy(e1);
-	cudaFree(d);
-	return best;
-}
-
-__global__ void qp_probe_copy_kernel(const float4 *__restrict__ src, float4 *__restrict__ dst,
-				     size_t n4)
-{
-	const size_t stride = size_t(gridDim.x) * blockDim.x;
-	for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < n4; i += stride)
-		dst[i] = src[i];
-}
-
-extern "C" double qp_probe_hbm_gbs(int device, size_t bytes, int repeats)
-{
-	const int dev = resolve_device(device);
-	if (dev < 0)
-		return 0.0;
-	DeviceGuard g;
-	if (g.enter(dev) != QP_OK)
-		return 0.0;
-	bytes = std::max<size_t>(bytes, 1 << 20) / 16 * 16;
-	float4 *a = nullptr, *b = nullptr;
-	if (cudaMalloc(&a, bytes) != cudaSuccess)
-		return 0.0;
-	if (cudaMalloc(&b, bytes) != cudaSuccess) {
-		cudaFree(a);
-		return 0.0;
+	if (pinned) {
+		cudaFreeHost(hin);
+		cudaFreeHost(hout);
+	} else {
+		std::free(hin);
+		std::free(hout);
 	}
-	cudaMemset(a, 1, bytes);
-	cudaEvent_t e0, e1;
-	cudaEventCreate(&e0);
-	cudaEventCreate(&e1);
-	double best = 0.0;
-	const int sms = dev_sms(dev);
-	for (int r = 0; r < std::max(1, repeats) + 1; ++r) {
-		cudaEventRecord(e0);
-		qp_probe_copy_kernel<<<sms * 16, 512>>>(a, b, bytes / 16);
-		cudaEventRecord(e1);
-		cudaEventSynchronize(e1);
-		float ms = 0;
-		cudaEventElapsedTime(&ms, e0, e1);
-		if (r > 0 && ms > 0)
-			best = std::max(best, 2.0 * double(bytes) / (ms * 1e-3) / 1e9);
-	}
-	cudaEventDestroy(e0);
-	cudaEventDestroy(e1);
-	cudaFree(a);
-	cudaFree(b);
+	cudaFree(din);
+	cudaFree(dout);
+	if (s0)
+		cudaStreamDestroy(s0);
+	if (s1)
+		cudaStreamDestroy(s1);
 	return best;
 }

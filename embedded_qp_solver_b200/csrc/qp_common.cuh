@@ -11,6 +11,35 @@
 
 namespace qpb {
 
+// Level scheduler for heavy-tailed iteration counts.  The reference's own test
+// distribution (matrix_ops.c:699-734) needs 3 ... 10 000 iterations per problem; a warp that
+// keeps 32 problems until the slowest one stops idles 90 % of its lanes there.  With levels, a
+// warp (a lane group in qp_bpq.cuh) that has iterated `cmin` times and has at most `thr` lanes
+// left EVICTS those problems: their ADMM state (z, u, iteration count) goes to scratch memory
+// and their index to the list of the next level.  Levels are separated by a grid-wide barrier
+// inside the one (cooperative) launch; at level l >= 1 warps take 32 queued problems at a time,
+// so stragglers share warps with stragglers.  A continued problem repeats the factorisation
+// and carries on from (z, u): the arithmetic is the one the single-level kernel does, bit for
+// bit, so WHERE a problem is evicted changes the schedule and never the result.
+constexpr int LEV_SLOTS = 16;                 // levels a launch can run (ctr words per kind)
+constexpr int LEV_CTR_BAR = 0;                // grid-barrier arrivals (monotonic inside a launch)
+constexpr int LEV_CTR_EXIT = 1;               // CTAs that left: the last one zeroes the block
+constexpr int LEV_CTR_COUNT = 2;              // [+ l] problems queued for level l
+constexpr int LEV_CTR_TICKET = 2 + LEV_SLOTS; // [+ l] warp tickets handed out at level l
+constexpr int LEV_CTR_WORDS = 2 + 2 * LEV_SLOTS;
+struct LevelArgs {
+	unsigned *ctr;       // LEV_CTR_WORDS words, zero at launch (the kernel leaves them zero);
+	                     // null: no level scheduler
+	unsigned *list[2];   // indices of the problems queued for the odd / the even levels
+	float *zs, *us;      // [count][n] z and u of a queued problem
+	int *its;            // [count]    iterations a queued problem has done
+	float *Rs;           // bpq: [count][n][n] inverse of a queued problem (null: refactor)
+	unsigned cmin0;      // evict only after cmin0 << (grow * level) iterations at this level
+	unsigned grow;
+	unsigned thr;        // ... and when at most thr lanes of the warp still iterate
+	unsigned max_level;  // the last level keeps every problem to the end
+};
+
 // Kernel arguments: one packed batch resident in device memory.
 // Mirrors qp_batch / qp_batch_solution / qp_options (include/qp_batch.h).
 struct KernelArgs {
@@ -26,6 +55,7 @@ struct KernelArgs {
 	float reltol;
 	unsigned max_iter;
 	int p_packed;          // tpq: P holds packed upper triangles, tpq_packed_stride(n) floats each
+	LevelArgs lev;         // level scheduler (lev.ctr == null: off)
 };
 
 // floats per problem of the packed upper triangle (row-major, i <= j), padded to 16 bytes
@@ -96,6 +126,11 @@ __device__ __forceinline__ void bulk_commit()
 __device__ __forceinline__ void bulk_wait_read()
 {
 	asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+// wait until all committed bulk stores have completed (their writes performed)
+__device__ __forceinline__ void bulk_wait_all()
+{
+	asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 // make generic-proxy shared-memory accesses visible to / ordered with the
 // async proxy (bulk copies)
@@ -216,6 +251,47 @@ __device__ __forceinline__ float4 lds128_volatile(const float4 *p)
 		     : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
 		     : "r"(smem_u32(p)));
 	return v;
+}
+
+// ---- grid-wide barrier of the level scheduler (cooperative launch: all CTAs resident) -------
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p)
+{
+	unsigned v;
+	asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+	return v;
+}
+// Every thread of every CTA calls it the same number of times; `target` = gridDim.x times the
+// number of barriers so far (the counter is reset by the last CTA to leave the kernel).
+__device__ __forceinline__ void grid_barrier(unsigned *bar, unsigned target)
+{
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		__threadfence();
+		atomicAdd(bar, 1u);
+		while (ld_acquire_u32(bar) < target)
+			__nanosleep(40);
+		__threadfence();
+	}
+	__syncthreads();
+}
+// After the last barrier: the last CTA to leave zeroes the counter block for the next launch.
+__device__ __forceinline__ void level_exit(unsigned *ctr)
+{
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		__threadfence();
+		if (atomicAdd(ctr + LEV_CTR_EXIT, 1u) == gridDim.x - 1) {
+			for (int k = 0; k < LEV_CTR_WORDS; ++k)
+				ctr[k] = 0u;
+			__threadfence();
+		}
+	}
+}
+// iterations a warp stays at `level` before it may evict
+__device__ __forceinline__ unsigned level_cmin(const LevelArgs &l, int level)
+{
+	const unsigned sh = l.grow * unsigned(level);
+	return sh >= 20u ? (l.cmin0 << 20) : (l.cmin0 << sh);
 }
 
 __device__ __forceinline__ float warp_sum(float v)

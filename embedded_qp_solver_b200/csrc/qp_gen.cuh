@@ -27,46 +27,9 @@
 // stopped; a group that has stopped keeps executing but no longer commits its state.
 #pragma once
 
-#include "qp_common.cuh"
+#include "qp_aux_args.h"
 
 namespace qpb {
-
-constexpr int GEN_WARPS = 4;      // warps per CTA
-constexpr int GEN_MAX_ROWS = 128; // m
-constexpr int GEN_RPL = 4;        // rows per lane
-
-struct GenArgs {
-	const float *P, *q, *A, *l, *u; // A [count][m][n] row-major; l, u [count][m]
-	const float *z0, *u0;           // [count][m] warm start or null
-	float *x, *z, *y;               // x [count][n]; z, y = rho u [count][m]; z, y may be null
-	int32_t *status, *iters;
-	unsigned long long count;
-	int n, m;
-	float rho, alpha;
-	float eps_abs_pri, eps_abs_dual; // sqrt(m) abstol, sqrt(n) abstol
-	float reltol;
-	unsigned max_iter;
-};
-
-__host__ __device__ inline int gen_ld(int n)
-{
-	return n | 1; // odd row stride: one lane per row reads conflict-free
-}
-
-// lanes per problem: the smallest group with n <= 2T and m <= 4T
-__host__ __device__ inline int gen_lanes(int n, int m)
-{
-	return (n <= 8 && m <= 16) ? 4 : ((n <= 16 && m <= 32) ? 8 : ((n <= 32 && m <= 64) ? 16 : 32));
-}
-
-// floats of shared memory per group, padded so that the groups of a warp start T banks
-// apart: the same element of every group's matrices then lies in a different bank window
-__host__ __device__ inline size_t gen_smem_floats_per_group(int n, int m, int T)
-{
-	const size_t need = size_t(n) * gen_ld(n) + size_t(m) * gen_ld(n) + 3 * (2 * T) + 2 * (GEN_RPL * T);
-	const size_t r = need % 32, want = size_t(T) % 32;
-	return need + (want + 32 - r) % 32;
-}
 
 // sum over the T lanes of a group (groups are aligned runs of T lanes)
 template <int T> __device__ __forceinline__ float group_sum(float v)

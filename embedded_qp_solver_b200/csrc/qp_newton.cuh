@@ -27,33 +27,9 @@
 // per trial, and does not subtract two nearly equal objective values in binary32.
 #pragma once
 
-#include "qp_common.cuh"
+#include "qp_aux_args.h"
 
 namespace qpb {
-
-constexpr int NEWTON_WARPS = 4;      // warps (= problems in flight) per CTA
-constexpr int NEWTON_MAX_SHRINKS = 512; // 0.9^512 ~ 4e-24: the step is gone long before
-
-struct NewtonArgs {
-	const float *P, *q, *x0; // x0 may be null (= 0)
-	float *x, *fval;         // fval may be null
-	int32_t *status, *steps; // may be null
-	unsigned long long count;
-	int n;
-	unsigned iterations;
-	float r; // constant term of the objective, for fval only
-	int gradient; // 1: gradient_descent_with_line_search (qp_solvers.c:65-101): d = -g, no inverse
-};
-
-__host__ __device__ inline int newton_ld(int n)
-{
-	return n | 1; // odd row stride: a lane per row reads conflict-free
-}
-
-__host__ __device__ inline size_t newton_smem_floats_per_warp(int n)
-{
-	return 2 * size_t(n) * newton_ld(n) + 4 * 64;
-}
 
 __global__ void __launch_bounds__(NEWTON_WARPS * 32) qp_newton_kernel(const NewtonArgs a)
 {

@@ -226,59 +226,106 @@ qp_tpq_kernel(const KernelArgs p)
 
 	bool out_pending = false; // this warp has a bulk store in flight from priv_out
 
+	// level scheduler (qp_common.cuh, LevelArgs): level 0 is the whole batch through the ring;
+	// level l >= 1 is the list of problems the warps of level l - 1 evicted
+	const bool levels = p.lev.ctr != nullptr;
+	int level = 0;
+	unsigned lev_cnt = 0; // problems queued for this level (level >= 1)
+	unsigned nbar = 0;    // grid barriers passed
+
 	for (;;) {
-		int t = 0;
-		if (lane == 0)
-			t = atomicAdd(ticket, 1);
-		t = __shfl_sync(FULL, t, 0);
-		const unsigned long long batch = blockIdx.x + (unsigned long long)t * gridDim.x;
-		if (batch >= nbatch)
-			break;
-		const int s = t % STAGES;
-		const int round = t / STAGES;
-		const unsigned long long first = batch * 32ull;
-		const unsigned long long left = p.count - first;
+		// ---- next warp batch -----------------------------------------------------------
+		unsigned long long first;
+		int s = 0, round = 0, t = 0;
+		bool have;
+		if (level == 0) {
+			if (lane == 0)
+				t = atomicAdd(ticket, 1);
+			t = __shfl_sync(FULL, t, 0);
+			const unsigned long long batch = blockIdx.x + (unsigned long long)t * gridDim.x;
+			have = batch < nbatch;
+			first = batch * 32ull;
+			s = t % STAGES;
+			round = t / STAGES;
+		} else {
+			unsigned tk = 0;
+			if (lane == 0)
+				tk = atomicAdd(p.lev.ctr + LEV_CTR_TICKET + level, 1u);
+			tk = __shfl_sync(FULL, tk, 0);
+			first = tk * 32ull;
+			have = first < lev_cnt;
+		}
+		if (!have) {
+			if (!levels)
+				break;
+			// end of this level for the warp.  Results a deeper level may rewrite must have
+			// landed; then every CTA meets at the grid barrier and reads the next list's length.
+			if (out_pending) {
+				if (lane == 0)
+					bulk_wait_all();
+				__syncwarp();
+				out_pending = false;
+			}
+			++nbar;
+			grid_barrier(p.lev.ctr + LEV_CTR_BAR, nbar * gridDim.x);
+			++level;
+			lev_cnt = ld_acquire_u32(p.lev.ctr + LEV_CTR_COUNT + level);
+			if (lev_cnt == 0)
+				break;
+			continue;
+		}
+		const unsigned long long left = (level == 0 ? p.count : (unsigned long long)lev_cnt) - first;
 		const int cnt = left < 32ull ? int(left) : 32;
 		const bool valid = lane < cnt;
+		// index of this lane's problem in the batch (idle lanes of a tail repeat the last one)
+		unsigned long long gidx = first + (valid ? lane : cnt - 1);
+		if (level > 0)
+			gidx = __ldcg(p.lev.list[level & 1] + gidx);
 		// penalty of this thread's problem (qp_batch.rho), requested before the wait
-		const float rho = (p.rho_v && valid) ? __ldg(p.rho_v + first + lane) : p.rho;
+		const float rho = p.rho_v ? __ldg(p.rho_v + gidx) : p.rho;
 
-		// wait until the stage has been armed for this round, then for its bytes
-		while (stage_round[s] < round + 1)
-			__nanosleep(20);
-		mbar_wait(&full_bar[s], uint32_t(round & 1));
-
-		// ---- stage -> registers / private area ------------------------------------
 		float a[N * (N + 1) / 2];
 		float z[N], u[N], w[N];
-		{
-			const float *st = ring + s * L::STAGE;
-			const float4 *slot4 = reinterpret_cast<const float4 *>(st + lane * L::PSLOT);
+		unsigned it0 = 0; // iterations done at earlier levels
+		// row-major n x n matrix (or its packed upper triangle) -> a[], 128 bits at a time
+		auto fill_a = [&](auto ld4) {
 			if (PACKED_IN) {
 				// the record is the upper triangle in the order a[] keeps it
-				const float4 *pk4 = reinterpret_cast<const float4 *>(st + lane * L::PKSLOT);
 #pragma unroll
 				for (int k = 0; k < L::PK / 4; ++k) {
-					const float4 v = pk4[k];
+					const float4 v = ld4(k);
 					const float e[4] = { v.x, v.y, v.z, v.w };
 #pragma unroll
-					for (int t = 0; t < 4; ++t)
-						if (4 * k + t < N * (N + 1) / 2)
-							a[4 * k + t] = e[t];
+					for (int tt = 0; tt < 4; ++tt)
+						if (4 * k + tt < N * (N + 1) / 2)
+							a[4 * k + tt] = e[tt];
 				}
-			} else
+			} else {
 #pragma unroll
-			for (int i = 0; i < N; ++i) {
+				for (int i = 0; i < N; ++i) {
 #pragma unroll
-				for (int c = i / 4; c < NQ; ++c) {
-					const float4 v = slot4[i * NQ + c];
-					const float e[4] = { v.x, v.y, v.z, v.w };
+					for (int c = i / 4; c < NQ; ++c) {
+						const float4 v = ld4(i * NQ + c);
+						const float e[4] = { v.x, v.y, v.z, v.w };
 #pragma unroll
-					for (int k = 0; k < 4; ++k)
-						if (4 * c + k >= i)
-							a[sidx<N>(i, 4 * c + k)] = e[k];
+						for (int k = 0; k < 4; ++k)
+							if (4 * c + k >= i)
+								a[sidx<N>(i, 4 * c + k)] = e[k];
+					}
 				}
 			}
+		};
+		if (level == 0) {
+			// wait until the stage has been armed for this round, then for its bytes
+			while (stage_round[s] < round + 1)
+				__nanosleep(20);
+			mbar_wait(&full_bar[s], uint32_t(round & 1));
+
+			// ---- stage -> registers / private area ------------------------------------
+			const float *st = ring + s * L::STAGE;
+			const float4 *slot4 =
+				reinterpret_cast<const float4 *>(st + lane * (PACKED_IN ? L::PKSLOT : L::PSLOT));
+			fill_a([&](int k) { return slot4[k]; });
 			const float4 *sv4 = reinterpret_cast<const float4 *>(st + L::STAGE_P);
 #pragma unroll
 			for (int k = 0; k < NQ; ++k)
@@ -307,12 +354,40 @@ qp_tpq_kernel(const KernelArgs p)
 				for (int j = 0; j < N; ++j)
 					z[j] = 0.0f, u[j] = 0.0f;
 			}
+			__syncwarp();
+			// the stage is free: order our generic-proxy reads before the async
+			// writes of the refill, then start the copy for ticket t + STAGES
+			fence_async_smem();
+			arm((unsigned long long)t + STAGES);
+		} else {
+			// ---- a queued problem: data straight from global memory, state from scratch ----
+			const float4 *src4 = reinterpret_cast<const float4 *>(
+				p.P + gidx * (unsigned long long)(PACKED_IN ? L::PK : N * N));
+			fill_a([&](int k) { return __ldg(src4 + k); });
+			const float4 *q4 = reinterpret_cast<const float4 *>(p.q) + gidx * NQ;
+#pragma unroll
+			for (int k = 0; k < NQ; ++k)
+				priv_vec4[k * 32 + lane] = __ldg(q4 + k);
+			if (BOUNDS) {
+				const float4 *l4 = reinterpret_cast<const float4 *>(p.lb) + gidx * NQ;
+				const float4 *h4 = reinterpret_cast<const float4 *>(p.ub) + gidx * NQ;
+#pragma unroll
+				for (int k = 0; k < NQ; ++k) {
+					priv_vec4[(NQ + k) * 32 + lane] = __ldg(l4 + k);
+					priv_vec4[(2 * NQ + k) * 32 + lane] = __ldg(h4 + k);
+				}
+			}
+			const float4 *zs4 = reinterpret_cast<const float4 *>(p.lev.zs) + gidx * NQ;
+			const float4 *us4 = reinterpret_cast<const float4 *>(p.lev.us) + gidx * NQ;
+#pragma unroll
+			for (int k = 0; k < NQ; ++k) {
+				const float4 vz = __ldcg(zs4 + k), vu = __ldcg(us4 + k);
+				z[4 * k] = vz.x, z[4 * k + 1] = vz.y, z[4 * k + 2] = vz.z, z[4 * k + 3] = vz.w;
+				u[4 * k] = vu.x, u[4 * k + 1] = vu.y, u[4 * k + 2] = vu.z, u[4 * k + 3] = vu.w;
+			}
+			it0 = unsigned(__ldcg(p.lev.its + gidx));
+			__syncwarp();
 		}
-		__syncwarp();
-		// the stage is free: order our generic-proxy reads before the async
-		// writes of the refill, then start the copy for ticket t + STAGES
-		fence_async_smem();
-		arm((unsigned long long)t + STAGES);
 
 		// ---- factor P + rho I  (replaces matrix_invert, matrix_ops.c:551-630) ----------
 #pragma unroll
@@ -326,10 +401,15 @@ qp_tpq_kernel(const KernelArgs p)
 			w[j] = 0.0f;
 		int my_iters = int(p.max_iter);
 		int my_status = QP_STATUS_MAX_ITER;
-		unsigned it = 0;
+		unsigned it = 0; // iterations at this level; the same number in every lane still looping
+		const unsigned itmax = p.max_iter - it0; // it0 < max_iter for a queued problem
 		const bool active = valid && !bad && p.max_iter > 0;
 		const float alpha = p.alpha;
 		const float rho2 = rho * rho, relrho = p.reltol * rho;
+		// next iteration count at which the warp looks at how many of its lanes still run
+		unsigned it_chk = 0xffffffffu;
+		if (levels && level < int(p.lev.max_level))
+			it_chk = (level_cmin(p.lev, level) + 7u) & ~7u;
 
 		// q lives in shared memory; it is fetched one iteration ahead (at the end of the
 		// body) so that the first FMAs of an iteration do not wait on the load
@@ -341,7 +421,7 @@ qp_tpq_kernel(const KernelArgs p)
 		// The body holds no warp-wide operation, so lanes simply leave the loop when their
 		// problem is done and wait for the others at the __syncwarp() behind it (no vote,
 		// no per-lane flag to test: ~10 instructions less per iteration).
-		bool conv = false;
+		bool conv = false, evict = false;
 		if (active) {
 			do {
 				// admm_update_x (:146-159): y = rho (z - u) - q ; x = (P + rho I)^-1 y
@@ -406,12 +486,43 @@ qp_tpq_kernel(const KernelArgs p)
 				const float eps_pri = fmaf(p.reltol, sqrt_approx(fmaxf(nx, nz)), p.eps_abs);
 				const float eps_dual = fmaf(relrho, sqrt_approx(nu), p.eps_abs);
 				conv = (rr < eps_pri * eps_pri) && (rho2 * ss < eps_dual * eps_dual);
-			} while (!conv && it < p.max_iter);
+				// level scheduler: every eighth iteration past the level's minimum, the lanes
+				// still here count themselves; when few are left they hand their problems
+				// to the next level instead of keeping the whole warp (a heuristic: it moves
+				// work between warps and cannot change a result)
+				if (it == it_chk) {
+					it_chk += 8u;
+					const bool more = !conv && it < itmax;
+					if (__popc(__ballot_sync(__activemask(), more)) <= int(p.lev.thr))
+						evict = more;
+				}
+			} while (!conv && !evict && it < itmax);
 		}
 		__syncwarp();
 		if (conv) {
 			my_status = QP_STATUS_CONVERGED;
-			my_iters = int(it);
+			my_iters = int(it0 + it);
+		}
+
+		// ---- evicted problems: state to scratch, index to the next level's list --------------
+		const unsigned em = levels ? __ballot_sync(FULL, evict) : 0u;
+		if (em) {
+			if (evict) {
+				float4 *zs4 = reinterpret_cast<float4 *>(p.lev.zs) + gidx * NQ;
+				float4 *us4 = reinterpret_cast<float4 *>(p.lev.us) + gidx * NQ;
+#pragma unroll
+				for (int k = 0; k < NQ; ++k) {
+					zs4[k] = make_float4(z[4 * k], z[4 * k + 1], z[4 * k + 2], z[4 * k + 3]);
+					us4[k] = make_float4(u[4 * k], u[4 * k + 1], u[4 * k + 2], u[4 * k + 3]);
+				}
+				p.lev.its[gidx] = int(it0 + it);
+			}
+			unsigned base = 0;
+			if (lane == 0)
+				base = atomicAdd(p.lev.ctr + LEV_CTR_COUNT + level + 1, unsigned(__popc(em)));
+			base = __shfl_sync(FULL, base, 0);
+			if (evict)
+				p.lev.list[(level + 1) & 1][base + __popc(em & ((1u << lane) - 1u))] = unsigned(gidx);
 		}
 
 		// ---- results ---------------------------------------------------------------
@@ -425,49 +536,69 @@ qp_tpq_kernel(const KernelArgs p)
 		} else if (!(nf == 0.0f)) {
 			my_status = QP_STATUS_NONFINITE;
 		}
-		if (valid) {
+		const bool mine = valid && !evict;
+		if (mine) {
 			if (p.status)
-				p.status[first + lane] = my_status;
+				p.status[gidx] = my_status;
 			if (p.iters)
-				p.iters[first + lane] = my_iters;
+				p.iters[gidx] = my_iters;
 		}
 
-		// previous bulk stores must have finished reading priv_out
-		if (out_pending) {
-			if (lane == 0)
-				bulk_wait_read();
-			__syncwarp();
-			out_pending = false;
-		}
-		float4 *out4 = reinterpret_cast<float4 *>(priv_out);
+		if (level == 0 && em == 0u) {
+			// previous bulk stores must have finished reading priv_out
+			if (out_pending) {
+				if (lane == 0)
+					bulk_wait_read();
+				__syncwarp();
+				out_pending = false;
+			}
+			float4 *out4 = reinterpret_cast<float4 *>(priv_out);
 #pragma unroll
-		for (int k = 0; k < NQ; ++k) {
-			out4[lane * NQ + k] =
-				make_float4(w[4 * k], w[4 * k + 1], w[4 * k + 2], w[4 * k + 3]);
-			out4[8 * N + lane * NQ + k] =
-				make_float4(z[4 * k], z[4 * k + 1], z[4 * k + 2], z[4 * k + 3]);
-			out4[16 * N + lane * NQ + k] =
-				make_float4(rho * u[4 * k], rho * u[4 * k + 1], rho * u[4 * k + 2],
-					    rho * u[4 * k + 3]);
+			for (int k = 0; k < NQ; ++k) {
+				out4[lane * NQ + k] =
+					make_float4(w[4 * k], w[4 * k + 1], w[4 * k + 2], w[4 * k + 3]);
+				out4[8 * N + lane * NQ + k] =
+					make_float4(z[4 * k], z[4 * k + 1], z[4 * k + 2], z[4 * k + 3]);
+				out4[16 * N + lane * NQ + k] =
+					make_float4(rho * u[4 * k], rho * u[4 * k + 1], rho * u[4 * k + 2],
+						    rho * u[4 * k + 3]);
+			}
+			fence_async_smem();
+			__syncwarp();
+			if (lane == 0) {
+				const uint32_t ob = uint32_t(cnt) * N * 4u;
+				if (p.x)
+					bulk_s2g(p.x + first * N, priv_out, ob);
+				if (p.z)
+					bulk_s2g(p.z + first * N, priv_out + 32 * N, ob);
+				if (p.lam)
+					bulk_s2g(p.lam + first * N, priv_out + 2 * 32 * N, ob);
+				bulk_commit();
+			}
+			out_pending = true;
+		} else if (mine) {
+			// a batch with evicted lanes, or a deeper level (scattered problems): per lane
+			float4 *x4 = reinterpret_cast<float4 *>(p.x) + gidx * NQ;
+			float4 *z4 = reinterpret_cast<float4 *>(p.z) + gidx * NQ;
+			float4 *l4 = reinterpret_cast<float4 *>(p.lam) + gidx * NQ;
+#pragma unroll
+			for (int k = 0; k < NQ; ++k) {
+				if (p.x)
+					x4[k] = make_float4(w[4 * k], w[4 * k + 1], w[4 * k + 2], w[4 * k + 3]);
+				if (p.z)
+					z4[k] = make_float4(z[4 * k], z[4 * k + 1], z[4 * k + 2], z[4 * k + 3]);
+				if (p.lam)
+					l4[k] = make_float4(rho * u[4 * k], rho * u[4 * k + 1], rho * u[4 * k + 2],
+							    rho * u[4 * k + 3]);
+			}
 		}
-		fence_async_smem();
-		__syncwarp();
-		if (lane == 0) {
-			const uint32_t ob = uint32_t(cnt) * N * 4u;
-			if (p.x)
-				bulk_s2g(p.x + first * N, priv_out, ob);
-			if (p.z)
-				bulk_s2g(p.z + first * N, priv_out + 32 * N, ob);
-			if (p.lam)
-				bulk_s2g(p.lam + first * N, priv_out + 2 * 32 * N, ob);
-			bulk_commit();
-		}
-		out_pending = true;
 	}
 	// drain outstanding bulk stores before the CTA's shared memory goes away
 	if (lane == 0)
 		bulk_wait_read();
 	__syncwarp();
+	if (levels)
+		level_exit(p.lev.ctr);
 }
 
 } // namespace qpb

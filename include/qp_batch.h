@@ -26,9 +26,11 @@
  * Plain C: pointers and sizes only.  All arrays are caller-owned; the library
  * never allocates or frees memory that the caller sees.  Element order of
  * every matrix is the reference's row-major `elements[row * ncols + col]`
- * (matrix/matrix_ops/matrix_ops.c:68-78).  P must be symmetric with
- * P + rho*I positive definite (a convex QP, ReadMe.txt:1-3); the upper
- * triangle is what the kernels read.
+ * (matrix/matrix_ops/matrix_ops.c:68-78).  P must be fully populated and
+ * symmetric, with P + rho*I positive definite (a convex QP, ReadMe.txt:1-3).
+ * Which triangle a kernel reads is unspecified (the thread-per-QP kernels
+ * read the upper one, the lane-group kernels read rows as columns); a caller
+ * who holds only one triangle passes it as QP_P_UPPER.
  *
  * The arithmetic type of the batch entry points is binary32 (`float`); the
  * reference computes in binary64.  The qf entry points take the reference's
@@ -44,7 +46,7 @@
 extern "C" {
 #endif
 
-#define QP_B200_ABI_VERSION 1
+#define QP_B200_ABI_VERSION 2 /* 2: qp_batch.p_layout, qp_options.schedule / outputs_only */
 
 /* largest problem dimension: the box ADMM entry points (qp_solve_batch, qp_solve_batch_ws,
  * qp_admm_qf, qp_admm_qf_batch) take n <= QP_MAX_DIM_BOX; the Newton, gradient and
@@ -99,7 +101,19 @@ typedef struct qp_batch {
 	                        qp_options.rho for all (the reference's RHO_ADMM,
 	                        qp_solvers.c:281).  A problem whose entry is not a
 	                        positive finite number ends with QP_STATUS_SINGULAR */
+	uint32_t p_layout;   /* QP_P_DENSE (the reference's layout) or QP_P_UPPER   */
+	uint32_t reserved;   /* 0                                                   */
 } qp_batch;
+
+/* Layout of qp_batch.P. */
+#define QP_P_DENSE 0 /* [count][n][n] row-major, matrix_ops.c:68-78               */
+#define QP_P_UPPER 1 /* [count][qp_packed_stride(n)]: the row-major upper triangle
+                        (i <= j: P00 P01 .. P0,n-1 P11 ..), n (n + 1) / 2 floats
+                        padded with zeros to a multiple of 4.  P is symmetric, so
+                        this is all of it: 544 instead of 1 024 bytes per problem at
+                        n = 16 over PCIe and out of HBM.  n = 8, 12, 16 only
+                        (QP_ERR_UNSUPPORTED otherwise); arrays 16-byte aligned   */
+size_t qp_packed_stride(uint32_t n); /* floats per problem of a QP_P_UPPER batch */
 
 /* Caller-owned outputs; any pointer may be NULL to skip that output. */
 typedef struct qp_batch_solution {
@@ -126,7 +140,33 @@ typedef struct qp_options {
 	uint32_t kernel;      /* QP_KERNEL_AUTO, or force one kernel family (tests,
 	                         measurements); a family that cannot take the
 	                         batch returns QP_ERR_UNSUPPORTED                   */
+	uint32_t schedule;    /* QP_SCHEDULE_*: how problems that need many more
+	                         iterations than their neighbours are handled      */
+	uint32_t reserved;    /* 0                                                  */
 } qp_options;
+
+/*
+ * Scheduling of uneven iteration counts.  The reference's own test problems
+ * (matirx_random_pos_def, matrix_ops.c:699-734) need 3 ... 10 000 iterations;
+ * with one problem per lane a warp would run to its slowest problem.
+ *   QP_SCHEDULE_LEVELS  a warp that is left with a few unfinished problems
+ *                       hands them (z, u, iteration count) to the next LEVEL,
+ *                       where stragglers share warps with stragglers; levels
+ *                       are separated by grid-wide barriers inside the one
+ *                       launch.  Results are bit-identical to QP_SCHEDULE_SINGLE.
+ *                       Uses a per-device scratch arena owned by the library
+ *                       (allocated on first use, grown when a larger batch
+ *                       arrives; 8 n + 12 bytes per problem, + 4 n^2 for
+ *                       24 <= n <= 40).
+ *   QP_SCHEDULE_SINGLE  every problem stays with the warp it started in; no
+ *                       scratch, no allocation, a plain kernel launch.
+ *   QP_SCHEDULE_AUTO    LEVELS when max_iter > 64, the batch has at least 4 096
+ *                       problems and the kernel family supports it (n <= 16 and
+ *                       n = 24, 32, 40), else SINGLE.
+ */
+#define QP_SCHEDULE_AUTO   0
+#define QP_SCHEDULE_SINGLE 1
+#define QP_SCHEDULE_LEVELS 2
 
 #define QP_KERNEL_AUTO 0
 #define QP_KERNEL_TPQ  1 /* one QP per thread:       n = 4, 8, 12, 16              */
@@ -309,6 +349,15 @@ unsigned long long qp_host_path_h2d_bytes(void);
  * wide: 0 = 128-bit moves, 1 = AVX-512 with ordinary stores, 2 = AVX-512 with non-temporal
  * stores (QP_ERR_UNSUPPORTED without AVX-512; n = 16 only), -1 = what the host path uses. */
 int qp_host_pack_upper(const float *P, float *out, size_t count, uint32_t n, int wide);
+
+/* Pure-copy ceiling of the QP_MEM_HOST path (measurement helper): moves h2d_bytes host to
+ * device and d2h_bytes device to host per repeat between pinned (pinned != 0) or pageable
+ * host buffers and `device`, both directions at once on two streams, in pieces of
+ * `piece_bytes` (0 = 32 MiB) the way the chunk pipeline does, and returns the seconds per
+ * repeat (best of `repeats`), or a negative QP_ERR_*.  No kernel runs: this is what the
+ * copy engines and the host's memory system alone allow for those byte counts. */
+double qp_probe_copy_seconds(int device, size_t h2d_bytes, size_t d2h_bytes, int pinned,
+			     size_t piece_bytes, int repeats);
 
 /* Diagnostics. */
 const char *qp_last_error(void);      /* text of the last QP_ERR_CUDA, per thread */

@@ -36,11 +36,35 @@ def test_default_options_are_the_reference_constants(qp):
     assert o.device == -1 and o.device_mask == 0
 
 
-def test_struct_sizes_match_header(qp):
+def test_struct_layouts_match_header(qp, tmp_path):
+    """The ctypes mirror against what a C compiler makes of include/qp_batch.h: size of every
+    struct and offset of every field."""
+    import subprocess
     from embedded_qp_solver_b200 import api
-    assert C.sizeof(api.qp_batch) == 80
-    assert C.sizeof(api.qp_batch_solution) == 40
-    assert C.sizeof(api.qp_options) == 48
+    structs = {"qp_batch": api.qp_batch, "qp_batch_solution": api.qp_batch_solution,
+               "qp_options": api.qp_options, "qp_general_batch": api.qp_general_batch,
+               "qp_general_solution": api.qp_general_solution,
+               "struct qp_ref_matrix": api.qp_ref_matrix,
+               "struct qp_ref_quadratic_form": api.qp_ref_quadratic_form}
+    rename = {"lam": "lambda"}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "qp_batch.h"', 'int main(void){']
+    for cname, st in structs.items():
+        lines.append(f'printf("{cname} %zu\\n", sizeof({cname}));')
+        for fname, _ in st._fields_:
+            lines.append(f'printf("{cname}.{fname} %zu\\n", offsetof({cname}, {rename.get(fname, fname)}));')
+    lines.append('printf("abi %d\\n", QP_B200_ABI_VERSION); return 0;}')
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)],
+                   check=True)
+    got = dict(l.rsplit(" ", 1) for l in subprocess.run([str(exe)], capture_output=True, text=True,
+                                                        check=True).stdout.strip().split("\n"))
+    for cname, st in structs.items():
+        assert int(got[cname]) == C.sizeof(st), cname
+        for fname, _ in st._fields_:
+            assert int(got[f"{cname}.{fname}"]) == getattr(st, fname).offset, f"{cname}.{fname}"
+    assert int(got["abi"]) == 2
 
 
 def test_api_misuse_returns_error_codes(qp):
