@@ -28,7 +28,7 @@ QP_OK, QP_ERR_INVALID, QP_ERR_UNSUPPORTED, QP_ERR_CUDA, QP_ERR_NO_DEVICE = 0, -1
 QP_ERR_IO = -5
 MEM_HOST, MEM_DEVICE = 0, 1
 KERNEL_AUTO, KERNEL_TPQ, KERNEL_GPQ, KERNEL_BPQ, KERNEL_CPQ = 0, 1, 2, 3, 4
-SCHEDULE_AUTO, SCHEDULE_SINGLE, SCHEDULE_LEVELS = 0, 1, 2
+SCHEDULE_AUTO, SCHEDULE_SINGLE, SCHEDULE_PASSES = 0, 1, 2
 P_DENSE, P_UPPER = 0, 1
 
 _fp = C.POINTER(C.c_float)
@@ -85,7 +85,7 @@ ABI_SYMBOLS = [
     "qp_newton_batch", "qp_newton_qf",
     "qp_problem_file_write", "qp_problem_file_count", "qp_problem_file_read",
     "qp_solve_general_batch", "qp_host_path_packs", "qp_host_path_h2d_bytes", "qp_host_pack_upper", "qp_gradient_batch", "qp_gradient_qf",
-    "qp_packed_stride", "qp_probe_copy_seconds",
+    "qp_packed_stride", "qp_probe_copy_seconds", "qp_schedule_stats",
 ]
 
 _lib = None
@@ -171,6 +171,8 @@ def load_library(path: Optional[str] = None):
     lib.qp_packed_stride.restype = C.c_size_t
     lib.qp_probe_copy_seconds.argtypes = [C.c_int, C.c_size_t, C.c_size_t, C.c_int, C.c_size_t, C.c_int]
     lib.qp_probe_copy_seconds.restype = C.c_double
+    lib.qp_schedule_stats.argtypes = [C.c_int] + [C.POINTER(C.c_ulonglong)] * 3
+    lib.qp_schedule_stats.restype = C.c_int
     lib.qp_last_error.restype = C.c_char_p
     lib.qp_device_count.restype = C.c_int
     lib.qp_kernel_for.argtypes = [C.c_uint32, C.c_int]
@@ -197,7 +199,7 @@ class Options:
     stream: int = 0
     chunk: int = 0
     kernel: int = 0   # KERNEL_AUTO / KERNEL_TPQ / KERNEL_GPQ / KERNEL_BPQ / KERNEL_CPQ
-    schedule: int = 0  # SCHEDULE_AUTO / SCHEDULE_SINGLE / SCHEDULE_LEVELS
+    schedule: int = 0  # SCHEDULE_AUTO / SCHEDULE_SINGLE / SCHEDULE_PASSES
 
     def to_c(self) -> qp_options:
         return qp_options(self.rho, self.alpha, self.abstol, self.reltol, int(self.max_iter),
@@ -610,6 +612,16 @@ def probe_copy_seconds(h2d_bytes: int, d2h_bytes: int, device: int = -1, pinned:
     if t < 0:
         raise QpError(int(t), "qp_probe_copy_seconds")
     return t
+
+
+def schedule_stats(device: int = -1) -> dict:
+    """Counters of the pass scheduler (``qp_schedule_stats``): problems that outlived the first
+    window, problems looked at, evictions by later passes."""
+    v = [C.c_ulonglong() for _ in range(3)]
+    rc = load_library().qp_schedule_stats(device, *[C.byref(x) for x in v])
+    if rc != QP_OK:
+        raise QpError(rc, "qp_schedule_stats")
+    return {"outlived": int(v[0].value), "seen": int(v[1].value), "evicted_later": int(v[2].value)}
 
 
 def host_path_h2d_bytes() -> int:

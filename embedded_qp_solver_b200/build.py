@@ -20,7 +20,11 @@ PUBLIC = os.path.join(os.path.dirname(HERE), "include", "qp_batch.h")
 COMMON = ["qp_common.cuh", "qp_internal.h", "qp_aux_args.h"]
 # translation unit -> headers it includes besides COMMON
 UNITS = {
-    "k_tpq.cu": ["qp_tpq.cuh"],
+    "k_tpq.cu": [],
+    "k_tpq4.cu": ["qp_tpq.cuh", "k_tpq_impl.cuh"],
+    "k_tpq8.cu": ["qp_tpq.cuh", "k_tpq_impl.cuh"],
+    "k_tpq12.cu": ["qp_tpq.cuh", "k_tpq_impl.cuh"],
+    "k_tpq16.cu": ["qp_tpq.cuh", "k_tpq_impl.cuh"],
     "k_bpq.cu": ["qp_bpq.cuh", "qp_gpq.cuh"],
     "k_gpq.cu": ["qp_gpq.cuh"],
     "k_cpq.cu": ["qp_cpq.cuh"],

@@ -25,9 +25,9 @@ bool bpq_eligible(const KernelArgs &a)
 
 namespace {
 
-template <int NP, bool PFI> int launch_bpq_form(const KernelArgs &a, int dev, cudaStream_t st)
+template <int NP, bool PFI, int MODE> int launch_bpq_m(const KernelArgs &a, int dev, cudaStream_t st)
 {
-	auto kern = qp_bpq_kernel<NP, PFI>;
+	auto kern = qp_bpq_kernel<NP, PFI, MODE>;
 	static PerDeviceOnce per_sm;
 	int b = per_sm.get(dev);
 	if (!b) {
@@ -35,35 +35,49 @@ template <int NP, bool PFI> int launch_bpq_form(const KernelArgs &a, int dev, cu
 		b = std::max(1, b);
 		per_sm.set(dev, b);
 	}
+	// (a list pass is sized for the whole batch: how long its list is, only the device knows)
 	constexpr unsigned long long per_cta = BPQ_WARPS * BpqCfg<NP>::G;
 	const unsigned long long need = (a.count + per_cta - 1) / per_cta;
 	unsigned long long grid = (unsigned long long)dev_sms(dev) * b;
 	grid = std::max(1ull, std::min(grid, need));
-	QP_CUDA(launch_kernel(kern, dim3((unsigned)grid), dim3(BPQ_WARPS * 32), 0, st, a));
+	kern<<<dim3((unsigned)grid), dim3(BPQ_WARPS * 32), 0, st>>>(a);
+	QP_CUDA(cudaGetLastError());
 	return QP_OK;
 }
 
-template <int NP> int launch_bpq(const KernelArgs &a, int dev, cudaStream_t st)
+// a pass mode is a separate instantiation: the plain kernel is untouched by the others
+template <int NP, bool PFI> int launch_bpq_form(const KernelArgs &a, int dev, cudaStream_t st, int mode)
+{
+	switch (mode) {
+	case PASS_FIRST: return launch_bpq_m<NP, PFI, PASS_FIRST>(a, dev, st);
+	case PASS_LIST:  return launch_bpq_m<NP, PFI, PASS_LIST>(a, dev, st);
+	}
+	return launch_bpq_m<NP, PFI, PASS_PLAIN>(a, dev, st);
+}
+
+// the product form is chosen by the caller's warm start; every pass of a solve uses the same
+// form (the saved "inverse" of an evicted problem is whatever the first pass built)
+template <int NP> int launch_bpq(const KernelArgs &a, int dev, cudaStream_t st, int mode)
 {
 	if constexpr (NP >= QPB_BPQ_PFI_FROM) {
 		if (a.z0 != nullptr)
-			return launch_bpq_form<NP, true>(a, dev, st);
+			return launch_bpq_form<NP, true>(a, dev, st, mode);
 	}
-	return launch_bpq_form<NP, false>(a, dev, st);
+	return launch_bpq_form<NP, false>(a, dev, st, mode);
 }
 
 } // namespace
 
-int launch_bpq_family(const KernelArgs &a, int dev, cudaStream_t st)
+int launch_bpq_family(const KernelArgs &a, int dev, cudaStream_t st, int mode)
 {
 	if (a.p_packed)
 		return QP_ERR_UNSUPPORTED;
 	switch (a.n) {
-	case 8:  return launch_bpq<8>(a, dev, st);
-	case 16: return launch_bpq<16>(a, dev, st);
-	case 24: return launch_bpq<24>(a, dev, st);
-	case 32: return launch_bpq<32>(a, dev, st);
-	case 40: return launch_bpq<40>(a, dev, st);
+	case 8:  return launch_bpq<8>(a, dev, st, mode);
+	case 16: return launch_bpq<16>(a, dev, st, mode);
+	case 24: return launch_bpq<24>(a, dev, st, mode);
+	case 32: return launch_bpq<32>(a, dev, st, mode);
+	case 40: return launch_bpq<40>(a, dev, st, mode);
 	}
 	return QP_ERR_UNSUPPORTED;
 }

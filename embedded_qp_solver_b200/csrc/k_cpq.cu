@@ -19,7 +19,7 @@ template <int TT> int launch_cpq(const KernelArgs &a, int dev, cudaStream_t st)
 
 int launch_cpq_family(const KernelArgs &a, int dev, cudaStream_t st)
 {
-	if (a.p_packed || a.lev.ctr)
+	if (a.p_packed)
 		return QP_ERR_UNSUPPORTED;
 	switch ((a.n + 15) / 16) {
 	case 1: return launch_cpq<1>(a, dev, st);

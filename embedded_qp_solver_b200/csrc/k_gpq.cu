@@ -45,7 +45,7 @@ template <int NP> int launch_gpq(const KernelArgs &a, int dev, cudaStream_t st)
 
 int launch_gpq_family(const KernelArgs &a, int dev, cudaStream_t st)
 {
-	if (a.p_packed || a.lev.ctr)
+	if (a.p_packed)
 		return QP_ERR_UNSUPPORTED;
 	switch ((a.n + 7) / 8 * 8) {
 	case 8:  return launch_gpq<8>(a, dev, st);

@@ -116,7 +116,7 @@ int resolve_device(int dev)
 	return cur < MAX_DEVICES ? cur : -1;
 }
 
-bool family_has_levels(int family, int n)
+bool family_has_passes(int family, int n)
 {
 	return family == QP_KERNEL_TPQ || (family == QP_KERNEL_BPQ && n >= 8);
 }
@@ -147,39 +147,51 @@ int pick_kernel(const KernelArgs &a, uint32_t forced)
 	return g ? QP_KERNEL_GPQ : 0;
 }
 
-// ---- scratch of the level scheduler: one grow-only arena per device -----------------------
+// ---- passes for heavy-tailed iteration counts (qp_common.cuh, PassArgs) -------------------
 //
-// A launch with levels needs a counter block, two index lists, the saved (z, u, iterations)
-// of evicted problems and, for qp_bpq.cuh, their inverses.  The arena belongs to the library
-// (the reference's pools are static too, kmalloc/kmalloc.c:37-42); launches that use it are
-// chained by an event, so callers on different streams of one device never share it in time.
+// Per device: a grow-only scratch arena (index lists, list lengths, the saved z / u /
+// iteration count of evicted problems and, for qp_bpq.cuh, their inverses) and three
+// counters the kernels keep (problems that outlived the first window, problems looked at,
+// evictions by later passes).  The arena belongs to the library (the reference's pools are
+// static too, kmalloc/kmalloc.c:37-42); solves that use it are chained by an event, so
+// callers on different streams of one device never share it in time.
+//
+// QP_SCHEDULE_AUTO follows what the device has seen: a plain launch counts the problems
+// that needed more than the first window; the counters are copied to pinned host memory
+// on a side stream behind every such solve (nobody waits for it), and the next solve looks
+// at the latest copy -- passes when more than 1 in 128 problems of the solves since the
+// last look outlived the window, a plain launch otherwise.  The schedule never changes a
+// result (bit for bit, tests/test_passes_gpu.py), only where the time goes.
+constexpr int MAX_PASSES = 16;
+constexpr int STAT_WORDS = 4; // hits, seen, later evictions, (spare)
 struct DevArena {
 	std::mutex mu;
 	char *base = nullptr;
 	size_t bytes = 0;
-	cudaEvent_t last = nullptr; // recorded behind the latest launch that used the arena
+	cudaEvent_t last = nullptr;  // recorded behind the latest solve that used the scratch
+	unsigned long long *stat_dev = nullptr;  // STAT_WORDS counters in device memory
+	unsigned long long *stat_host = nullptr; // pinned: their latest copy
+	cudaStream_t side = nullptr;             // carries the copies
+	cudaEvent_t ev_side = nullptr;
+	unsigned long long look_hits = 0, look_seen = 0; // counters at AUTO's last look
+	bool heavy = false;                      // AUTO's current belief about this device's work
 };
 DevArena g_arena[MAX_DEVICES];
 
-struct LevelPolicy {
-	unsigned cmin0, grow, thr, max_level;
+struct PassPolicy {
+	unsigned w0, grow; // window of pass k = w0 << (grow k)
 };
 
-// QPB200_LEVELS="cmin0,grow,thr,max_level" overrides the defaults (measurements)
-LevelPolicy level_policy(int family, int n)
+// thread-per-QP and lane groups: 24, 48, 96, ... iterations (the benchmark distribution needs
+// at most 18, so a first pass evicts nothing of it).  QPB200_PASSES="w0,grow" overrides
+// (measurements, tests).
+PassPolicy pass_policy(int)
 {
-	LevelPolicy pol;
-	if (family == QP_KERNEL_TPQ)
-		pol = { 16u, 2u, 12u, 6u }; // evict at <= 12 lanes after 16, 64, 256, ... iterations
-	else
-		pol = { 16u, 1u, unsigned(n / 4), 9u }; // bpq: when one group of n/4 lanes is left
-	if (const char *e = std::getenv("QPB200_LEVELS")) {
-		unsigned a = 0, b = 0, c = 0, d = 0;
-		if (std::sscanf(e, "%u,%u,%u,%u", &a, &b, &c, &d) == 4 && a > 0 && d > 0) {
-			pol.cmin0 = a, pol.grow = b, pol.max_level = std::min(d, unsigned(LEV_SLOTS - 2));
-			if (c > 0)
-				pol.thr = c;
-		}
+	PassPolicy pol = { 24u, 1u };
+	if (const char *e = std::getenv("QPB200_PASSES")) {
+		unsigned a = 0, b = 0;
+		if (std::sscanf(e, "%u,%u", &a, &b) == 2 && a > 0)
+			pol.w0 = a, pol.grow = std::min(b, 4u);
 	}
 	return pol;
 }
@@ -187,6 +199,31 @@ LevelPolicy level_policy(int family, int n)
 size_t up256(size_t v)
 {
 	return (v + 255) / 256 * 256;
+}
+
+int arena_stats_init(DevArena &ar)
+{
+	if (ar.stat_dev)
+		return QP_OK;
+	QP_CUDA(cudaMalloc(&ar.stat_dev, STAT_WORDS * 8));
+	QP_CUDA(cudaMemset(ar.stat_dev, 0, STAT_WORDS * 8));
+	QP_CUDA(cudaHostAlloc(&ar.stat_host, STAT_WORDS * 8, cudaHostAllocDefault));
+	std::memset(ar.stat_host, 0, STAT_WORDS * 8);
+	QP_CUDA(cudaStreamCreateWithFlags(&ar.side, cudaStreamNonBlocking));
+	QP_CUDA(cudaEventCreateWithFlags(&ar.ev_side, cudaEventDisableTiming));
+	QP_CUDA(cudaEventCreateWithFlags(&ar.last, cudaEventDisableTiming));
+	return QP_OK;
+}
+
+int launch_family(const KernelArgs &a, int fam, int dev, cudaStream_t st, int mode)
+{
+	switch (fam) {
+	case QP_KERNEL_TPQ: return launch_tpq_family(a, dev, st, mode);
+	case QP_KERNEL_BPQ: return launch_bpq_family(a, dev, st, mode);
+	case QP_KERNEL_GPQ: return launch_gpq_family(a, dev, st);
+	case QP_KERNEL_CPQ: return launch_cpq_family(a, dev, st);
+	}
+	return QP_ERR_UNSUPPORTED;
 }
 
 // Solve one device-resident batch on `dev`, stream `st` (the device is current).
@@ -197,35 +234,61 @@ int launch_solver(KernelArgs a, int dev, cudaStream_t st, uint32_t forced, uint3
 	const int fam = pick_kernel(a, forced);
 	if (!fam)
 		return QP_ERR_UNSUPPORTED;
-	bool levels = false;
-	if (family_has_levels(fam, a.n) && a.count < 0xfffff000ull) {
-		if (schedule == QP_SCHEDULE_LEVELS)
-			levels = a.max_iter > 16;
-		else if (schedule == QP_SCHEDULE_AUTO)
-			levels = a.max_iter > 64 && a.count >= 4096;
+	const PassPolicy pol = pass_policy(fam);
+	const bool can = family_has_passes(fam, a.n) && a.count < 0xfffffff0ull && a.max_iter > pol.w0;
+	bool passes = can && schedule == QP_SCHEDULE_PASSES;
+	bool look = can && schedule == QP_SCHEDULE_AUTO && a.max_iter > 64 && a.count >= 4096;
+	if (look) { // a stream that is being captured into a graph cannot take the side-stream copy
+		cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+		if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone)
+			look = false, cudaGetLastError();
 	}
-	auto launch = [&]() -> int {
-		switch (fam) {
-		case QP_KERNEL_TPQ: return launch_tpq_family(a, dev, st);
-		case QP_KERNEL_BPQ: return launch_bpq_family(a, dev, st);
-		case QP_KERNEL_GPQ: return launch_gpq_family(a, dev, st);
-		case QP_KERNEL_CPQ: return launch_cpq_family(a, dev, st);
-		}
-		return QP_ERR_UNSUPPORTED;
-	};
-	if (!levels)
-		return launch();
+	if (!passes && !look)
+		return launch_family(a, fam, dev, st, PASS_PLAIN);
 
 	DevArena &ar = g_arena[dev];
 	std::lock_guard<std::mutex> lk(ar.mu);
+	if (int rc = arena_stats_init(ar))
+		return rc;
+	if (look) {
+		const unsigned long long hits = ar.stat_host[0], seen = ar.stat_host[1];
+		if (seen > ar.look_seen) {
+			ar.heavy = (hits - ar.look_hits) * 128ull > (seen - ar.look_seen);
+			ar.look_hits = hits, ar.look_seen = seen;
+		}
+		passes = ar.heavy;
+	}
+	a.ps.stats = ar.stat_dev;
+	a.ps.probe = std::min(pol.w0, a.max_iter);
+	auto copy_stats = [&]() -> int {
+		QP_CUDA(cudaEventRecord(ar.ev_side, st));
+		QP_CUDA(cudaStreamWaitEvent(ar.side, ar.ev_side, 0));
+		QP_CUDA(cudaMemcpyAsync(ar.stat_host, ar.stat_dev, STAT_WORDS * 8, cudaMemcpyDeviceToHost, ar.side));
+		return QP_OK;
+	};
+	if (!passes) {
+		if (int rc = launch_family(a, fam, dev, st, PASS_PLAIN))
+			return rc;
+		return copy_stats();
+	}
+
+	// windows of the passes: w0, w0 << grow, ... ; the last one runs every problem out
+	unsigned win[MAX_PASSES];
+	int npass = 0;
+	for (unsigned long long cum = 0; npass < MAX_PASSES; ++npass) {
+		const unsigned long long w = (unsigned long long)pol.w0 << std::min(pol.grow * unsigned(npass), 24u);
+		if (cum + w >= a.max_iter || npass == MAX_PASSES - 1) {
+			win[npass++] = a.max_iter;
+			break;
+		}
+		win[npass] = unsigned(w);
+		cum += w;
+	}
 	const size_t c = size_t(a.count), n = size_t(a.n);
 	const bool want_R = fam == QP_KERNEL_BPQ;
-	const size_t o_list0 = up256(LEV_CTR_WORDS * 4), o_list1 = o_list0 + up256(c * 4),
-		     o_its = o_list1 + up256(c * 4), o_zs = o_its + up256(c * 4),
-		     o_us = o_zs + up256(c * n * 4), o_R = o_us + up256(c * n * 4),
-		     need = o_R + (want_R ? up256(c * n * n * 4) : 0);
-	if (!ar.last)
-		QP_CUDA(cudaEventCreateWithFlags(&ar.last, cudaEventDisableTiming));
+	const size_t o_list0 = 256, o_list1 = o_list0 + up256(c * 4), o_its = o_list1 + up256(c * 4),
+		     o_zs = o_its + up256(c * 4), o_us = o_zs + up256(c * n * 4),
+		     o_R = o_us + up256(c * n * 4), need = o_R + (want_R ? up256(c * n * n * 4) : 0);
 	if (ar.bytes < need) {
 		QP_CUDA(cudaEventSynchronize(ar.last)); // nobody is using the old one any more
 		if (ar.base)
@@ -233,26 +296,58 @@ int launch_solver(KernelArgs a, int dev, cudaStream_t st, uint32_t forced, uint3
 		ar.base = nullptr, ar.bytes = 0;
 		QP_CUDA(cudaMalloc(&ar.base, need));
 		ar.bytes = need;
-		// the kernels leave the counter block zero behind them; it starts zero
-		QP_CUDA(cudaMemset(ar.base, 0, o_list0));
 	}
 	QP_CUDA(cudaStreamWaitEvent(st, ar.last, 0));
-	const LevelPolicy pol = level_policy(fam, a.n);
-	a.lev.ctr = reinterpret_cast<unsigned *>(ar.base);
-	a.lev.list[1] = reinterpret_cast<unsigned *>(ar.base + o_list0); // level 1 reads list[1]
-	a.lev.list[0] = reinterpret_cast<unsigned *>(ar.base + o_list1);
-	a.lev.its = reinterpret_cast<int *>(ar.base + o_its);
-	a.lev.zs = reinterpret_cast<float *>(ar.base + o_zs);
-	a.lev.us = reinterpret_cast<float *>(ar.base + o_us);
-	a.lev.Rs = want_R ? reinterpret_cast<float *>(ar.base + o_R) : nullptr;
-	a.lev.cmin0 = pol.cmin0, a.lev.grow = pol.grow, a.lev.thr = pol.thr,
-	a.lev.max_level = pol.max_level;
-	const int rc = launch();
-	if (rc != QP_OK)
-		return rc;
+	unsigned *cnt = reinterpret_cast<unsigned *>(ar.base); // [npass] list lengths
+	unsigned *list[2] = { reinterpret_cast<unsigned *>(ar.base + o_list0),
+			      reinterpret_cast<unsigned *>(ar.base + o_list1) };
+	QP_CUDA(cudaMemsetAsync(cnt, 0, MAX_PASSES * 4, st));
+	a.ps.its = reinterpret_cast<int *>(ar.base + o_its);
+	a.ps.zs = reinterpret_cast<float *>(ar.base + o_zs);
+	a.ps.us = reinterpret_cast<float *>(ar.base + o_us);
+	a.ps.Rs = want_R ? reinterpret_cast<float *>(ar.base + o_R) : nullptr;
+	for (int k = 0; k < npass; ++k) {
+		const bool last = k == npass - 1;
+		a.ps.window = win[k];
+		a.ps.list = k ? list[(k - 1) & 1] : nullptr;
+		a.ps.list_count = k ? cnt + (k - 1) : nullptr;
+		a.ps.next_list = last ? nullptr : list[k & 1];
+		a.ps.next_count = last ? nullptr : cnt + k;
+		if (int rc = launch_family(a, fam, dev, st, k ? PASS_LIST : PASS_FIRST))
+			return rc;
+	}
 	QP_CUDA(cudaEventRecord(ar.last, st));
+	return copy_stats();
+}
+
+} // namespace
+
+extern "C" int qp_schedule_stats(int device, unsigned long long *outlived, unsigned long long *seen,
+				 unsigned long long *evicted_later)
+{
+	const int dev = resolve_device(device);
+	if (dev < 0)
+		return QP_ERR_INVALID;
+	unsigned long long v[STAT_WORDS] = { 0, 0, 0, 0 };
+	DevArena &ar = g_arena[dev];
+	std::lock_guard<std::mutex> lk(ar.mu);
+	if (ar.stat_dev) {
+		DeviceGuard g;
+		if (g.enter(dev) != QP_OK)
+			return QP_ERR_NO_DEVICE;
+		QP_CUDA(cudaDeviceSynchronize());
+		QP_CUDA(cudaMemcpy(v, ar.stat_dev, sizeof(v), cudaMemcpyDeviceToHost));
+	}
+	if (outlived)
+		*outlived = v[0];
+	if (seen)
+		*seen = v[1];
+	if (evicted_later)
+		*evicted_later = v[2];
 	return QP_OK;
 }
+
+namespace {
 
 int check_problem(const qp_batch *pb, const qp_batch_solution *sol)
 {
@@ -281,7 +376,7 @@ int check_options(const qp_options &o)
 		return QP_ERR_INVALID;
 	if (!(o.abstol >= 0.0f) || !(o.reltol >= 0.0f))
 		return QP_ERR_INVALID;
-	if (o.schedule > QP_SCHEDULE_LEVELS)
+	if (o.schedule > QP_SCHEDULE_PASSES)
 		return QP_ERR_INVALID;
 	return QP_OK;
 }

@@ -94,7 +94,17 @@ template <int T> struct GroupRing {
 	}
 };
 
-template <int NP, bool PFI>
+// MODE (qp_common.cuh, PassArgs):
+//   PASS_PLAIN  every problem of the batch to the end: the round-1 kernel
+//   PASS_FIRST  the same with p.ps.window iterations per problem; what has not converged by
+//               then is evicted: z, u, iteration count AND the inverse (4 n^2 bytes, so that
+//               nobody eliminates twice) to scratch, the index to next_list
+//   PASS_LIST   the problems of p.ps.list, G at a time: the saved inverse is reloaded (same
+//               layout as P, no elimination), z / u / iteration count from scratch,
+//               p.ps.window more iterations; evicts again unless next_list is null
+// One instantiation per mode: as a run-time flag the two kinds of round cost ~100 spilled
+// registers in the hot loops.
+template <int NP, bool PFI, int MODE>
 __global__ void __launch_bounds__(BPQ_WARPS * 32, BpqCfg<NP>::MINB)
 qp_bpq_kernel(const KernelArgs p)
 {
@@ -104,6 +114,8 @@ qp_bpq_kernel(const KernelArgs p)
 	__shared__ __align__(16) float sm[BPQ_WARPS * C::GG * C::GROUP];
 	__shared__ float4 ctab[5]; // columns of -I_4, then a zero vector
 
+	if (MODE != PASS_LIST && p.ps.stats && blockIdx.x == 0 && threadIdx.x == 32)
+		atomicAdd(p.ps.stats + 1, p.count);
 	if (threadIdx.x < 5) {
 		const int t = threadIdx.x;
 		ctab[t] = make_float4(t == 0 ? -1.0f : 0.0f, t == 1 ? -1.0f : 0.0f, t == 2 ? -1.0f : 0.0f,
@@ -122,50 +134,30 @@ qp_bpq_kernel(const KernelArgs p)
 	const float alpha = p.alpha;
 	const bool relax = (alpha != 1.0f);
 
-	// level scheduler (qp_common.cuh, LevelArgs): level 0 is the whole batch by a static grid
-	// stride; level l >= 1 is the list of problems whose groups were evicted at level l - 1,
-	// handed out G at a time through a global ticket
-	const bool levels = p.lev.ctr != nullptr;
-	int level = 0;
-	unsigned long long base = ((unsigned long long)blockIdx.x * BPQ_WARPS + warp) * G;
-	for (;; base += (unsigned long long)gridDim.x * BPQ_WARPS * G) {
-		unsigned long long total = p.count;
-		if (level > 0) {
-			unsigned tk = 0;
-			if (lane == 0)
-				tk = atomicAdd(p.lev.ctr + LEV_CTR_TICKET + level, 1u);
-			base = (unsigned long long)__shfl_sync(FULL, tk, 0) * G;
-			total = ld_acquire_u32(p.lev.ctr + LEV_CTR_COUNT + level); // final since the barrier
-		}
-		if (base >= total) {
-			if (!levels)
-				break;
-			++level; // the barrier behind level l is the (l + 1)-th of the launch
-			grid_barrier(p.lev.ctr + LEV_CTR_BAR, unsigned(level) * gridDim.x);
-			if (ld_acquire_u32(p.lev.ctr + LEV_CTR_COUNT + level) == 0)
-				break;
-			continue;
-		}
+	constexpr bool LIST = MODE == PASS_LIST;
+	// problems this launch works on: the batch, or the list the previous pass left
+	const unsigned long long total = LIST ? (unsigned long long)__ldcg(p.ps.list_count) : p.count;
+	const unsigned long long stride = (unsigned long long)gridDim.x * BPQ_WARPS * G;
+	for (unsigned long long base = ((unsigned long long)blockIdx.x * BPQ_WARPS + warp) * G;
+	     base < total; base += stride) {
 		const bool valid = (grp < G) && (base + grp < total);
 		unsigned long long prob = base + grp;
-		if (level > 0)
-			prob = valid ? __ldcg(p.lev.list[level & 1] + prob) : 0ull;
-		// a queued problem whose inverse was saved at eviction: no elimination
-		const bool reload = level > 0 && p.lev.Rs != nullptr;
+		if (LIST)
+			prob = valid ? __ldcg(p.ps.list + prob) : 0ull;
 		// penalty of this group's problem (qp_batch.rho)
 		const float rho = (p.rho_v && valid) ? __ldg(p.rho_v + prob) : p.rho;
+		const float rho2 = rho * rho, relrho = p.reltol * rho;
 
 		// ---- load: rows 4g..4g+3 of P + rho I, read as column blocks of the symmetric P ------
 		float2 S[2][NP]; // S[rp][j] = (row 4g+2rp, row 4g+2rp+1) at column j
 		{
+			// (a listed problem brings its inverse: same layout, written by an earlier launch)
 			const float4 *Pp = reinterpret_cast<const float4 *>(
-				(reload ? p.lev.Rs : p.P) + (valid ? prob : 0ull) * (unsigned long long)(NP * NP)) + g;
+				(LIST ? p.ps.Rs : p.P) + (valid ? prob : 0ull) * (unsigned long long)(NP * NP)) + g;
 #pragma unroll
 			for (int j = 0; j < NP; ++j) {
-				// (the saved inverses were written by this launch: not through the read-only path)
-				float4 v = valid ? (reload ? __ldcg(Pp + j * (NP / 4)) : __ldg(Pp + j * (NP / 4)))
-						 : make_float4(0.f, 0.f, 0.f, 0.f);
-				if (j / 4 == g && !reload) { // the diagonal element of row 4g + (j % 4)
+				float4 v = valid ? __ldg(Pp + j * (NP / 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+				if (j / 4 == g && !LIST) { // the diagonal element of row 4g + (j % 4)
 					const float d = valid ? rho : 1.0f; // idle lanes / tail: identity
 					if (j % 4 == 0) v.x += d;
 					if (j % 4 == 1) v.y += d;
@@ -194,12 +186,12 @@ qp_bpq_kernel(const KernelArgs p)
 				*reinterpret_cast<float4 *>(dst + 4 * (4 * c + t)) =
 					make_float4(S[0][4 * c + t].x, S[0][4 * c + t].y, S[1][4 * c + t].x, S[1][4 * c + t].y);
 		};
-		if (g == 0 && !reload) {
+		if constexpr (!LIST) {
+		if (g == 0) {
 #pragma unroll
 			for (int c = 0; c < NC; ++c)
 				publish_chunk(bc, c);
 		}
-		if (!reload) {
 #pragma unroll
 		for (int seg = 0; seg < NSEG; ++seg) {
 		const int Kseg = (seg + 1) * SEG < NC ? (seg + 1) * SEG : NC;
@@ -316,9 +308,9 @@ qp_bpq_kernel(const KernelArgs p)
 							  : make_float4(p.ub_s, p.ub_s, p.ub_s, p.ub_s);
 			float4 vz = (valid && p.z0) ? __ldg(reinterpret_cast<const float4 *>(p.z0) + o4) : zero4;
 			float4 vu = (valid && p.u0) ? __ldg(reinterpret_cast<const float4 *>(p.u0) + o4) : zero4;
-			if (level > 0 && valid) { // a queued problem carries on from its saved state
-				vz = __ldcg(reinterpret_cast<const float4 *>(p.lev.zs) + o4);
-				vu = __ldcg(reinterpret_cast<const float4 *>(p.lev.us) + o4);
+			if (LIST && valid) { // carries on from its saved state
+				vz = __ldcg(reinterpret_cast<const float4 *>(p.ps.zs) + o4);
+				vu = __ldcg(reinterpret_cast<const float4 *>(p.ps.us) + o4);
 			}
 			q[0] = vq.x, q[1] = vq.y, q[2] = vq.z, q[3] = vq.w;
 			lo[0] = vl.x, lo[1] = vl.y, lo[2] = vl.z, lo[3] = vl.w;
@@ -330,22 +322,18 @@ qp_bpq_kernel(const KernelArgs p)
 
 		// ---- ADMM iterations (qp_solvers.c:284-310) -----------------------------------------
 		int status = QP_STATUS_MAX_ITER;
-		unsigned it = 0; // iterations at this level: the same number in every group still looping
-		// iterations left: a queued problem has done its[prob] < max_iter of them
-		const unsigned itmax = p.max_iter - ((level > 0 && valid) ? unsigned(__ldcg(p.lev.its + prob)) : 0u);
-		// next iteration count at which the warp looks at how many of its groups still run
-		unsigned it_chk = 0xffffffffu;
-		if (levels && level < int(p.lev.max_level))
-			it_chk = (level_cmin(p.lev, level) + 7u) & ~7u;
-		bool evict = false;
-		// every eighth iteration past the level's minimum: when at most lev.thr lanes (one
-		// group) are left, they hand their problem to the next level
-		auto want_evict = [&](bool conv_now) {
-			it_chk += 8u;
-			const bool more = !conv_now && it < itmax;
-			return more && __popc(__ballot_sync(__activemask(), more)) <= int(p.lev.thr);
-		};
+		unsigned it = 0;
 		const bool active = valid && !bad && p.max_iter > 0; // uniform inside a group
+		// iterations of this launch: to the end (PASS_PLAIN), the window (PASS_FIRST; the host
+		// passes min(window, max_iter)), or the window and what the problem has left (PASS_LIST)
+		unsigned done0 = 0, it_stop = 0;
+		if (LIST) {
+			if (valid)
+				done0 = unsigned(__ldcg(p.ps.its + prob)); // < max_iter
+			const unsigned left_it = p.max_iter - done0;
+			it_stop = left_it < p.ps.window ? left_it : p.ps.window;
+		}
+#define QPB_BPQ_IT_END (MODE == PASS_PLAIN ? p.max_iter : (LIST ? it_stop : p.ps.window))
 		// x = R y for my four rows, y broadcast from shared memory (full-inverse variant)
 		auto publish_y = [&](float *yb) {
 			*reinterpret_cast<float4 *>(yb + 4 * g) =
@@ -402,10 +390,8 @@ qp_bpq_kernel(const KernelArgs p)
 		// decides for everybody
 		auto converged = [&](float rr, float ss, float nx, float nz, float nu, unsigned am) {
 			const float eps_pri = fmaf(p.reltol, sqrt_approx(fmaxf(nx, nz)), p.eps_abs);
-			// (rho^2 and reltol * rho are recomputed here: two multiplications per iteration
-			// instead of two registers the kernel does not have)
-			const float eps_dual = fmaf(p.reltol * rho, sqrt_approx(nu), p.eps_abs);
-			int conv = (rr < eps_pri * eps_pri) && ((rho * rho) * ss < eps_dual * eps_dual);
+			const float eps_dual = fmaf(relrho, sqrt_approx(nu), p.eps_abs);
+			int conv = (rr < eps_pri * eps_pri) && (rho2 * ss < eps_dual * eps_dual);
 			if constexpr ((T & (T - 1)) != 0)
 				conv = __shfl_sync(am, conv, gbase);
 			return conv != 0;
@@ -447,9 +433,7 @@ qp_bpq_kernel(const KernelArgs p)
 				nz = ring.sum(nz, am), nu = ring.sum(nu, am);
 				++it;
 				conv = converged(rr, ss, nx, nz, nu, am);
-				if (it == it_chk)
-					evict = want_evict(conv);
-			} while (!conv && !evict && it < itmax);
+			} while (!conv && it < QPB_BPQ_IT_END);
 		}
 		} else {
 		// Full inverse.  The loop is software-pipelined: the mat-vec of the NEXT iteration is
@@ -473,49 +457,66 @@ qp_bpq_kernel(const KernelArgs p)
 				nz = ring.sum(nz, am), nu = ring.sum(nu, am);
 				matvec(yb, xr);
 				conv = converged(rr, ss, nx, nz, nu, am);
-				if (it == it_chk)
-					evict = want_evict(conv);
-			} while (!conv && !evict && it < itmax);
+			} while (!conv && it < QPB_BPQ_IT_END);
 		}
 		}
+#undef QPB_BPQ_IT_END
 		__syncwarp();
 		if (conv)
 			status = QP_STATUS_CONVERGED;
 
-		// ---- evicted groups: state (and the inverse) to scratch, index to the next list -------
-		const unsigned em = levels ? __ballot_sync(FULL, evict && g == 0) : 0u;
-		if (em) {
-			if (evict) {
-				const unsigned long long o4 = prob * (unsigned long long)(NP / 4) + g;
-				reinterpret_cast<float4 *>(p.lev.zs)[o4] = make_float4(z[0], z[1], z[2], z[3]);
-				reinterpret_cast<float4 *>(p.lev.us)[o4] = make_float4(u[0], u[1], u[2], u[3]);
-				if (p.lev.Rs) {
-					float4 *Rp = reinterpret_cast<float4 *>(
-						p.lev.Rs + prob * (unsigned long long)(NP * NP)) + g;
+		// ---- the window closed on an unfinished problem: state and inverse to scratch, index to
+		// the list of the next launch ------------------------------------------------------------
+		bool evict = false;
+		if (MODE != PASS_PLAIN) {
+			if (p.ps.next_list)
+				evict = active && !conv && done0 + it < p.max_iter;
+			const unsigned em = __ballot_sync(FULL, evict && g == 0);
+			if (em) {
+				if (evict) {
+					const unsigned long long o4 = prob * (unsigned long long)(NP / 4) + g;
+					reinterpret_cast<float4 *>(p.ps.zs)[o4] = make_float4(z[0], z[1], z[2], z[3]);
+					reinterpret_cast<float4 *>(p.ps.us)[o4] = make_float4(u[0], u[1], u[2], u[3]);
+					if (!LIST) { // a listed problem's inverse is in place already
+						float4 *Rp = reinterpret_cast<float4 *>(
+							p.ps.Rs + prob * (unsigned long long)(NP * NP)) + g;
 #pragma unroll
-					for (int j = 0; j < NP; ++j)
-						Rp[j * (NP / 4)] = make_float4(S[0][j].x, S[0][j].y, S[1][j].x, S[1][j].y);
+						for (int j = 0; j < NP; ++j)
+							Rp[j * (NP / 4)] = make_float4(S[0][j].x, S[0][j].y, S[1][j].x, S[1][j].y);
+					}
+					if (g == 0)
+						p.ps.its[prob] = int(done0 + it);
 				}
-				if (g == 0)
-					p.lev.its[prob] = int(p.max_iter - itmax + it);
+				unsigned slot = 0;
+				if (lane == 0) {
+					slot = atomicAdd(p.ps.next_count, unsigned(__popc(em)));
+					if (p.ps.stats)
+						atomicAdd(p.ps.stats + (LIST ? 2 : 0), (unsigned long long)__popc(em));
+				}
+				slot = __shfl_sync(FULL, slot, 0);
+				if (evict && g == 0)
+					p.ps.next_list[slot + __popc(em & ((1u << lane) - 1u))] = unsigned(prob);
 			}
-			unsigned slot = 0;
-			if (lane == 0)
-				slot = atomicAdd(p.lev.ctr + LEV_CTR_COUNT + level + 1, unsigned(__popc(em)));
-			slot = __shfl_sync(FULL, slot, 0);
-			if (evict && g == 0)
-				p.lev.list[(level + 1) & 1][slot + __popc(em & ((1u << lane) - 1u))] = unsigned(prob);
 		}
 
 		// ---- results ---------------------------------------------------------------------------
 		float nf = fmaf(x[0], 0.0f, fmaf(x[1], 0.0f, fmaf(x[2], 0.0f, x[3] * 0.0f)));
 		nf = ring.sum(nf, FULL);
-		int iters = int(p.max_iter - itmax + it);
+		int iters = int(done0 + it);
 		if (bad) {
 			status = QP_STATUS_SINGULAR;
 			iters = 0;
 		} else if (!(nf == 0.0f)) {
 			status = QP_STATUS_NONFINITE;
+		}
+		if (MODE == PASS_PLAIN) {
+			// how many problems would have been evicted by a first pass with this window: the
+			// host reads it later and picks the schedule of the NEXT call (qp_batch.cu)
+			if (p.ps.stats) {
+				const unsigned m = __ballot_sync(FULL, valid && g == 0 && unsigned(iters) > p.ps.probe);
+				if (m && lane == 0)
+					atomicAdd(p.ps.stats, (unsigned long long)__popc(m));
+			}
 		}
 		if (valid && !evict) {
 			const unsigned long long o4 = prob * (unsigned long long)(NP / 4) + g;
@@ -534,8 +535,6 @@ qp_bpq_kernel(const KernelArgs p)
 			}
 		}
 	}
-	if (levels)
-		level_exit(p.lev.ctr);
 }
 
 } // namespace qpb

@@ -11,33 +11,40 @@
 
 namespace qpb {
 
-// Level scheduler for heavy-tailed iteration counts.  The reference's own test
+// Passes for heavy-tailed iteration counts.  The reference's own test
 // distribution (matrix_ops.c:699-734) needs 3 ... 10 000 iterations per problem; a warp that
-// keeps 32 problems until the slowest one stops idles 90 % of its lanes there.  With levels, a
-// warp (a lane group in qp_bpq.cuh) that has iterated `cmin` times and has at most `thr` lanes
-// left EVICTS those problems: their ADMM state (z, u, iteration count) goes to scratch memory
-// and their index to the list of the next level.  Levels are separated by a grid-wide barrier
-// inside the one (cooperative) launch; at level l >= 1 warps take 32 queued problems at a time,
-// so stragglers share warps with stragglers.  A continued problem repeats the factorisation
-// and carries on from (z, u): the arithmetic is the one the single-level kernel does, bit for
-// bit, so WHERE a problem is evicted changes the schedule and never the result.
-constexpr int LEV_SLOTS = 16;                 // levels a launch can run (ctr words per kind)
-constexpr int LEV_CTR_BAR = 0;                // grid-barrier arrivals (monotonic inside a launch)
-constexpr int LEV_CTR_EXIT = 1;               // CTAs that left: the last one zeroes the block
-constexpr int LEV_CTR_COUNT = 2;              // [+ l] problems queued for level l
-constexpr int LEV_CTR_TICKET = 2 + LEV_SLOTS; // [+ l] warp tickets handed out at level l
-constexpr int LEV_CTR_WORDS = 2 + 2 * LEV_SLOTS;
-struct LevelArgs {
-	unsigned *ctr;       // LEV_CTR_WORDS words, zero at launch (the kernel leaves them zero);
-	                     // null: no level scheduler
-	unsigned *list[2];   // indices of the problems queued for the odd / the even levels
-	float *zs, *us;      // [count][n] z and u of a queued problem
-	int *its;            // [count]    iterations a queued problem has done
-	float *Rs;           // bpq: [count][n][n] inverse of a queued problem (null: refactor)
-	unsigned cmin0;      // evict only after cmin0 << (grow * level) iterations at this level
-	unsigned grow;
-	unsigned thr;        // ... and when at most thr lanes of the warp still iterate
-	unsigned max_level;  // the last level keeps every problem to the end
+// keeps 32 problems until the slowest one stops idles 90 % of its lanes there.  With passes,
+// a problem gets a WINDOW of iterations per launch (24 or 16 at first, then growing); one
+// that has not converged when its window closes is EVICTED: its ADMM state (z, u, iteration
+// count) goes to scratch memory in HBM and its index to a list in HBM that the NEXT launch
+// (stream order is the barrier) works through 32 at a time -- stragglers share warps with
+// stragglers, and no warp idles for longer than a window.  The list lengths stay on the
+// device; the host enqueues a fixed, small number of launches and never synchronises.
+// A continued problem repeats the factorisation (qp_bpq.cuh: reloads its saved inverse) and
+// carries on from (z, u): the arithmetic is the one the plain kernel does, bit for bit --
+// WHERE a problem is evicted changes the schedule and never the result.
+//
+//   PASS_PLAIN  the whole batch, every problem to the end (the round-1 kernel); optionally
+//               counts the problems that needed more than `probe` iterations (stats[0]) and
+//               the problems it looked at (stats[1]), which is how the host notices that the
+//               next call should use passes
+//   PASS_FIRST  the whole batch, `window` iterations each, the unfinished ones to next_list
+//   PASS_LIST   the problems of `list`, state from scratch, `window` more iterations each,
+//               the unfinished ones to next_list (null: the last pass runs everything out)
+constexpr int PASS_PLAIN = 0, PASS_FIRST = 1, PASS_LIST = 2;
+struct PassArgs {
+	unsigned long long *stats;  // null, or: [0] += problems that outlived the first window
+	                            // (PASS_PLAIN: iters > probe; PASS_FIRST: evicted), [1] += problems
+	                            // looked at (both), [2] += evictions by PASS_LIST launches
+	unsigned probe;
+	unsigned window;            // PASS_FIRST / PASS_LIST: iterations per problem in this launch
+	const unsigned *list;       // PASS_LIST: problem indices ...
+	const unsigned *list_count; // ... and how many (written by the previous launch)
+	unsigned *next_list;        // evicted problems are appended here (null: nobody is evicted)
+	unsigned *next_count;
+	float *zs, *us;             // [count][n] z and u of an evicted problem
+	int *its;                   // [count]    iterations an evicted problem has done
+	float *Rs;                  // bpq: [count][n][n] its inverse (or eta file)
 };
 
 // Kernel arguments: one packed batch resident in device memory.
@@ -55,7 +62,7 @@ struct KernelArgs {
 	float reltol;
 	unsigned max_iter;
 	int p_packed;          // tpq: P holds packed upper triangles, tpq_packed_stride(n) floats each
-	LevelArgs lev;         // level scheduler (lev.ctr == null: off)
+	PassArgs ps;           // passes for heavy-tailed iteration counts (see above)
 };
 
 // floats per problem of the packed upper triangle (row-major, i <= j), padded to 16 bytes
@@ -251,47 +258,6 @@ __device__ __forceinline__ float4 lds128_volatile(const float4 *p)
 		     : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
 		     : "r"(smem_u32(p)));
 	return v;
-}
-
-// ---- grid-wide barrier of the level scheduler (cooperative launch: all CTAs resident) -------
-__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p)
-{
-	unsigned v;
-	asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-	return v;
-}
-// Every thread of every CTA calls it the same number of times; `target` = gridDim.x times the
-// number of barriers so far (the counter is reset by the last CTA to leave the kernel).
-__device__ __forceinline__ void grid_barrier(unsigned *bar, unsigned target)
-{
-	__syncthreads();
-	if (threadIdx.x == 0) {
-		__threadfence();
-		atomicAdd(bar, 1u);
-		while (ld_acquire_u32(bar) < target)
-			__nanosleep(40);
-		__threadfence();
-	}
-	__syncthreads();
-}
-// After the last barrier: the last CTA to leave zeroes the counter block for the next launch.
-__device__ __forceinline__ void level_exit(unsigned *ctr)
-{
-	__syncthreads();
-	if (threadIdx.x == 0) {
-		__threadfence();
-		if (atomicAdd(ctr + LEV_CTR_EXIT, 1u) == gridDim.x - 1) {
-			for (int k = 0; k < LEV_CTR_WORDS; ++k)
-				ctr[k] = 0u;
-			__threadfence();
-		}
-	}
-}
-// iterations a warp stays at `level` before it may evict
-__device__ __forceinline__ unsigned level_cmin(const LevelArgs &l, int level)
-{
-	const unsigned sh = l.grow * unsigned(level);
-	return sh >= 20u ? (l.cmin0 << 20) : (l.cmin0 << sh);
 }
 
 __device__ __forceinline__ float warp_sum(float v)

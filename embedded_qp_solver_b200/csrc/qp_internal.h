@@ -72,32 +72,17 @@ inline bool aligned16(const void *p)
 	return (reinterpret_cast<uintptr_t>(p) & 15u) == 0;
 }
 
-// Launch a kernel, cooperatively when the batch runs with the level scheduler (the levels are
-// separated by grid-wide barriers, so every CTA must be resident: grid <= SMs x CTAs/SM and a
-// cooperative launch, which the runtime refuses instead of deadlocking).
-template <typename K>
-inline cudaError_t launch_kernel(K kern, dim3 grid, dim3 block, size_t smem, cudaStream_t st,
-				 const KernelArgs &a)
-{
-	if (a.lev.ctr) {
-		void *params[] = { const_cast<KernelArgs *>(&a) };
-		return cudaLaunchCooperativeKernel(reinterpret_cast<const void *>(kern), grid, block,
-						   params, smem, st);
-	}
-	kern<<<grid, block, smem, st>>>(a);
-	return cudaGetLastError();
-}
-
 // family launchers: QP_OK, QP_ERR_UNSUPPORTED (the family does not take this batch) or
 // QP_ERR_CUDA
 bool tpq_eligible(const KernelArgs &a);
 bool bpq_eligible(const KernelArgs &a);
-int launch_tpq_family(const KernelArgs &a, int dev, cudaStream_t st);
-int launch_bpq_family(const KernelArgs &a, int dev, cudaStream_t st);
+// mode = PASS_PLAIN / PASS_FIRST / PASS_LIST (qp_common.cuh)
+int launch_tpq_family(const KernelArgs &a, int dev, cudaStream_t st, int mode);
+int launch_bpq_family(const KernelArgs &a, int dev, cudaStream_t st, int mode);
 int launch_gpq_family(const KernelArgs &a, int dev, cudaStream_t st);
 int launch_cpq_family(const KernelArgs &a, int dev, cudaStream_t st);
-// which families run the level scheduler (KernelArgs::lev)
-bool family_has_levels(int family, int n);
+// which families have the pass modes (KernelArgs::ps)
+bool family_has_passes(int family, int n);
 
 int launch_newton(const NewtonArgs &a, int dev, cudaStream_t st);
 int launch_gen(const GenArgs &a, int dev, cudaStream_t st);

@@ -129,8 +129,17 @@ __device__ __forceinline__ void ldlt_solve(const float (&a)[N * (N + 1) / 2], fl
 }
 
 // ---- the kernel -----------------------------------------------------------------
+//
+// MODE (qp_common.cuh, PassArgs):
+//   PASS_PLAIN  every problem of the batch to the end: the round-1 kernel
+//   PASS_FIRST  the same with p.ps.window iterations per problem; what has not converged by
+//               then is evicted (z, u, iteration count to scratch, index to next_list)
+//   PASS_LIST   the problems of p.ps.list (scattered: data straight from global memory, z / u /
+//               iteration count from scratch, results by per-lane stores), p.ps.window more
+//               iterations each; evicts again unless next_list is null
+// One instantiation per mode: a mode is a compile-time constant in the loops.
 
-template <int N, bool BOUNDS, bool WARM, bool RELAX, bool PACKED_IN>
+template <int N, bool BOUNDS, bool WARM, bool RELAX, bool PACKED_IN, int MODE>
 __global__ void
 __launch_bounds__(TpqCfg<N, BOUNDS, WARM>::WARPS * 32, TpqCfg<N, BOUNDS, WARM>::MINB)
 qp_tpq_kernel(const KernelArgs p)
@@ -140,6 +149,7 @@ qp_tpq_kernel(const KernelArgs p)
 	constexpr int STAGES = Cfg::STAGES;
 	constexpr int NQ = N / 4; // float4 per vector
 	constexpr unsigned FULL = 0xffffffffu;
+	constexpr bool LIST = MODE == PASS_LIST;
 
 	extern __shared__ __align__(128) unsigned char smem_raw[];
 	float *ring = reinterpret_cast<float *>(smem_raw);
@@ -154,17 +164,23 @@ qp_tpq_kernel(const KernelArgs p)
 	float4 *priv_vec4 = reinterpret_cast<float4 *>(priv);
 	float *priv_out = priv + L::PRIV_VEC;
 
-	const unsigned long long nbatch = (p.count + 31ull) / 32ull;
+	// problems this launch works on: the batch, or the list the previous pass left
+	const unsigned long long total = LIST ? (unsigned long long)__ldcg(p.ps.list_count) : p.count;
+	const unsigned long long nbatch = (total + 31ull) / 32ull;
 
-	if (threadIdx.x == 0) {
-		for (int s = 0; s < STAGES; ++s) {
-			mbar_init(&full_bar[s], 1);
-			stage_round[s] = 0;
+	if (!LIST) {
+		if (threadIdx.x == 0) {
+			if (p.ps.stats && blockIdx.x == 0)
+				atomicAdd(p.ps.stats + 1, p.count);
+			for (int s = 0; s < STAGES; ++s) {
+				mbar_init(&full_bar[s], 1);
+				stage_round[s] = 0;
+			}
+			*ticket = 0;
+			asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 		}
-		*ticket = 0;
-		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+		__syncthreads();
 	}
-	__syncthreads();
 
 	// Arm stage (t % STAGES) with the data of ticket t.  Called by a whole warp.
 	auto arm = [&](unsigned long long t) {
@@ -221,72 +237,45 @@ qp_tpq_kernel(const KernelArgs p)
 		}
 	};
 
-	if (warp < STAGES)
-		arm(warp);
+	if (!LIST) {
+		if (warp < STAGES)
+			arm(warp);
+	}
 
 	bool out_pending = false; // this warp has a bulk store in flight from priv_out
-
-	// level scheduler (qp_common.cuh, LevelArgs): level 0 is the whole batch through the ring;
-	// level l >= 1 is the list of problems the warps of level l - 1 evicted
-	const bool levels = p.lev.ctr != nullptr;
-	int level = 0;
-	unsigned lev_cnt = 0; // problems queued for this level (level >= 1)
-	unsigned nbar = 0;    // grid barriers passed
+	unsigned long long lbatch = (unsigned long long)blockIdx.x * Cfg::WARPS + warp; // LIST: static stride
 
 	for (;;) {
-		// ---- next warp batch -----------------------------------------------------------
-		unsigned long long first;
-		int s = 0, round = 0, t = 0;
-		bool have;
-		if (level == 0) {
+		int t = 0;
+		unsigned long long batch;
+		if (LIST) {
+			batch = lbatch;
+			lbatch += (unsigned long long)gridDim.x * Cfg::WARPS;
+		} else {
 			if (lane == 0)
 				t = atomicAdd(ticket, 1);
 			t = __shfl_sync(FULL, t, 0);
-			const unsigned long long batch = blockIdx.x + (unsigned long long)t * gridDim.x;
-			have = batch < nbatch;
-			first = batch * 32ull;
-			s = t % STAGES;
-			round = t / STAGES;
-		} else {
-			unsigned tk = 0;
-			if (lane == 0)
-				tk = atomicAdd(p.lev.ctr + LEV_CTR_TICKET + level, 1u);
-			tk = __shfl_sync(FULL, tk, 0);
-			first = tk * 32ull;
-			have = first < lev_cnt;
+			batch = blockIdx.x + (unsigned long long)t * gridDim.x;
 		}
-		if (!have) {
-			if (!levels)
-				break;
-			// end of this level for the warp.  Results a deeper level may rewrite must have
-			// landed; then every CTA meets at the grid barrier and reads the next list's length.
-			if (out_pending) {
-				if (lane == 0)
-					bulk_wait_all();
-				__syncwarp();
-				out_pending = false;
-			}
-			++nbar;
-			grid_barrier(p.lev.ctr + LEV_CTR_BAR, nbar * gridDim.x);
-			++level;
-			lev_cnt = ld_acquire_u32(p.lev.ctr + LEV_CTR_COUNT + level);
-			if (lev_cnt == 0)
-				break;
-			continue;
-		}
-		const unsigned long long left = (level == 0 ? p.count : (unsigned long long)lev_cnt) - first;
+		if (batch >= nbatch)
+			break;
+		const int s = t % STAGES;
+		const int round = t / STAGES;
+		const unsigned long long first = batch * 32ull;
+		const unsigned long long left = total - first;
 		const int cnt = left < 32ull ? int(left) : 32;
 		const bool valid = lane < cnt;
-		// index of this lane's problem in the batch (idle lanes of a tail repeat the last one)
-		unsigned long long gidx = first + (valid ? lane : cnt - 1);
-		if (level > 0)
-			gidx = __ldcg(p.lev.list[level & 1] + gidx);
+		// index of this lane's problem.  LIST: read from the list; the idle lanes of a tail
+		// repeat the last entry (they compute on valid data and store nothing)
+		unsigned long long gidx = first + lane;
+		if (LIST)
+			gidx = __ldcg(p.ps.list + first + (valid ? lane : cnt - 1));
 		// penalty of this thread's problem (qp_batch.rho), requested before the wait
-		const float rho = p.rho_v ? __ldg(p.rho_v + gidx) : p.rho;
+		const float rho = (p.rho_v && (LIST || valid)) ? __ldg(p.rho_v + gidx) : p.rho;
 
 		float a[N * (N + 1) / 2];
 		float z[N], u[N], w[N];
-		unsigned it0 = 0; // iterations done at earlier levels
+		unsigned done0 = 0; // LIST: iterations the problem has behind it
 		// row-major n x n matrix (or its packed upper triangle) -> a[], 128 bits at a time
 		auto fill_a = [&](auto ld4) {
 			if (PACKED_IN) {
@@ -315,7 +304,7 @@ qp_tpq_kernel(const KernelArgs p)
 				}
 			}
 		};
-		if (level == 0) {
+		if constexpr (!LIST) {
 			// wait until the stage has been armed for this round, then for its bytes
 			while (stage_round[s] < round + 1)
 				__nanosleep(20);
@@ -360,7 +349,7 @@ qp_tpq_kernel(const KernelArgs p)
 			fence_async_smem();
 			arm((unsigned long long)t + STAGES);
 		} else {
-			// ---- a queued problem: data straight from global memory, state from scratch ----
+			// ---- listed problems: data straight from global memory, state from scratch ------
 			const float4 *src4 = reinterpret_cast<const float4 *>(
 				p.P + gidx * (unsigned long long)(PACKED_IN ? L::PK : N * N));
 			fill_a([&](int k) { return __ldg(src4 + k); });
@@ -377,15 +366,15 @@ qp_tpq_kernel(const KernelArgs p)
 					priv_vec4[(2 * NQ + k) * 32 + lane] = __ldg(h4 + k);
 				}
 			}
-			const float4 *zs4 = reinterpret_cast<const float4 *>(p.lev.zs) + gidx * NQ;
-			const float4 *us4 = reinterpret_cast<const float4 *>(p.lev.us) + gidx * NQ;
+			const float4 *zs4 = reinterpret_cast<const float4 *>(p.ps.zs) + gidx * NQ;
+			const float4 *us4 = reinterpret_cast<const float4 *>(p.ps.us) + gidx * NQ;
 #pragma unroll
 			for (int k = 0; k < NQ; ++k) {
 				const float4 vz = __ldcg(zs4 + k), vu = __ldcg(us4 + k);
 				z[4 * k] = vz.x, z[4 * k + 1] = vz.y, z[4 * k + 2] = vz.z, z[4 * k + 3] = vz.w;
 				u[4 * k] = vu.x, u[4 * k + 1] = vu.y, u[4 * k + 2] = vu.z, u[4 * k + 3] = vu.w;
 			}
-			it0 = unsigned(__ldcg(p.lev.its + gidx));
+			done0 = unsigned(__ldcg(p.ps.its + gidx)); // < max_iter
 			__syncwarp();
 		}
 
@@ -401,15 +390,17 @@ qp_tpq_kernel(const KernelArgs p)
 			w[j] = 0.0f;
 		int my_iters = int(p.max_iter);
 		int my_status = QP_STATUS_MAX_ITER;
-		unsigned it = 0; // iterations at this level; the same number in every lane still looping
-		const unsigned itmax = p.max_iter - it0; // it0 < max_iter for a queued problem
+		unsigned it = 0;
 		const bool active = valid && !bad && p.max_iter > 0;
 		const float alpha = p.alpha;
 		const float rho2 = rho * rho, relrho = p.reltol * rho;
-		// next iteration count at which the warp looks at how many of its lanes still run
-		unsigned it_chk = 0xffffffffu;
-		if (levels && level < int(p.lev.max_level))
-			it_chk = (level_cmin(p.lev, level) + 7u) & ~7u;
+		// iterations of this launch: to the end (PASS_PLAIN), the window (PASS_FIRST; the host
+		// passes min(window, max_iter)), or the window and what the problem has left (PASS_LIST)
+		unsigned it_stop = 0;
+		if (LIST) {
+			const unsigned left_it = p.max_iter - done0;
+			it_stop = left_it < p.ps.window ? left_it : p.ps.window;
+		}
 
 		// q lives in shared memory; it is fetched one iteration ahead (at the end of the
 		// body) so that the first FMAs of an iteration do not wait on the load
@@ -421,7 +412,7 @@ qp_tpq_kernel(const KernelArgs p)
 		// The body holds no warp-wide operation, so lanes simply leave the loop when their
 		// problem is done and wait for the others at the __syncwarp() behind it (no vote,
 		// no per-lane flag to test: ~10 instructions less per iteration).
-		bool conv = false, evict = false;
+		bool conv = false;
 		if (active) {
 			do {
 				// admm_update_x (:146-159): y = rho (z - u) - q ; x = (P + rho I)^-1 y
@@ -486,43 +477,42 @@ qp_tpq_kernel(const KernelArgs p)
 				const float eps_pri = fmaf(p.reltol, sqrt_approx(fmaxf(nx, nz)), p.eps_abs);
 				const float eps_dual = fmaf(relrho, sqrt_approx(nu), p.eps_abs);
 				conv = (rr < eps_pri * eps_pri) && (rho2 * ss < eps_dual * eps_dual);
-				// level scheduler: every eighth iteration past the level's minimum, the lanes
-				// still here count themselves; when few are left they hand their problems
-				// to the next level instead of keeping the whole warp (a heuristic: it moves
-				// work between warps and cannot change a result)
-				if (it == it_chk) {
-					it_chk += 8u;
-					const bool more = !conv && it < itmax;
-					if (__popc(__ballot_sync(__activemask(), more)) <= int(p.lev.thr))
-						evict = more;
-				}
-			} while (!conv && !evict && it < itmax);
+			} while (!conv && it < (MODE == PASS_PLAIN ? p.max_iter : (LIST ? it_stop : p.ps.window)));
 		}
 		__syncwarp();
 		if (conv) {
 			my_status = QP_STATUS_CONVERGED;
-			my_iters = int(it0 + it);
+			my_iters = int(done0 + it);
 		}
 
-		// ---- evicted problems: state to scratch, index to the next level's list --------------
-		const unsigned em = levels ? __ballot_sync(FULL, evict) : 0u;
-		if (em) {
-			if (evict) {
-				float4 *zs4 = reinterpret_cast<float4 *>(p.lev.zs) + gidx * NQ;
-				float4 *us4 = reinterpret_cast<float4 *>(p.lev.us) + gidx * NQ;
+		// ---- the window closed on an unfinished problem: state to scratch, index to the list ---
+		bool evict = false;
+		unsigned em = 0;
+		if (MODE != PASS_PLAIN) {
+			if (p.ps.next_list)
+				evict = active && !conv && done0 + it < p.max_iter;
+			em = __ballot_sync(FULL, evict);
+			if (em) {
+				if (evict) {
+					float4 *zs4 = reinterpret_cast<float4 *>(p.ps.zs) + gidx * NQ;
+					float4 *us4 = reinterpret_cast<float4 *>(p.ps.us) + gidx * NQ;
 #pragma unroll
-				for (int k = 0; k < NQ; ++k) {
-					zs4[k] = make_float4(z[4 * k], z[4 * k + 1], z[4 * k + 2], z[4 * k + 3]);
-					us4[k] = make_float4(u[4 * k], u[4 * k + 1], u[4 * k + 2], u[4 * k + 3]);
+					for (int k = 0; k < NQ; ++k) {
+						zs4[k] = make_float4(z[4 * k], z[4 * k + 1], z[4 * k + 2], z[4 * k + 3]);
+						us4[k] = make_float4(u[4 * k], u[4 * k + 1], u[4 * k + 2], u[4 * k + 3]);
+					}
+					p.ps.its[gidx] = int(done0 + it);
 				}
-				p.lev.its[gidx] = int(it0 + it);
+				unsigned base = 0;
+				if (lane == 0) {
+					base = atomicAdd(p.ps.next_count, unsigned(__popc(em)));
+					if (p.ps.stats)
+						atomicAdd(p.ps.stats + (LIST ? 2 : 0), (unsigned long long)__popc(em));
+				}
+				base = __shfl_sync(FULL, base, 0);
+				if (evict)
+					p.ps.next_list[base + __popc(em & ((1u << lane) - 1u))] = unsigned(gidx);
 			}
-			unsigned base = 0;
-			if (lane == 0)
-				base = atomicAdd(p.lev.ctr + LEV_CTR_COUNT + level + 1, unsigned(__popc(em)));
-			base = __shfl_sync(FULL, base, 0);
-			if (evict)
-				p.lev.list[(level + 1) & 1][base + __popc(em & ((1u << lane) - 1u))] = unsigned(gidx);
 		}
 
 		// ---- results ---------------------------------------------------------------
@@ -543,8 +533,17 @@ qp_tpq_kernel(const KernelArgs p)
 			if (p.iters)
 				p.iters[gidx] = my_iters;
 		}
+		if (MODE == PASS_PLAIN) {
+			// how many problems would have been evicted by a first pass with this window: the
+			// host reads it later and picks the schedule of the NEXT call (qp_batch.cu)
+			if (p.ps.stats) {
+				const unsigned m = __ballot_sync(FULL, valid && unsigned(my_iters) > p.ps.probe);
+				if (m && lane == 0)
+					atomicAdd(p.ps.stats, (unsigned long long)__popc(m));
+			}
+		}
 
-		if (level == 0 && em == 0u) {
+		if (!LIST && em == 0u) {
 			// previous bulk stores must have finished reading priv_out
 			if (out_pending) {
 				if (lane == 0)
@@ -577,7 +576,8 @@ qp_tpq_kernel(const KernelArgs p)
 			}
 			out_pending = true;
 		} else if (mine) {
-			// a batch with evicted lanes, or a deeper level (scattered problems): per lane
+			// a batch with evicted lanes, or listed (scattered) problems: per-lane stores.
+			// (Nothing of an evicted problem is written here; whoever finishes it writes it.)
 			float4 *x4 = reinterpret_cast<float4 *>(p.x) + gidx * NQ;
 			float4 *z4 = reinterpret_cast<float4 *>(p.z) + gidx * NQ;
 			float4 *l4 = reinterpret_cast<float4 *>(p.lam) + gidx * NQ;
@@ -597,8 +597,6 @@ qp_tpq_kernel(const KernelArgs p)
 	if (lane == 0)
 		bulk_wait_read();
 	__syncwarp();
-	if (levels)
-		level_exit(p.lev.ctr);
 }
 
 } // namespace qpb

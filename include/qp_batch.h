@@ -46,7 +46,7 @@
 extern "C" {
 #endif
 
-#define QP_B200_ABI_VERSION 2 /* 2: qp_batch.p_layout, qp_options.schedule / outputs_only */
+#define QP_B200_ABI_VERSION 2 /* 2: qp_batch.p_layout, qp_options.schedule */
 
 /* largest problem dimension: the box ADMM entry points (qp_solve_batch, qp_solve_batch_ws,
  * qp_admm_qf, qp_admm_qf_batch) take n <= QP_MAX_DIM_BOX; the Newton, gradient and
@@ -149,24 +149,35 @@ typedef struct qp_options {
  * Scheduling of uneven iteration counts.  The reference's own test problems
  * (matirx_random_pos_def, matrix_ops.c:699-734) need 3 ... 10 000 iterations;
  * with one problem per lane a warp would run to its slowest problem.
- *   QP_SCHEDULE_LEVELS  a warp that is left with a few unfinished problems
- *                       hands them (z, u, iteration count) to the next LEVEL,
- *                       where stragglers share warps with stragglers; levels
- *                       are separated by grid-wide barriers inside the one
- *                       launch.  Results are bit-identical to QP_SCHEDULE_SINGLE.
- *                       Uses a per-device scratch arena owned by the library
- *                       (allocated on first use, grown when a larger batch
- *                       arrives; 8 n + 12 bytes per problem, + 4 n^2 for
- *                       24 <= n <= 40).
- *   QP_SCHEDULE_SINGLE  every problem stays with the warp it started in; no
- *                       scratch, no allocation, a plain kernel launch.
- *   QP_SCHEDULE_AUTO    LEVELS when max_iter > 64, the batch has at least 4 096
- *                       problems and the kernel family supports it (n <= 16 and
- *                       n = 24, 32, 40), else SINGLE.
+ *   QP_SCHEDULE_PASSES  a problem gets a window of iterations per kernel launch
+ *                       (24 in the first, doubling each time); one that has not
+ *                       converged when its window closes is handed (z, u,
+ *                       iteration count) to a list in device memory, which
+ *                       the next launch on the same stream works through 32
+ *                       at a time: stragglers share warps with stragglers and
+ *                       no warp idles for longer than a window.  The list
+ *                       lengths stay on the device; the library enqueues
+ *                       about log2(max_iter / 24) launches and never
+ *                       synchronises.  Results are bit-identical to
+ *                       QP_SCHEDULE_SINGLE.  Uses a per-device scratch arena
+ *                       owned by the library (allocated on first use, grown
+ *                       when a larger batch arrives; 8 n + 12 bytes per
+ *                       problem, + 4 n^2 for 24 <= n <= 40); solves that use
+ *                       it are serialised on the device.
+ *   QP_SCHEDULE_SINGLE  one launch, every problem stays with the warp it
+ *                       started in; no scratch, no allocation.
+ *   QP_SCHEDULE_AUTO    SINGLE, except for batches of at least 4 096 problems
+ *                       with max_iter > 64 on the kernel families that have
+ *                       passes (n = 4, 8, 12, 16 and n = 24, 32, 40): there
+ *                       the single launch also counts the problems that needed
+ *                       more than 24 iterations, the count reaches the host
+ *                       asynchronously, and the NEXT such solve on the device
+ *                       uses PASSES when more than 1 problem in 128 did (and
+ *                       goes back to SINGLE when the tail disappears).
  */
 #define QP_SCHEDULE_AUTO   0
 #define QP_SCHEDULE_SINGLE 1
-#define QP_SCHEDULE_LEVELS 2
+#define QP_SCHEDULE_PASSES 2
 
 #define QP_KERNEL_AUTO 0
 #define QP_KERNEL_TPQ  1 /* one QP per thread:       n = 4, 8, 12, 16              */
@@ -349,6 +360,13 @@ unsigned long long qp_host_path_h2d_bytes(void);
  * wide: 0 = 128-bit moves, 1 = AVX-512 with ordinary stores, 2 = AVX-512 with non-temporal
  * stores (QP_ERR_UNSUPPORTED without AVX-512; n = 16 only), -1 = what the host path uses. */
 int qp_host_pack_upper(const float *P, float *out, size_t count, uint32_t n, int wide);
+
+/* Counters of the schedules above on `device` since the process started (any pointer may be
+ * NULL): *outlived = problems that needed more than the first window (counted by AUTO's
+ * probing single launches and by first passes), *seen = problems those launches looked at,
+ * *evicted_later = evictions by the later passes.  Waits for the device. */
+int qp_schedule_stats(int device, unsigned long long *outlived, unsigned long long *seen,
+		      unsigned long long *evicted_later);
 
 /* Pure-copy ceiling of the QP_MEM_HOST path (measurement helper): moves h2d_bytes host to
  * device and d2h_bytes device to host per repeat between pinned (pinned != 0) or pageable

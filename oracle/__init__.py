@@ -40,7 +40,7 @@ def build(ref: bool | None = None) -> None:
     if ref is None:
         ref = os.path.isdir(REFERENCE_ROOT)
     if ref:
-        subprocess.run(["make", "-s", "-C", HERE, "ref"], check=True)
+        subprocess.run(["make", "-s", "-C", HERE, "ref", "reffast"], check=True)
         if os.path.exists(os.path.join(HERE, "..", "embedded_qp_solver_b200", "lib",
                                        "libqpb200.so")):
             subprocess.run(["make", "-s", "-C", HERE, "compat"], check=True)
@@ -168,8 +168,13 @@ class Oracle:
         return secs, x
 
 
-def ref_available(n: int) -> bool:
-    return os.path.exists(os.path.join(HERE, "_ref", f"libqpref_n{n}.so"))
+def ref_available(n: int, fast: bool = False) -> bool:
+    return os.path.exists(os.path.join(HERE, "_ref", f"libqpref_n{n}{'_fast' if fast else ''}.so"))
+
+
+# compiler flags of the two builds of the unmodified reference (oracle/Makefile)
+REF_FLAGS = "gcc -O3 -ffp-contract=off"                 # parity build, bit-comparable with the port
+REF_FAST_FLAGS = "gcc -O3 -march=x86-64-v3"             # timed build (bench.py CPU arm)
 
 
 class Reference:
@@ -178,8 +183,8 @@ class Reference:
     The reference keeps global static pools (kmalloc/kmalloc.c:37-42): one
     instance per process and per n, not thread-safe; parallel use = fork."""
 
-    def __init__(self, n: int):
-        path = os.path.join(HERE, "_ref", f"libqpref_n{n}.so")
+    def __init__(self, n: int, fast: bool = False):
+        path = os.path.join(HERE, "_ref", f"libqpref_n{n}{'_fast' if fast else ''}.so")
         if not os.path.exists(path):
             raise FileNotFoundError(
                 f"{path} missing: run `make -C oracle ref` where {REFERENCE_ROOT} exists")
