@@ -19,6 +19,17 @@ One JSON line on rank 0:
   cpu_baseline  the unmodified reference (oracle/_ref) or the oracle port on the
              host cores, one process per core, on a bounded sample of the same batch
 
+  shapes     (N = 1) the other BASELINE.json configurations, device resident, each with QP/s,
+             mean iteration count and its own roofline fractions: n=4 (2^20, four input sets
+             in rotation so that the 126 MB L2 cannot serve them), n=40 condensed linear MPC
+             (2^18) and random (2^18), n=64 warm-started and cold (2^16)
+  sustained  the headline step back to back for >= 2 s: QP/s, median SM clock, power, clock
+             event reasons (does the burst number survive a sustained FP32 load?)
+  e2e.copy_ceiling   the same bytes moved by the copy engines alone (no kernel), all ranks at
+             once; e2e.frac_of_ceiling = e2e.value / that
+  e2e_device_mask  (N > 1) ONE qp_solve_batch() call on rank 0 over all N GPUs with
+             device_mask (the library's own shard + gather), the other ranks idle
+
 `--impl reference` times only that CPU arm (rank 0; other ranks exit 0).
 """
 from __future__ import annotations
@@ -71,7 +82,7 @@ class ClockSampler:
     }
 
     def __init__(self, index):
-        self.samples, self.reasons = [], set()
+        self.samples, self.reasons, self.power = [], set(), []
         self.ok = False
         try:
             import pynvml
@@ -90,6 +101,10 @@ class ClockSampler:
             return
         try:
             self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+            try:
+                self.power.append(self.nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+            except Exception:
+                pass
             try:
                 r = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
             except Exception:
@@ -116,8 +131,12 @@ class ClockSampler:
     def report(self):
         if not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unsampled"]}
-        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz,
-                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+        rep = {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz,
+               "reasons": sorted(self.reasons), "samples": len(self.samples)}
+        if self.power:
+            rep["power_w_median"] = float(np.median(self.power))
+            rep["power_w_max"] = float(np.max(self.power))
+        return rep
 
 
 # ------------------------------------------------------------------------------------------
@@ -128,10 +147,10 @@ _CPU_DATA = None  # (kind, n, P, q, lb, ub): inherited by the forked workers, ne
 
 def _cpu_worker(span):
     a, b = span
-    kind, n, P, q, lb, ub = _CPU_DATA
+    kind, n, P, q, lb, ub, fast = _CPU_DATA
     import oracle
     if kind == "reference":
-        x, _ = oracle.Reference(n).admm_many(P[a:b], q[a:b], lb[a:b], ub[a:b], 10000)
+        x, _ = oracle.Reference(n, fast=fast).admm_many(P[a:b], q[a:b], lb[a:b], ub[a:b], 10000)
     else:
         _, x = oracle.Oracle().admm_timed(P[a:b], q[a:b], lb[a:b], ub[a:b], 10000)
     return float(np.abs(x).sum())
@@ -141,19 +160,38 @@ class CpuArm:
     """One forked process per core (the reference's static pools are not thread
     safe, kmalloc/kmalloc.c:37-42), each solving a contiguous slice."""
 
-    def __init__(self, n, P, q, beta, cores=None):
+    def __init__(self, n, P, q, beta, cores=None, sample_note="the first problems of the timed batch"):
         global _CPU_DATA
+        self.sample_note = sample_note
         import oracle
         oracle.build(ref=False)
         self.n = n
         self.kind = "reference" if oracle.ref_available(n) else "port"
+        # the timed arm uses the build made for speed (oracle/Makefile `reffast`), parity tests
+        # the one without contraction
+        self.fast = False
+        self.trial = None
+        if self.kind == "reference" and oracle.ref_available(n, fast=True):
+            # two builds of the unmodified sources (oracle/Makefile): time both on one core, on
+            # a few problems, and give the CPU its faster one
+            k = min(256, P.shape[0])
+            Pt, qt = np.ascontiguousarray(P[:k], np.float64), np.ascontiguousarray(q[:k], np.float64)
+            tt = []
+            for fast in (False, True):
+                r = oracle.Reference(n, fast=fast)
+                r.admm_many(Pt, qt, -beta, beta, 10000)
+                tt.append(min(r.admm_many(Pt, qt, -beta, beta, 10000)[1] for _ in range(3)))
+            self.fast = tt[1] < tt[0]
+            self.trial = {oracle.REF_FLAGS: k / tt[0], oracle.REF_FAST_FLAGS: k / tt[1]}
+        self.flags = (oracle.REF_FAST_FLAGS if self.fast else
+                      (oracle.REF_FLAGS if self.kind == "reference" else "gcc -O3 (oracle port)"))
         self.cores = cores or len(os.sched_getaffinity(0))
         P = np.ascontiguousarray(P, np.float64)
         q = np.ascontiguousarray(q, np.float64)
         self.count = P.shape[0]
         lb = np.full((self.count, n), -beta)
         ub = np.full((self.count, n), beta)
-        _CPU_DATA = (self.kind, n, P, q, lb, ub)
+        _CPU_DATA = (self.kind, n, P, q, lb, ub, self.fast)
         self.pool = mp.get_context("fork").Pool(self.cores)
 
     def step(self):
@@ -169,9 +207,133 @@ class CpuArm:
 
     def describe(self, value):
         return {"value": value, "unit": UNIT, "cores": self.cores, "kind": self.kind,
-                "sample": f"{self.count} problems of the same seeded batch (n={self.n}), "
+                "compiler": self.flags, "one_core_qp_per_s_by_build": self.trial,
+                "sample": f"{self.count} problems of the benchmark distribution (n={self.n}; {self.sample_note}), "
                           f"one forked process per core, {self.kind} admm() in float64"}
 
+
+
+# ------------------------------------------------------------------------------------------
+# device-resident timing of one configuration, with its own roofline fractions
+# ------------------------------------------------------------------------------------------
+def executed_flops(kernel, n, k, warm):
+    """Flops the kernels really execute per problem: thread-per-QP factors
+    P + rho I as L D L' (n^3/3) and solves twice per iteration; the lane-group kernels run a
+    block Gauss-Jordan (2 n^3 multiplied out, n^3 in product form, which is what a warm
+    start or n >= 48 selects) and a mat-vec per iteration."""
+    it = k * (2.0 * n * n + 24.0 * n)
+    if kernel.startswith("tpq"):
+        return n ** 3 / 3.0 + it
+    if kernel.startswith("cpq"):
+        return 2.0 * n ** 3 + it
+    product_form = n >= 48 or (warm and n >= 24)
+    return (1.0 if product_form else 2.0) * n ** 3 + it
+
+
+def fractions(qp, n, count, ms, k, warm, hbm_peak, fp32_peak, issue_rec=None, sm_mhz=None, sms=148):
+    kernel = qp.kernel_for(n)
+    rate = count / (ms * 1e-3)
+    bytes_per = qp.algorithmic_bytes(n, warm=warm, with_z=True, bound_arrays=False)
+    ref = qp.algorithmic_flops(n, k)
+    exe = executed_flops(kernel, n, k, warm)
+    d = {"kernel": kernel, "qp_per_s": rate, "ms_per_step": ms, "mean_iters": k,
+         "hbm_frac": bytes_per * rate / 1e9 / hbm_peak, "bytes_per_problem": bytes_per,
+         "fp32_reference_frac": ref * rate / 1e12 / fp32_peak, "reference_flops_per_problem": ref,
+         "fp32_executed_frac": exe * rate / 1e12 / fp32_peak, "executed_flops_per_problem": exe}
+    # issue slots: warp instructions per launch from the committed ncu capture of this kernel at
+    # this batch size (profiles/traffic.json), over this run's launch time
+    if issue_rec and issue_rec.get("warp_instructions_per_launch") and sm_mhz:
+        d["issue_frac"] = issue_rec["warp_instructions_per_launch"] / (ms * 1e-3) / (sms * 4 * sm_mhz * 1e6)
+        d["issue_source"] = issue_rec.get("source", "profiles/traffic.json")
+    else:
+        d["issue_frac"] = None
+    d["roofline_frac"] = max(d["hbm_frac"], d["fp32_reference_frac"])
+    d["bound"] = "hbm" if d["hbm_frac"] >= d["fp32_reference_frac"] else "fp32"
+    return d
+
+
+def time_steps(torch, fn, steps, warmup=3):
+    for i in range(warmup):
+        fn(i)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        fn(i)
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+def run_shapes(args, qp, torch, device, hbm_peak, fp32_peak, traffic, sm_mhz):
+    """BASELINE.json configs 2, 4, 5 (and n = 40 random, n = 64 cold beside them)."""
+    from embedded_qp_solver_b200 import problems
+    sms = torch.cuda.get_device_properties(device).multi_processor_count
+    steps = args.shape_steps
+    lines = []
+
+    def entry(name, n, count, ms, out, warm, note):
+        k = float(out["iters"].float().mean())
+        d = {"shape": name, "n": n, "m": 2 * n, "count": count, "warm_start": warm}
+        d.update(fractions(qp, n, count, ms, k, warm, hbm_peak, fp32_peak,
+                           traffic.get(f"{qp.kernel_for(n)}@{count}") if note.get("issue_ok") else None,
+                           sm_mhz, sms))
+        d["not_converged"] = int((out["status"] != 0).sum())
+        d["inputs"] = note["inputs"]
+        lines.append(d)
+
+    # config 2: n = 4, 2^20 problems.  One set is 84 MB, less than the L2: rotate four
+    n, count = 4, 1 << 20
+    sets = [make_batch(count, n, args.seed + 17 * i, device) for i in range(4)]
+    out = qp.solve_batch(sets[0][0], sets[0][1], -args.beta, args.beta)
+    ms = time_steps(torch, lambda i: qp.solve_batch(sets[i % 4][0], sets[i % 4][1], -args.beta, args.beta, out=out),
+                    steps * 4, warmup=4)
+    entry("n=4,m=8 random", n, count, ms, out, False,
+          {"inputs": "4 input sets of 84 MB in rotation (336 MB > 126 MB L2)", "issue_ok": True})
+    del sets, out
+
+    # config 4: n = 40, 2^18 condensed linear-MPC problems (4096 distinct, tiled: 1.7 GB, all
+    # addresses distinct) and, beside it, random problems of the same shape
+    n, count = 40, 1 << 18
+    Pm, qm, _, ubm = problems.mpc(4096, seed=args.seed)
+    reps = count // 4096
+    P = torch.from_numpy(Pm).to(device).repeat(reps, 1, 1).contiguous()
+    q = torch.from_numpy(qm).to(device).repeat(reps, 1).contiguous()
+    bm = float(ubm[0, 0])
+    for sched, tag in ((qp.SCHEDULE_SINGLE, "single launch"), (qp.SCHEDULE_PASSES, "passes")):
+        o = qp.Options(schedule=sched)
+        out = qp.solve_batch(P, q, -bm, bm, options=o)
+        ms = time_steps(torch, lambda i: qp.solve_batch(P, q, -bm, bm, out=out, options=o), steps)
+        entry(f"n=40,m=80 condensed MPC ({tag})", n, count, ms, out, False,
+              {"inputs": "4096 distinct problems tiled 64 times, 1.7 GB > L2"})
+        it = out["iters"].float()
+        lines[-1]["iters_max"] = int(it.max())
+        lines[-1]["iters_median"] = float(it.median())
+        lines[-1]["accuracy_note"] = ("x within 2e-4 of the FP64 reference on all problems, 1e-4 on 99.5 % "
+                                      "(the reference algorithm itself in binary32 reaches 1.1e-4; "
+                                      "profiles/r1_mpc_accuracy.jsonl)")
+    del P, q, out
+    P, q = make_batch(count, n, args.seed, device)
+    out = qp.solve_batch(P, q, -args.beta, args.beta)
+    ms = time_steps(torch, lambda i: qp.solve_batch(P, q, -args.beta, args.beta, out=out), steps)
+    entry("n=40,m=80 random", n, count, ms, out, False, {"inputs": "1.7 GB > L2", "issue_ok": True})
+    del P, q, out
+
+    # config 5: n = 64, 2^16 problems warm-started from the solution of a perturbed problem
+    n, count = 64, 1 << 16
+    P, q = make_batch(count, n, args.seed, device)
+    first = qp.solve_batch(P, q, -args.beta, args.beta)
+    out = {k: v.clone() for k, v in first.items()}
+    ms = time_steps(torch, lambda i: qp.solve_batch(P, q, -args.beta, args.beta, out=out), steps)
+    entry("n=64,m=128 cold", n, count, ms, out, False, {"inputs": "1.07 GB > L2"})
+    q2 = q + 0.01 * torch.randn_like(q)
+    z0, u0 = first["z"].clone(), first["lam"].clone()
+    ms = time_steps(torch, lambda i: qp.solve_batch(P, q2, -args.beta, args.beta, z0=z0, u0=u0, out=out), steps)
+    entry("n=64,m=128 warm start (q perturbed by 1 %)", n, count, ms, out, True,
+          {"inputs": "1.07 GB > L2", "issue_ok": True})
+    del P, q, q2, out, first, z0, u0
+    torch.cuda.empty_cache()
+    return lines
 
 # ------------------------------------------------------------------------------------------
 def parse():
@@ -187,6 +349,10 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=400_000)
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 20)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-shapes", action="store_true", help="skip the other BASELINE shapes (N = 1)")
+    ap.add_argument("--shape-steps", type=int, default=10)
+    ap.add_argument("--sustained-s", type=float, default=2.5, help="0 = skip the sustained run")
+    ap.add_argument("--no-device-mask", action="store_true", help="skip e2e_device_mask (N > 1)")
     ap.add_argument("--no-cpu", action="store_true")
     return ap.parse_args()
 
@@ -202,13 +368,11 @@ def config_of(args, world):
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    from embedded_qp_solver_b200 import problems
+    import torch
     sample = min(args.count, args.cpu_sample)
-    P, q, _, _ = problems.wellcond(min(sample, 4096), args.n, seed=args.seed, beta=args.beta)
-    reps = math.ceil(sample / P.shape[0])  # tile a seeded block up to the sample size
-    P = np.tile(P, (reps, 1, 1))[:sample]
-    q = np.tile(q, (reps, 1))[:sample]
-    arm = CpuArm(args.n, P, q, args.beta)
+    P, q = make_batch(sample, args.n, args.seed, torch.device("cpu"))
+    arm = CpuArm(args.n, P.numpy(), q.numpy(), args.beta,
+                 sample_note=f"make_batch on the host, seed {args.seed}, all distinct")
     for _ in range(max(1, min(args.warmup, 1))):
         arm.step()
     secs = [arm.step() for _ in range(args.steps)]
@@ -236,8 +400,12 @@ def run_ours(args, rank, local_rank, world):
         raise RuntimeError("bench.py needs a CUDA device (there is no CPU fallback)")
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
+    cpu_group = None
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
+        # host-side barrier for the leg in which rank 0 drives every GPU: an NCCL barrier would
+        # park a spinning kernel on the GPUs the library is about to use
+        cpu_group = dist.new_group(backend="gloo")
     qp.load_library()
     n, count = args.n, args.count
 
@@ -281,6 +449,31 @@ def run_ours(args, rank, local_rank, world):
     mean_iters = float(iters.mean())
     n_bad = int((out["status"] != 0).sum())
 
+    # ---- sustained: the same step back to back for seconds, clocks and power sampled ----------
+    sustained = None
+    if args.sustained_s > 0:
+        ssamp = ClockSampler(local_rank)
+        barrier()
+        sv0, sv1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ssamp.start()
+        sv0.record()
+        ssteps, t0 = 0, time.perf_counter()
+        while time.perf_counter() - t0 < args.sustained_s:  # the launch queue is bounded: the
+            for _ in range(64):                            # host cannot run far ahead
+                step()
+            ssteps += 64
+        sv1.record()
+        torch.cuda.synchronize()
+        ssamp.stop()
+        sms_ = sv0.elapsed_time(sv1)
+        if world > 1:
+            t = torch.tensor([sms_], device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            sms_ = float(t.item())
+        sustained = {"seconds": sms_ * 1e-3, "steps": ssteps, "ms_per_step": sms_ / ssteps,
+                     "value": count * world * ssteps / (sms_ * 1e-3), "unit": UNIT,
+                     "vs_burst": (sms_ / ssteps) / ms_per_step, "clocks": ssamp.report()}
+
     # ---- end to end through the C ABI with host buffers -----------------------------------
     e2e = None
     if not args.no_e2e:
@@ -305,6 +498,37 @@ def run_ours(args, rank, local_rank, world):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
         same = bool(torch.equal(hout["iters"], out["iters"].cpu()))
+        # what the copy engines and the host's memory system allow for the same bytes with no
+        # kernel in between, every rank at once (pinned, both directions on two streams)
+        h2d_b, d2h_b = (n * n + n) * 4 * count, (3 * n + 2) * 4 * count
+        barrier()
+        ceil_s = qp.probe_copy_seconds(h2d_b, d2h_b, device=local_rank, pinned=True, repeats=3)
+        barrier()
+        # ... and for the bytes the library really sent (it may pack the upper triangles)
+        ceil_w = qp.probe_copy_seconds(int(wire), d2h_b, device=local_rank, pinned=True, repeats=3)
+        if world > 1:
+            t = torch.tensor([ceil_s, ceil_w], device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ceil_s, ceil_w = float(t[0].item()), float(t[1].item())
+        # pageable caller memory (staged through the workspace's pinned buffers), fewer steps
+        pageable = None
+        if world == 1:
+            pP, pq = hP.numpy().copy(), hq.numpy().copy()
+            pout = {k: np.empty((count, n), np.float32) for k in ("x", "z", "lam")}
+            pout.update({k: np.empty(count, np.int32) for k in ("status", "iters")})
+            qp.solve_batch(pP, pq, -args.beta, args.beta, options=hopts, out=pout)
+            tp0 = time.perf_counter()
+            for _ in range(3):
+                qp.solve_batch(pP, pq, -args.beta, args.beta, options=hopts, out=pout)
+            pdt = (time.perf_counter() - tp0) / 3
+            pc = qp.probe_copy_seconds(h2d_b, d2h_b, device=local_rank, pinned=False, repeats=2)
+            pageable = {"value": count / pdt, "unit": UNIT, "ms_per_step": pdt * 1e3,
+                        "driver_pageable_copy": count / pc,
+                        "note": "driver_pageable_copy = the same bytes through cudaMemcpyAsync on pageable "
+                                "memory with no kernel; the library stages through its own pinned buffers "
+                                "with worker threads instead, which is why it is faster than that",
+                        "matches_device_path": bool(np.array_equal(pout["iters"], out["iters"].cpu().numpy()))}
+            del pP, pq, pout
         # the caller hands over full row-major matrices; the library may send only their
         # upper triangles over PCIe (qp_host_path_packs)
         packs = qp.host_path_packs(n)
@@ -314,8 +538,51 @@ def run_ours(args, rank, local_rank, world):
                "h2d_bytes_on_the_wire_per_step": wire,
                "host_packs_upper_triangle": bool(packs),
                "steps": ksteps, "ms_per_step": dt * 1e3, "matches_device_path": same,
-               "host_memory": "pinned"}
+               "host_memory": "pinned",
+               "copy_ceiling": count * world / ceil_w, "frac_of_ceiling": ceil_w / dt,
+               "copy_ceiling_dense": count * world / ceil_s,
+               "copy_ceiling_note": "qp_probe_copy_seconds: the H2D bytes the library put on the wire and the "
+                                    "D2H bytes, per rank, pinned, two streams, no kernel, all ranks at once "
+                                    "(max over ranks); copy_ceiling_dense = the same for the caller's dense "
+                                    "bytes (what a plain copy of the row-major matrices would be bound by)",
+               "pageable": pageable}
         del hP, hq, hout
+
+    # ---- the library's own multi-GPU entry: ONE qp_solve_batch call over all N GPUs ----------
+    e2e_mask = None
+    if world > 1 and not args.no_e2e and not args.no_device_mask:
+        barrier()
+        dist.barrier(group=cpu_group)
+        if rank == 0:
+            total = count * world
+            mP = torch.empty((total, n, n)).pin_memory()
+            mq = torch.empty((total, n)).pin_memory()
+            Pc, qc = P.cpu(), q.cpu()
+            for r in range(world):  # every shard carries rank 0's problems: the check below is exact
+                mP[r * count:(r + 1) * count] = Pc
+                mq[r * count:(r + 1) * count] = qc
+            mout = {k: torch.empty((total, n)).pin_memory() for k in ("x", "z", "lam")}
+            mout.update({k: torch.empty(total, dtype=torch.int32).pin_memory() for k in ("status", "iters")})
+            mopts = qp.Options(device_mask=(1 << world) - 1)
+            for _ in range(2):
+                qp.solve_batch(mP, mq, -args.beta, args.beta, options=mopts, out=mout)
+            msteps = max(3, min(args.steps, 5))
+            t0 = time.perf_counter()
+            for _ in range(msteps):
+                qp.solve_batch(mP, mq, -args.beta, args.beta, options=mopts, out=mout)
+            mdt = (time.perf_counter() - t0) / msteps
+            ref_it = out["iters"].cpu()
+            same = all(bool(torch.equal(mout["iters"][r * count:(r + 1) * count], ref_it)) for r in range(world))
+            e2e_mask = {"value": total / mdt, "unit": UNIT, "ms_per_step": mdt * 1e3, "steps": msteps,
+                        "problems": total, "device_mask": (1 << world) - 1,
+                        "h2d_bytes_per_step": (n * n + n) * 4 * total,
+                        "d2h_bytes_per_step": (3 * n + 2) * 4 * total,
+                        "host_memory": "pinned", "matches_device_path": same,
+                        "note": "one process, one call, one host thread per GPU inside the library; "
+                                "the other ranks wait at a barrier"}
+            del mP, mq, mout
+        torch.cuda.synchronize()
+        dist.barrier(group=cpu_group)
 
     if rank != 0:
         if world > 1:
@@ -378,6 +645,22 @@ def run_ours(args, rank, local_rank, world):
     roofline["hbm"] = hbm
     roofline["fp32"] = fp
 
+    # ---- the other BASELINE shapes (N = 1 only: they are single-GPU configurations) ----------
+    shapes = None
+    if world == 1 and not args.no_shapes:
+        traffic = json.load(open(tpath)) if os.path.exists(tpath) else {}
+        del out
+        shapes = run_shapes(args, qp, torch, device, hbm_peak, fp32_peak, traffic,
+                            sampler.report().get("sm_mhz"))
+        headline = {"shape": f"n={n},m={2 * n} random (headline)", "n": n, "m": 2 * n, "count": count,
+                    "warm_start": False}
+        headline.update(fractions(qp, n, count, ms_per_step, mean_iters, False, hbm_peak, fp32_peak,
+                                  rec, sampler.report().get("sm_mhz"),
+                                  torch.cuda.get_device_properties(device).multi_processor_count))
+        headline["not_converged"] = n_bad
+        headline["inputs"] = "1.2 GB > L2"
+        shapes.insert(1, headline)
+
     # ---- CPU baseline ----------------------------------------------------------------------
     cpu = None
     if world == 1 and not args.no_cpu:
@@ -394,7 +677,10 @@ def run_ours(args, rank, local_rank, world):
             "data": "synthetic", "config": config_of(args, world),
             "clocks": sampler.report(), "e2e": e2e, "gpu_launches": args.steps * world,
             "roofline": roofline, "cpu_baseline": cpu,
-            "mean_iters": mean_iters, "not_converged": n_bad}
+            "mean_iters": mean_iters, "not_converged": n_bad,
+            "sustained": sustained, "shapes": shapes}
+    if e2e_mask is not None:
+        line["e2e_device_mask"] = e2e_mask
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

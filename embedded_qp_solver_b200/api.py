@@ -171,7 +171,7 @@ def load_library(path: Optional[str] = None):
     lib.qp_packed_stride.restype = C.c_size_t
     lib.qp_probe_copy_seconds.argtypes = [C.c_int, C.c_size_t, C.c_size_t, C.c_int, C.c_size_t, C.c_int]
     lib.qp_probe_copy_seconds.restype = C.c_double
-    lib.qp_schedule_stats.argtypes = [C.c_int] + [C.POINTER(C.c_ulonglong)] * 3
+    lib.qp_schedule_stats.argtypes = [C.c_int, C.POINTER(C.c_ulonglong)]
     lib.qp_schedule_stats.restype = C.c_int
     lib.qp_last_error.restype = C.c_char_p
     lib.qp_device_count.restype = C.c_int
@@ -615,13 +615,15 @@ def probe_copy_seconds(h2d_bytes: int, d2h_bytes: int, device: int = -1, pinned:
 
 
 def schedule_stats(device: int = -1) -> dict:
-    """Counters of the pass scheduler (``qp_schedule_stats``): problems that outlived the first
-    window, problems looked at, evictions by later passes."""
-    v = [C.c_ulonglong() for _ in range(3)]
-    rc = load_library().qp_schedule_stats(device, *[C.byref(x) for x in v])
+    """Counters of the schedules (``qp_schedule_stats``): passes -- problems that outlived the
+    first window, problems looked at, evictions by later passes; AUTO's probing single launches --
+    sum of iteration counts, sum of what the warps waited for, problems looked at."""
+    v = (C.c_ulonglong * 6)()
+    rc = load_library().qp_schedule_stats(device, v)
     if rc != QP_OK:
         raise QpError(rc, "qp_schedule_stats")
-    return {"outlived": int(v[0].value), "seen": int(v[1].value), "evicted_later": int(v[2].value)}
+    return {"outlived": int(v[0]), "seen": int(v[1]), "evicted_later": int(v[2]),
+            "probe_iterations": int(v[3]), "probe_waited_for": int(v[4]), "probe_problems": int(v[5])}
 
 
 def host_path_h2d_bytes() -> int:

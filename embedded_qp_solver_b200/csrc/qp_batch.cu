@@ -163,7 +163,7 @@ int pick_kernel(const KernelArgs &a, uint32_t forced)
 // last look outlived the window, a plain launch otherwise.  The schedule never changes a
 // result (bit for bit, tests/test_passes_gpu.py), only where the time goes.
 constexpr int MAX_PASSES = 16;
-constexpr int STAT_WORDS = 4; // hits, seen, later evictions, (spare)
+constexpr int STAT_WORDS = 8; // PassArgs::stats, [6..7] spare
 struct DevArena {
 	std::mutex mu;
 	char *base = nullptr;
@@ -173,8 +173,10 @@ struct DevArena {
 	unsigned long long *stat_host = nullptr; // pinned: their latest copy
 	cudaStream_t side = nullptr;             // carries the copies
 	cudaEvent_t ev_side = nullptr;
-	unsigned long long look_hits = 0, look_seen = 0; // counters at AUTO's last look
+	unsigned long long look[STAT_WORDS] = {}; // the counters at AUTO's last look
 	bool heavy = false;                      // AUTO's current belief about this device's work
+	std::chrono::steady_clock::time_point last_copy; // when the counters were last sent for
+	bool copied_once = false;
 };
 DevArena g_arena[MAX_DEVICES];
 
@@ -237,7 +239,10 @@ int launch_solver(KernelArgs a, int dev, cudaStream_t st, uint32_t forced, uint3
 	const PassPolicy pol = pass_policy(fam);
 	const bool can = family_has_passes(fam, a.n) && a.count < 0xfffffff0ull && a.max_iter > pol.w0;
 	bool passes = can && schedule == QP_SCHEDULE_PASSES;
-	bool look = can && schedule == QP_SCHEDULE_AUTO && a.max_iter > 64 && a.count >= 4096;
+	// (the probe adds iteration counts per lane in 32 bits: with 148 SMs a lane sees fewer than
+	// count / 1024 problems)
+	bool look = can && schedule == QP_SCHEDULE_AUTO && a.max_iter > 64 && a.count >= 4096 &&
+		    (a.count / 1024 + 1) * (unsigned long long)a.max_iter < 0xffffffffull;
 	if (look) { // a stream that is being captured into a graph cannot take the side-stream copy
 		cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
 		if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone)
@@ -251,16 +256,36 @@ int launch_solver(KernelArgs a, int dev, cudaStream_t st, uint32_t forced, uint3
 	if (int rc = arena_stats_init(ar))
 		return rc;
 	if (look) {
-		const unsigned long long hits = ar.stat_host[0], seen = ar.stat_host[1];
-		if (seen > ar.look_seen) {
-			ar.heavy = (hits - ar.look_hits) * 128ull > (seen - ar.look_seen);
-			ar.look_hits = hits, ar.look_seen = seen;
+		unsigned long long now[STAT_WORDS], d[STAT_WORDS];
+		for (int k = 0; k < STAT_WORDS; ++k)
+			now[k] = ar.stat_host[k], d[k] = now[k] - ar.look[k];
+		if (!ar.heavy && d[5] > 0) {
+			// single launches since the last look: passes pay when the warps mostly waited for
+			// their slowest problem (less than half of the lane-iterations did work) AND the
+			// iterations are what the time goes to (a pass repeats the factorisation, or moves
+			// the inverse through HBM): mean iteration count >= 16 (thread per QP) / 64 (lane
+			// groups).  Measured both ways on the reference's distribution and the condensed
+			// MPC set, profiles/README.md "Passes".
+			const double mean = double(d[3]) / double(d[5]);
+			const double worked = d[4] ? double(d[3]) / double(d[4]) : 1.0;
+			ar.heavy = worked < 0.5 && mean >= (fam == QP_KERNEL_TPQ ? 16.0 : 64.0);
+			std::memcpy(ar.look, now, sizeof(now));
+		} else if (ar.heavy && d[1] > 0) {
+			// passes since the last look: back to single launches when fewer than 1 problem in
+			// 128 outlived the first window
+			ar.heavy = d[0] * 128ull > d[1];
+			std::memcpy(ar.look, now, sizeof(now));
 		}
 		passes = ar.heavy;
 	}
 	a.ps.stats = ar.stat_dev;
-	a.ps.probe = std::min(pol.w0, a.max_iter);
 	auto copy_stats = [&]() -> int {
+		// an event between back-to-back launches costs a microsecond or two of the stream's
+		// time: behind short solves that follow each other closely, copy every 200 us only
+		const auto now = std::chrono::steady_clock::now();
+		if (ar.copied_once && now - ar.last_copy < std::chrono::microseconds(200))
+			return QP_OK;
+		ar.last_copy = now, ar.copied_once = true;
 		QP_CUDA(cudaEventRecord(ar.ev_side, st));
 		QP_CUDA(cudaStreamWaitEvent(ar.side, ar.ev_side, 0));
 		QP_CUDA(cudaMemcpyAsync(ar.stat_host, ar.stat_dev, STAT_WORDS * 8, cudaMemcpyDeviceToHost, ar.side));
@@ -322,13 +347,12 @@ int launch_solver(KernelArgs a, int dev, cudaStream_t st, uint32_t forced, uint3
 
 } // namespace
 
-extern "C" int qp_schedule_stats(int device, unsigned long long *outlived, unsigned long long *seen,
-				 unsigned long long *evicted_later)
+extern "C" int qp_schedule_stats(int device, unsigned long long stats[6])
 {
 	const int dev = resolve_device(device);
-	if (dev < 0)
+	if (dev < 0 || !stats)
 		return QP_ERR_INVALID;
-	unsigned long long v[STAT_WORDS] = { 0, 0, 0, 0 };
+	unsigned long long v[STAT_WORDS] = {};
 	DevArena &ar = g_arena[dev];
 	std::lock_guard<std::mutex> lk(ar.mu);
 	if (ar.stat_dev) {
@@ -338,12 +362,8 @@ extern "C" int qp_schedule_stats(int device, unsigned long long *outlived, unsig
 		QP_CUDA(cudaDeviceSynchronize());
 		QP_CUDA(cudaMemcpy(v, ar.stat_dev, sizeof(v), cudaMemcpyDeviceToHost));
 	}
-	if (outlived)
-		*outlived = v[0];
-	if (seen)
-		*seen = v[1];
-	if (evicted_later)
-		*evicted_later = v[2];
+	for (int k = 0; k < 6; ++k)
+		stats[k] = v[k];
 	return QP_OK;
 }
 

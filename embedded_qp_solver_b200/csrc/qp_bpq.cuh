@@ -114,8 +114,11 @@ qp_bpq_kernel(const KernelArgs p)
 	__shared__ __align__(16) float sm[BPQ_WARPS * C::GG * C::GROUP];
 	__shared__ float4 ctab[5]; // columns of -I_4, then a zero vector
 
-	if (MODE != PASS_LIST && p.ps.stats && blockIdx.x == 0 && threadIdx.x == 32)
+	__shared__ unsigned long long cta_stat[3]; // PASS_PLAIN probe: iterations, waited-for, problems
+	if (MODE == PASS_FIRST && p.ps.stats && blockIdx.x == 0 && threadIdx.x == 32)
 		atomicAdd(p.ps.stats + 1, p.count);
+	if (threadIdx.x < 3)
+		cta_stat[threadIdx.x] = 0ull;
 	if (threadIdx.x < 5) {
 		const int t = threadIdx.x;
 		ctab[t] = make_float4(t == 0 ? -1.0f : 0.0f, t == 1 ? -1.0f : 0.0f, t == 2 ? -1.0f : 0.0f,
@@ -135,6 +138,7 @@ qp_bpq_kernel(const KernelArgs p)
 	const bool relax = (alpha != 1.0f);
 
 	constexpr bool LIST = MODE == PASS_LIST;
+	unsigned st_it = 0, st_wait = 0, st_n = 0; // PASS_PLAIN probe, per lane
 	// problems this launch works on: the batch, or the list the previous pass left
 	const unsigned long long total = LIST ? (unsigned long long)__ldcg(p.ps.list_count) : p.count;
 	const unsigned long long stride = (unsigned long long)gridDim.x * BPQ_WARPS * G;
@@ -510,12 +514,15 @@ qp_bpq_kernel(const KernelArgs p)
 			status = QP_STATUS_NONFINITE;
 		}
 		if (MODE == PASS_PLAIN) {
-			// how many problems would have been evicted by a first pass with this window: the
-			// host reads it later and picks the schedule of the NEXT call (qp_batch.cu)
+			// the probe of QP_SCHEDULE_AUTO: what my group's problem needed and what its warp
+			// waited for (per-lane sums in the groups' first lanes, added up at the end)
 			if (p.ps.stats) {
-				const unsigned m = __ballot_sync(FULL, valid && g == 0 && unsigned(iters) > p.ps.probe);
-				if (m && lane == 0)
-					atomicAdd(p.ps.stats, (unsigned long long)__popc(m));
+				const bool lead = valid && g == 0;
+				const unsigned mine_it = lead ? unsigned(iters) : 0u;
+				const unsigned mx = __reduce_max_sync(FULL, mine_it);
+				st_it += mine_it;
+				st_wait += lead ? mx : 0u;
+				st_n += lead ? 1u : 0u;
 			}
 		}
 		if (valid && !evict) {
@@ -533,6 +540,21 @@ qp_bpq_kernel(const KernelArgs p)
 				if (p.iters)
 					p.iters[prob] = iters;
 			}
+		}
+	}
+	if (MODE == PASS_PLAIN) {
+		if (p.ps.stats) { // one add per warp to the CTA's sums, one per CTA to the device's
+			__syncwarp();
+			const unsigned a = __reduce_add_sync(FULL, st_it), b = __reduce_add_sync(FULL, st_wait),
+				       c = __reduce_add_sync(FULL, st_n);
+			if (lane == 0) {
+				atomicAdd(&cta_stat[0], (unsigned long long)a);
+				atomicAdd(&cta_stat[1], (unsigned long long)b);
+				atomicAdd(&cta_stat[2], (unsigned long long)c);
+			}
+			__syncthreads();
+			if (threadIdx.x < 3 && cta_stat[threadIdx.x])
+				atomicAdd(p.ps.stats + 3 + threadIdx.x, cta_stat[threadIdx.x]);
 		}
 	}
 }

@@ -25,18 +25,21 @@ namespace qpb {
 // WHERE a problem is evicted changes the schedule and never the result.
 //
 //   PASS_PLAIN  the whole batch, every problem to the end (the round-1 kernel); optionally
-//               counts the problems that needed more than `probe` iterations (stats[0]) and
-//               the problems it looked at (stats[1]), which is how the host notices that the
-//               next call should use passes
+//               adds up the iteration counts and what the warps waited for (stats[3..5]),
+//               which is how the host notices that the next call should use passes
 //   PASS_FIRST  the whole batch, `window` iterations each, the unfinished ones to next_list
 //   PASS_LIST   the problems of `list`, state from scratch, `window` more iterations each,
 //               the unfinished ones to next_list (null: the last pass runs everything out)
 constexpr int PASS_PLAIN = 0, PASS_FIRST = 1, PASS_LIST = 2;
 struct PassArgs {
-	unsigned long long *stats;  // null, or: [0] += problems that outlived the first window
-	                            // (PASS_PLAIN: iters > probe; PASS_FIRST: evicted), [1] += problems
-	                            // looked at (both), [2] += evictions by PASS_LIST launches
-	unsigned probe;
+	unsigned long long *stats;  // null, or counters the kernels add to (qp_batch.cu reads them):
+	                            // [0] problems that outlived the first window (PASS_FIRST: evicted)
+	                            // [1] problems a PASS_FIRST launch looked at
+	                            // [2] evictions by PASS_LIST launches
+	                            // PASS_PLAIN (the probe of QP_SCHEDULE_AUTO), one add per CTA:
+	                            // [3] sum of iteration counts, [4] sum over warps of (largest
+	                            // iteration count in the warp x problems in the warp) -- [3] / [4]
+	                            // is the fraction of lane-iterations that did work --, [5] problems
 	unsigned window;            // PASS_FIRST / PASS_LIST: iterations per problem in this launch
 	const unsigned *list;       // PASS_LIST: problem indices ...
 	const unsigned *list_count; // ... and how many (written by the previous launch)

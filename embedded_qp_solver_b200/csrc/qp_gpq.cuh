@@ -31,9 +31,10 @@
 //   * Arithmetic is issued as packed FP32 pairs (fma.rn.f32x2, SASS FFMA2): a row
 //     lives in registers as NP/2 float2, the elimination multiplier is the scalar
 //     broadcast operand of FFMA2 and the pivot rows arrive from shared memory as
-//     128-bit loads that are already two aligned pairs.  FFMA2 does not raise the
-//     FP32 peak, it halves the issue slots the FMAs need -- this kernel is
-//     issue-bound, not pipe-bound (profiles/README.md).
+//     128-bit loads that are already two aligned pairs.  FFMA2 neither raises the
+//     FP32 peak nor saves issue slots (one FFMA2 takes two, measured:
+//     profiles/r1_probe_ffma2_issue.txt); what it saves is instruction fetch/decode
+//     and register-file reads of the shared multiplier (profiles/README.md).
 #pragma once
 
 #include "qp_common.cuh"

@@ -152,6 +152,7 @@ qp_tpq_kernel(const KernelArgs p)
 	constexpr bool LIST = MODE == PASS_LIST;
 
 	extern __shared__ __align__(128) unsigned char smem_raw[];
+	__shared__ unsigned long long cta_stat[3]; // PASS_PLAIN probe: iterations, waited-for, problems
 	float *ring = reinterpret_cast<float *>(smem_raw);
 	float *priv_all = ring + STAGES * L::STAGE;
 	uint64_t *full_bar = reinterpret_cast<uint64_t *>(priv_all + Cfg::WARPS * L::PRIV);
@@ -170,8 +171,9 @@ qp_tpq_kernel(const KernelArgs p)
 
 	if (!LIST) {
 		if (threadIdx.x == 0) {
-			if (p.ps.stats && blockIdx.x == 0)
+			if (MODE == PASS_FIRST && p.ps.stats && blockIdx.x == 0)
 				atomicAdd(p.ps.stats + 1, p.count);
+			cta_stat[0] = cta_stat[1] = cta_stat[2] = 0ull;
 			for (int s = 0; s < STAGES; ++s) {
 				mbar_init(&full_bar[s], 1);
 				stage_round[s] = 0;
@@ -243,6 +245,7 @@ qp_tpq_kernel(const KernelArgs p)
 	}
 
 	bool out_pending = false; // this warp has a bulk store in flight from priv_out
+	unsigned st_it = 0, st_wait = 0, st_n = 0; // PASS_PLAIN probe, per lane
 	unsigned long long lbatch = (unsigned long long)blockIdx.x * Cfg::WARPS + warp; // LIST: static stride
 
 	for (;;) {
@@ -534,12 +537,15 @@ qp_tpq_kernel(const KernelArgs p)
 				p.iters[gidx] = my_iters;
 		}
 		if (MODE == PASS_PLAIN) {
-			// how many problems would have been evicted by a first pass with this window: the
-			// host reads it later and picks the schedule of the NEXT call (qp_batch.cu)
+			// the probe of QP_SCHEDULE_AUTO: what my problem needed and what its warp waited for
+			// (per-lane sums, added up once at the end of the kernel; the host keeps them from
+			// overflowing 32 bits by not probing absurd max_iter x count combinations)
 			if (p.ps.stats) {
-				const unsigned m = __ballot_sync(FULL, valid && unsigned(my_iters) > p.ps.probe);
-				if (m && lane == 0)
-					atomicAdd(p.ps.stats, (unsigned long long)__popc(m));
+				const unsigned mine_it = valid ? unsigned(my_iters) : 0u;
+				const unsigned mx = __reduce_max_sync(FULL, mine_it);
+				st_it += mine_it;
+				st_wait += valid ? mx : 0u;
+				st_n += valid ? 1u : 0u;
 			}
 		}
 
@@ -597,6 +603,21 @@ qp_tpq_kernel(const KernelArgs p)
 	if (lane == 0)
 		bulk_wait_read();
 	__syncwarp();
+	if (MODE == PASS_PLAIN) {
+		if (p.ps.stats) { // one add per warp to the CTA's sums, one per CTA to the device's
+			const unsigned a = __reduce_add_sync(FULL, st_it), b = __reduce_add_sync(FULL, st_wait),
+				       c = __reduce_add_sync(FULL, st_n);
+			if (lane == 0) {
+				// (the per-lane sums fit 32 bits, their sum over 32 lanes may not: widen first)
+				atomicAdd(&cta_stat[0], (unsigned long long)a);
+				atomicAdd(&cta_stat[1], (unsigned long long)b);
+				atomicAdd(&cta_stat[2], (unsigned long long)c);
+			}
+			__syncthreads();
+			if (threadIdx.x < 3 && cta_stat[threadIdx.x])
+				atomicAdd(p.ps.stats + 3 + threadIdx.x, cta_stat[threadIdx.x]);
+		}
+	}
 }
 
 } // namespace qpb

@@ -169,11 +169,14 @@ typedef struct qp_options {
  *   QP_SCHEDULE_AUTO    SINGLE, except for batches of at least 4 096 problems
  *                       with max_iter > 64 on the kernel families that have
  *                       passes (n = 4, 8, 12, 16 and n = 24, 32, 40): there
- *                       the single launch also counts the problems that needed
- *                       more than 24 iterations, the count reaches the host
+ *                       the single launch also adds up, per warp, the
+ *                       iterations its problems needed and the iterations it
+ *                       waited for its slowest one; the sums reach the host
  *                       asynchronously, and the NEXT such solve on the device
- *                       uses PASSES when more than 1 problem in 128 did (and
- *                       goes back to SINGLE when the tail disappears).
+ *                       uses PASSES when less than half of the lane-iterations
+ *                       did work and the mean iteration count is at least 16
+ *                       (n <= 16) or 64 (n >= 24); it goes back to SINGLE when
+ *                       fewer than 1 problem in 128 outlives the first window.
  */
 #define QP_SCHEDULE_AUTO   0
 #define QP_SCHEDULE_SINGLE 1
@@ -361,12 +364,15 @@ unsigned long long qp_host_path_h2d_bytes(void);
  * stores (QP_ERR_UNSUPPORTED without AVX-512; n = 16 only), -1 = what the host path uses. */
 int qp_host_pack_upper(const float *P, float *out, size_t count, uint32_t n, int wide);
 
-/* Counters of the schedules above on `device` since the process started (any pointer may be
- * NULL): *outlived = problems that needed more than the first window (counted by AUTO's
- * probing single launches and by first passes), *seen = problems those launches looked at,
- * *evicted_later = evictions by the later passes.  Waits for the device. */
-int qp_schedule_stats(int device, unsigned long long *outlived, unsigned long long *seen,
-		      unsigned long long *evicted_later);
+/* Counters of the schedules above on `device` since the process started:
+ *   stats[0] problems that outlived the first window of a PASSES solve,
+ *   stats[1] problems those first passes looked at,
+ *   stats[2] evictions by the later passes,
+ *   stats[3] sum of iteration counts seen by AUTO's probing single launches,
+ *   stats[4] sum over their warps of (largest iteration count x problems in the warp),
+ *   stats[5] problems they looked at.
+ * Waits for the device. */
+int qp_schedule_stats(int device, unsigned long long stats[6]);
 
 /* Pure-copy ceiling of the QP_MEM_HOST path (measurement helper): moves h2d_bytes host to
  * device and d2h_bytes device to host per repeat between pinned (pinned != 0) or pageable

@@ -38,7 +38,8 @@ def test_reference_arm_line():
 
 @pytest.mark.gpu
 def test_our_arm_line():
-    l = run_bench("--steps", "5", "--warmup", "3", "--count", "65536", "--cpu-sample", "20000")
+    l = run_bench("--steps", "5", "--warmup", "3", "--count", "65536", "--cpu-sample", "20000",
+                  "--shape-steps", "2", "--sustained-s", "0.5")
     assert BASE_KEYS | {"roofline", "clocks"} <= set(l)
     assert l["n_gpus"] == 1 and l["steps"] == 5 and l["warmup"] >= 3 and l["gpu_launches"] == 5
     assert l["scaling"] == "weak" and l["dtype"] == "f32" and l["data"] == "synthetic"
@@ -52,3 +53,15 @@ def test_our_arm_line():
     assert l["cpu_baseline"]["value"] > 0 and l["cpu_baseline"]["cores"] >= 1
     assert "sm_mhz" in l["clocks"] and "reasons" in l["clocks"]
     assert l["not_converged"] == 0
+    assert e["copy_ceiling"] > 0 and 0 < e["frac_of_ceiling"] <= 1.3
+    assert e["pageable"]["value"] > 0 and e["pageable"]["matches_device_path"] is True
+    su = l["sustained"]
+    assert su["seconds"] >= 0.5 and su["value"] > 0 and "sm_mhz" in su["clocks"]
+    sh = {d["shape"]: d for d in l["shapes"]}
+    assert len(sh) >= 6
+    for d in sh.values():
+        assert d["qp_per_s"] > 0 and d["not_converged"] == 0 and d["mean_iters"] >= 1
+        assert {"hbm_frac", "fp32_reference_frac", "fp32_executed_frac", "issue_frac", "roofline_frac"} <= set(d)
+    assert any(k.startswith("n=4,") for k in sh) and any("MPC" in k for k in sh)
+    assert any("warm" in k for k in sh) and any(k.startswith("n=64") and "cold" in k for k in sh)
+    assert "compiler" in l["cpu_baseline"]

@@ -170,33 +170,40 @@ def test_host_path_with_passes(qp):
 
 def test_auto_follows_the_tail(qp):
     """QP_SCHEDULE_AUTO: small batches and small iteration caps are plain launches that count
-    nothing; a large batch is a plain launch that counts the problems outliving the first
-    window, and the solve after one that saw a heavy tail runs in passes (and goes back)."""
+    nothing; a large batch is a plain launch that adds up what its warps did and what they
+    waited for, and the solve after one whose warps mostly waited runs in passes (and goes
+    back when nothing outlives the first window any more)."""
     n = 16
     P, q, _, _ = problems.refdist(4096, n, seed=41, box=1e4)
     Pw, qw, _, _ = problems.wellcond(4096, n, seed=42, beta=0.5)
     ref = run(qp, P, q, -1e4, 1e4, qp.SCHEDULE_SINGLE, options=qp.Options(max_iter=300))
+    # whatever earlier tests left behind: two well-conditioned solves put AUTO into single launches
+    for _ in range(2):
+        run(qp, Pw, qw, -0.5, 0.5, qp.SCHEDULE_AUTO, options=qp.Options(max_iter=300))
     s0 = qp.schedule_stats()
     run(qp, P[:512], q[:512], -1e4, 1e4, qp.SCHEDULE_AUTO, options=qp.Options(max_iter=300))
     run(qp, P, q, -1e4, 1e4, qp.SCHEDULE_AUTO, options=qp.Options(max_iter=50))
     assert qp.schedule_stats() == s0     # small batch / few iterations allowed: nothing counted
-    # heavy tail: at the latest the second solve uses passes
-    for k in range(3):
-        a = run(qp, P, q, -1e4, 1e4, qp.SCHEDULE_AUTO, options=qp.Options(max_iter=300))
-        same(a, ref, f"auto #{k}")
+    # heavy tail: the first solve probes, the second one runs in passes
+    a = run(qp, P, q, -1e4, 1e4, qp.SCHEDULE_AUTO, options=qp.Options(max_iter=300))
+    same(a, ref, "auto, probing")
     s1 = qp.schedule_stats()
-    assert s1["seen"] - s0["seen"] == 3 * 4096
-    assert s1["outlived"] - s0["outlived"] > 3 * 1024
-    assert s1["evicted_later"] > s0["evicted_later"], "AUTO never switched to passes"
-    # the tail disappears: back to plain launches (nothing is evicted at all any more)
+    assert s1["probe_problems"] - s0["probe_problems"] == 4096 and s1["seen"] == s0["seen"]
+    assert s1["probe_iterations"] - s0["probe_iterations"] == int(ref["iters"].sum())
+    worked = (s1["probe_iterations"] - s0["probe_iterations"]) / (s1["probe_waited_for"] - s0["probe_waited_for"])
+    assert worked < 0.5
+    for k in range(2):
+        a = run(qp, P, q, -1e4, 1e4, qp.SCHEDULE_AUTO, options=qp.Options(max_iter=300))
+        same(a, ref, f"auto, passes #{k}")
+    s2 = qp.schedule_stats()
+    assert s2["seen"] - s1["seen"] == 2 * 4096 and s2["outlived"] - s1["outlived"] > 2 * 1024
+    assert s2["evicted_later"] > s1["evicted_later"] and s2["probe_problems"] == s1["probe_problems"]
+    # the tail disappears: one more solve in passes (nothing evicted), then single launches again
     for k in range(3):
         run(qp, Pw, qw, -0.5, 0.5, qp.SCHEDULE_AUTO, options=qp.Options(max_iter=300))
-    s2 = qp.schedule_stats()
-    assert s2["outlived"] == s1["outlived"] and s2["evicted_later"] == s1["evicted_later"]
-    a = run(qp, P, q, -1e4, 1e4, qp.SCHEDULE_AUTO, options=qp.Options(max_iter=300))
     s3 = qp.schedule_stats()
-    assert s3["evicted_later"] == s2["evicted_later"], "first heavy solve after a light one should be plain"
-    same(a, ref, "auto after light")
+    assert s3["outlived"] == s2["outlived"] and s3["seen"] - s2["seen"] == 4096
+    assert s3["probe_problems"] - s2["probe_problems"] == 2 * 4096
 
 
 def test_two_streams_share_the_arena(qp):
