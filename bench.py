@@ -349,6 +349,7 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=400_000)
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 20)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-chunk", type=int, default=0, help="qp_options.chunk of the host path (0 = library's choice)")
     ap.add_argument("--no-shapes", action="store_true", help="skip the other BASELINE shapes (N = 1)")
     ap.add_argument("--shape-steps", type=int, default=10)
     ap.add_argument("--sustained-s", type=float, default=2.5, help="0 = skip the sustained run")
@@ -481,7 +482,7 @@ def run_ours(args, rank, local_rank, world):
         hout = {k: torch.empty((count, n)).pin_memory() for k in ("x", "z", "lam")}
         hout.update({k: torch.empty(count, dtype=torch.int32).pin_memory()
                      for k in ("status", "iters")})
-        hopts = qp.Options(device=local_rank)
+        hopts = qp.Options(device=local_rank, chunk=args.e2e_chunk)
         for _ in range(max(3, min(args.warmup, 5))):
             qp.solve_batch(hP, hq, -args.beta, args.beta, options=hopts, out=hout)
         ksteps = args.e2e_steps or min(args.steps, 20)
@@ -499,17 +500,63 @@ def run_ours(args, rank, local_rank, world):
             dt = float(t.item())
         same = bool(torch.equal(hout["iters"], out["iters"].cpu()))
         # what the copy engines and the host's memory system allow for the same bytes with no
-        # kernel in between, every rank at once (pinned, both directions on two streams)
+        # kernel in between: the very buffers of the timed run, H2D on one stream and D2H on
+        # another, five rounds back to back behind a barrier so that all ranks copy AT THE SAME
+        # TIME (a probe that allocates its own buffers lets the ranks drift apart and overstates
+        # what N GPUs get from one host)
         h2d_b, d2h_b = (n * n + n) * 4 * count, (3 * n + 2) * 4 * count
-        barrier()
-        ceil_s = qp.probe_copy_seconds(h2d_b, d2h_b, device=local_rank, pinned=True, repeats=3)
-        barrier()
+        sc0, sc1 = torch.cuda.Stream(device), torch.cuda.Stream(device)
+        dPf, hPf = P.view(-1), hP.view(-1)
+
+        def copy_rounds(p_floats, rounds=5):
+            barrier()
+            t0c = time.perf_counter()
+            for _ in range(rounds):
+                with torch.cuda.stream(sc0):
+                    dPf[:p_floats].copy_(hPf[:p_floats], non_blocking=True)
+                    q.copy_(hq, non_blocking=True)
+                with torch.cuda.stream(sc1):
+                    for k_ in hout:
+                        hout[k_].copy_(out[k_], non_blocking=True)
+            torch.cuda.synchronize()
+            dtc = (time.perf_counter() - t0c) / rounds
+            if world > 1:
+                tt = torch.tensor([dtc], device=device)
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                dtc = float(tt.item())
+            return dtc
+
+        copy_rounds(count * n * n, rounds=1)
+        ceil_s = copy_rounds(count * n * n)
         # ... and for the bytes the library really sent (it may pack the upper triangles)
-        ceil_w = qp.probe_copy_seconds(int(wire), d2h_b, device=local_rank, pinned=True, repeats=3)
-        if world > 1:
-            t = torch.tensor([ceil_s, ceil_w], device=device)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ceil_s, ceil_w = float(t[0].item()), float(t[1].item())
+        wire_p_floats = max(0, int(wire) - n * 4 * count) // 4
+        ceil_w = ceil_s if wire_p_floats >= count * n * n else copy_rounds(wire_p_floats)
+        P.copy_(hP)  # the rounds above left (the same) data in place; make that explicit
+        torch.cuda.synchronize()
+        # a caller that produces the QP_P_UPPER layout itself (row-major upper triangles, 544
+        # instead of 1024 bytes of P per problem at n = 16): same call, 47 % fewer bytes
+        upper = None
+        if n in (8, 12, 16):
+            iu = torch.triu_indices(n, n)
+            hU = torch.zeros((count, qp.packed_stride(n))).pin_memory()
+            hU[:, :iu.shape[1]] = hP[:, iu[0], iu[1]]
+            for _ in range(2):
+                qp.solve_batch(hU, hq, -args.beta, args.beta, options=hopts, out=hout, p_layout=qp.P_UPPER)
+            barrier()
+            tu0 = time.perf_counter()
+            for _ in range(ksteps):
+                qp.solve_batch(hU, hq, -args.beta, args.beta, options=hopts, out=hout, p_layout=qp.P_UPPER)
+            torch.cuda.synchronize()
+            udt = (time.perf_counter() - tu0) / ksteps
+            if world > 1:
+                t = torch.tensor([udt], device=device)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                udt = float(t.item())
+            upper = {"value": count * world / udt, "unit": UNIT, "ms_per_step": udt * 1e3,
+                     "h2d_bytes_per_step": (qp.packed_stride(n) + n) * 4 * count,
+                     "d2h_bytes_per_step": d2h_b,
+                     "matches_device_path": bool(torch.equal(hout["iters"], out["iters"].cpu()))}
+            del hU
         # pageable caller memory (staged through the workspace's pinned buffers), fewer steps
         pageable = None
         if world == 1:
@@ -541,11 +588,12 @@ def run_ours(args, rank, local_rank, world):
                "host_memory": "pinned",
                "copy_ceiling": count * world / ceil_w, "frac_of_ceiling": ceil_w / dt,
                "copy_ceiling_dense": count * world / ceil_s,
-               "copy_ceiling_note": "qp_probe_copy_seconds: the H2D bytes the library put on the wire and the "
-                                    "D2H bytes, per rank, pinned, two streams, no kernel, all ranks at once "
-                                    "(max over ranks); copy_ceiling_dense = the same for the caller's dense "
-                                    "bytes (what a plain copy of the row-major matrices would be bound by)",
-               "pageable": pageable}
+               "copy_ceiling_note": "the H2D bytes the library put on the wire and the D2H bytes of one step, "
+                                    "from and to the same pinned buffers, two streams, no kernel, five rounds "
+                                    "with all ranks copying at the same time (max over ranks); "
+                                    "copy_ceiling_dense = the same for the caller's dense bytes (what a plain "
+                                    "copy of the row-major matrices is bound by)",
+               "pageable": pageable, "caller_packed_upper_layout": upper}
         del hP, hq, hout
 
     # ---- the library's own multi-GPU entry: ONE qp_solve_batch call over all N GPUs ----------
