@@ -27,6 +27,7 @@ def solve_file(path: str):
                           options=api.Options(abstol=1e-7, reltol=1e-7, max_iter=20000))
     x = res["x"].astype(np.float64)
     f = 0.5 * np.einsum("ci,cij,cj->c", x, P, x) + np.einsum("ci,ci->c", q, x)
+    solve_file.not_converged = np.flatnonzero(res["status"] != api.STATUS_CONVERGED)
     return P, q, x, f
 
 
@@ -39,6 +40,14 @@ def main(argv=None) -> int:
     for v in f:
         print("reference implementation gave:")
         print("f(x_min) = %e" % v)
+    bad = solve_file.not_converged
+    if len(bad):
+        # binary32 ADMM at a 1e-7 tolerance can run into its iteration cap on the reference's
+        # ill-conditioned test matrices: what was printed for these records is not an optimum
+        print(f"qp_ref: {len(bad)} record(s) did not reach the 1e-7 tolerance within 20000 "
+              f"iterations (first: {int(bad[0])}); their f(x_min) is an upper bound only",
+              file=sys.stderr)
+        return 1
     return 0
 
 
