@@ -276,7 +276,8 @@ def run_shapes(args, qp, torch, device, hbm_peak, fp32_peak, traffic, sm_mhz):
         k = float(out["iters"].float().mean())
         d = {"shape": name, "n": n, "m": 2 * n, "count": count, "warm_start": warm}
         d.update(fractions(qp, n, count, ms, k, warm, hbm_peak, fp32_peak,
-                           traffic.get(f"{qp.kernel_for(n)}@{count}") if note.get("issue_ok") else None,
+                           traffic.get(note.get("issue_key") or f"{qp.kernel_for(n)}@{count}")
+                           if (note.get("issue_ok") or note.get("issue_key")) else None,
                            sm_mhz, sms))
         d["not_converged"] = int((out["status"] != 0).sum())
         d["inputs"] = note["inputs"]
@@ -325,7 +326,8 @@ def run_shapes(args, qp, torch, device, hbm_peak, fp32_peak, traffic, sm_mhz):
     first = qp.solve_batch(P, q, -args.beta, args.beta)
     out = {k: v.clone() for k, v in first.items()}
     ms = time_steps(torch, lambda i: qp.solve_batch(P, q, -args.beta, args.beta, out=out), steps)
-    entry("n=64,m=128 cold", n, count, ms, out, False, {"inputs": "1.07 GB > L2"})
+    entry("n=64,m=128 cold", n, count, ms, out, False,
+          {"inputs": "1.07 GB > L2", "issue_key": f"{qp.kernel_for(n)}@{count} cold"})
     q2 = q + 0.01 * torch.randn_like(q)
     z0, u0 = first["z"].clone(), first["lam"].clone()
     ms = time_steps(torch, lambda i: qp.solve_batch(P, q2, -args.beta, args.beta, z0=z0, u0=u0, out=out), steps)
