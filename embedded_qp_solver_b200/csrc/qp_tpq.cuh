@@ -246,7 +246,10 @@ qp_tpq_kernel(const KernelArgs p)
 
 	bool out_pending = false; // this warp has a bulk store in flight from priv_out
 	unsigned st_it = 0, st_wait = 0, st_n = 0; // PASS_PLAIN probe, per lane
-	unsigned long long lbatch = (unsigned long long)blockIdx.x * Cfg::WARPS + warp; // LIST: static stride
+	// LIST: static stride, warp-major -- a short list (the late passes hold a few hundred
+	// stragglers that each run thousands of dependent iterations) spreads over the SMs one warp
+	// per SM instead of filling the first few CTAs, whose warps would share issue slots
+	unsigned long long lbatch = (unsigned long long)warp * gridDim.x + blockIdx.x;
 
 	for (;;) {
 		int t = 0;
