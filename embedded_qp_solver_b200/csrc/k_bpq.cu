@@ -36,8 +36,9 @@ template <int NP, bool PFI, int MODE> int launch_bpq_m(const KernelArgs &a, int 
 		per_sm.set(dev, b);
 	}
 	// (a list pass is sized for the whole batch: how long its list is, only the device knows)
-	constexpr unsigned long long per_cta = BPQ_WARPS * BpqCfg<NP>::G;
-	const unsigned long long need = (a.count + per_cta - 1) / per_cta;
+	// (a small batch spreads over the SMs, one warp's worth per CTA: latency counts there)
+	constexpr unsigned long long per_warp = BpqCfg<NP>::G;
+	const unsigned long long need = (a.count + per_warp - 1) / per_warp;
 	unsigned long long grid = (unsigned long long)dev_sms(dev) * b;
 	grid = std::max(1ull, std::min(grid, need));
 	kern<<<dim3((unsigned)grid), dim3(BPQ_WARPS * 32), 0, st>>>(a);

@@ -30,9 +30,10 @@ int launch_tpq_m(const KernelArgs &a, int dev, cudaStream_t st)
 	// (a list pass is sized for the whole batch: how long its list is, only the device knows)
 	const unsigned long long nbatch = (a.count + 31ull) / 32ull;
 	unsigned long long grid = (unsigned long long)dev_sms(dev) * b;
-	// every warp of a CTA should have a batch to work on
-	const unsigned long long need = (nbatch + Cfg::WARPS - 1) / Cfg::WARPS;
-	grid = std::max(1ull, std::min(grid, need));
+	// a small batch spreads over the SMs (one warp batch per CTA, the other warps leave at once)
+	// rather than filling a few CTAs whose warps would share issue slots: it is latency that
+	// counts there
+	grid = std::max(1ull, std::min(grid, nbatch));
 	kern<<<dim3((unsigned)grid), dim3(Cfg::WARPS * 32), L::BYTES, st>>>(a);
 	QP_CUDA(cudaGetLastError());
 	return QP_OK;

@@ -142,10 +142,9 @@ qp_bpq_kernel(const KernelArgs p)
 	// problems this launch works on: the batch, or the list the previous pass left
 	const unsigned long long total = LIST ? (unsigned long long)__ldcg(p.ps.list_count) : p.count;
 	const unsigned long long stride = (unsigned long long)gridDim.x * BPQ_WARPS * G;
-	// (a list pass deals its warps' work warp-major: a short list spreads over the SMs one warp
-	// per SM instead of filling the first few CTAs)
-	for (unsigned long long base = (LIST ? (unsigned long long)warp * gridDim.x + blockIdx.x
-					     : (unsigned long long)blockIdx.x * BPQ_WARPS + warp) * G;
+	// (work is dealt warp-major: a small batch, or the short list of a late pass, spreads over
+	// the SMs one warp per SM instead of filling the first few CTAs)
+	for (unsigned long long base = ((unsigned long long)warp * gridDim.x + blockIdx.x) * G;
 	     base < total; base += stride) {
 		const bool valid = (grp < G) && (base + grp < total);
 		unsigned long long prob = base + grp;
