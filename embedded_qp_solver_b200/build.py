@@ -26,6 +26,7 @@ UNITS = {
     "k_tpq12.cu": ["qp_tpq.cuh", "k_tpq_impl.cuh"],
     "k_tpq16.cu": ["qp_tpq.cuh", "k_tpq_impl.cuh"],
     "k_bpq.cu": ["qp_bpq.cuh", "qp_gpq.cuh"],
+    "k_bpqs.cu": ["qp_bpq_stream.cuh", "qp_bpq.cuh", "qp_gpq.cuh"],
     "k_gpq.cu": ["qp_gpq.cuh"],
     "k_cpq.cu": ["qp_cpq.cuh"],
     "k_aux.cu": ["qp_gen.cuh", "qp_newton.cuh"],

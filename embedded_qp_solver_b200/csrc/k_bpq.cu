@@ -23,6 +23,15 @@ bool bpq_eligible(const KernelArgs &a)
 	return true;
 }
 
+// the streaming second pass keeps the full inverse in registers: not for the batches that
+// launch_bpq() below solves in product form
+bool bpq_stream_eligible(const KernelArgs &a)
+{
+	// (and it takes lb and ub as a pair of arrays or not at all)
+	return bpq_eligible(a) && !(a.n >= QPB_BPQ_PFI_FROM && a.z0 != nullptr) &&
+	       ((a.lb == nullptr) == (a.ub == nullptr));
+}
+
 namespace {
 
 template <int NP, bool PFI, int MODE> int launch_bpq_m(const KernelArgs &a, int dev, cudaStream_t st)

@@ -187,9 +187,14 @@ struct PassPolicy {
 // thread-per-QP and lane groups: 24, 48, 96, ... iterations (the benchmark distribution needs
 // at most 18, so a first pass evicts nothing of it).  QPB200_PASSES="w0,grow" overrides
 // (measurements, tests).
-PassPolicy pass_policy(int)
+// Lane groups followed by the streaming pass (qp_bpq_stream.cuh): a first window of 6 -- it only
+// has to tell the expected stragglers from the rest (the classifier in qp_bpq.cuh needs about 6
+// iterations), every iteration beyond that is cheaper in the streaming kernel, where no group
+// waits for another (condensed-MPC set, 2^18 problems: window 24 64 M QP/s, 12 75 M, 8 78 M,
+// 6 and 4 80-81 M).
+PassPolicy pass_policy(int, bool stream)
 {
-	PassPolicy pol = { 24u, 1u };
+	PassPolicy pol = { stream ? 6u : 24u, 1u };
 	if (const char *e = std::getenv("QPB200_PASSES")) {
 		unsigned a = 0, b = 0;
 		if (std::sscanf(e, "%u,%u", &a, &b) == 2 && a > 0)
@@ -236,7 +241,9 @@ int launch_solver(KernelArgs a, int dev, cudaStream_t st, uint32_t forced, uint3
 	const int fam = pick_kernel(a, forced);
 	if (!fam)
 		return QP_ERR_UNSUPPORTED;
-	const PassPolicy pol = pass_policy(fam);
+	const char *se = std::getenv("QPB200_BPQ_STREAM"); // =0: list passes instead of the streaming pass
+	const bool stream = fam == QP_KERNEL_BPQ && !(se && se[0] == '0') && bpq_stream_eligible(a);
+	const PassPolicy pol = pass_policy(fam, stream);
 	const bool can = family_has_passes(fam, a.n) && a.count < 0xfffffff0ull && a.max_iter > pol.w0;
 	bool passes = can && schedule == QP_SCHEDULE_PASSES;
 	// (the probe adds iteration counts per lane in 32 bits: with 148 SMs a lane sees fewer than
@@ -268,12 +275,18 @@ int launch_solver(KernelArgs a, int dev, cudaStream_t st, uint32_t forced, uint3
 			// MPC set, profiles/README.md "Passes".
 			const double mean = double(d[3]) / double(d[5]);
 			const double worked = d[4] ? double(d[3]) / double(d[4]) : 1.0;
-			ar.heavy = worked < 0.5 && mean >= (fam == QP_KERNEL_TPQ ? 16.0 : 64.0);
+			// (the streaming pass has no list passes to pay for and no group waits in it: it is
+			// ahead as soon as a quarter of the lane-iterations wait and the iterations, not the
+			// elimination, are where the time goes -- MPC set: 0.58 worked, mean 36)
+			ar.heavy = stream ? (worked < 0.75 && mean >= 24.0)
+					  : (worked < 0.5 && mean >= (fam == QP_KERNEL_TPQ ? 16.0 : 64.0));
 			std::memcpy(ar.look, now, sizeof(now));
 		} else if (ar.heavy && d[1] > 0) {
 			// passes since the last look: back to single launches when fewer than 1 problem in
-			// 128 outlived the first window
-			ar.heavy = d[0] * 128ull > d[1];
+			// 128 outlived the first window -- or, with the streaming pass (whose first window
+			// nearly everything outlives), when the streamed problems needed fewer than 20
+			// iterations on average
+			ar.heavy = stream ? (d[7] == 0 || d[6] >= 20ull * d[7]) : d[0] * 128ull > d[1];
 			std::memcpy(ar.look, now, sizeof(now));
 		}
 		passes = ar.heavy;
@@ -313,7 +326,8 @@ int launch_solver(KernelArgs a, int dev, cudaStream_t st, uint32_t forced, uint3
 	const bool want_R = fam == QP_KERNEL_BPQ;
 	const size_t o_list0 = 256, o_list1 = o_list0 + up256(c * 4), o_its = o_list1 + up256(c * 4),
 		     o_zs = o_its + up256(c * 4), o_us = o_zs + up256(c * n * 4),
-		     o_R = o_us + up256(c * n * 4), need = o_R + (want_R ? up256(c * n * n * 4) : 0);
+		     o_xs = o_us + up256(c * n * 4), o_R = o_xs + (want_R ? up256(c * n * 4) : 0),
+		     need = o_R + (want_R ? up256(c * n * n * 4) : 0);
 	if (ar.bytes < need) {
 		QP_CUDA(cudaEventSynchronize(ar.last)); // nobody is using the old one any more
 		if (ar.base)
@@ -331,6 +345,28 @@ int launch_solver(KernelArgs a, int dev, cudaStream_t st, uint32_t forced, uint3
 	a.ps.zs = reinterpret_cast<float *>(ar.base + o_zs);
 	a.ps.us = reinterpret_cast<float *>(ar.base + o_us);
 	a.ps.Rs = want_R ? reinterpret_cast<float *>(ar.base + o_R) : nullptr;
+	a.ps.xs = (want_R && stream) ? reinterpret_cast<float *>(ar.base + o_xs) : nullptr;
+	// lane groups with the full inverse: two launches -- a first window for everybody, then the
+	// streaming kernel (qp_bpq_stream.cuh) runs the unfinished problems out, each lane group
+	// taking its next one as soon as its current one stops.
+	if (stream && npass >= 2) {
+		a.ps.window = win[0];
+		a.ps.list = nullptr, a.ps.list_count = nullptr;
+		a.ps.next_list = list[0], a.ps.next_count = cnt;
+		a.ps.next_list2 = list[1], a.ps.next_count2 = cnt + 1;
+		if (int rc = launch_family(a, fam, dev, st, PASS_FIRST))
+			return rc;
+		a.ps.window = a.max_iter;
+		a.ps.list = list[0], a.ps.list_count = cnt;
+		a.ps.list2 = list[1], a.ps.list_count2 = cnt + 1;
+		a.ps.next_list = nullptr, a.ps.next_count = nullptr;
+		a.ps.next_list2 = nullptr, a.ps.next_count2 = nullptr;
+		a.ps.stream_ctr = cnt + (MAX_PASSES - 1);
+		if (int rc = launch_bpq_stream_family(a, dev, st))
+			return rc;
+		QP_CUDA(cudaEventRecord(ar.last, st));
+		return copy_stats();
+	}
 	for (int k = 0; k < npass; ++k) {
 		const bool last = k == npass - 1;
 		a.ps.window = win[k];

@@ -301,6 +301,19 @@ qp_bpq_kernel(const KernelArgs p)
 		}
 		}
 		__syncwarp();
+		// PASS_FIRST: the inverse (or eta file) goes to scratch now, for every problem, in uniform
+		// code -- not after the window from the lanes of the evicted ones.  (Keeping S alive
+		// behind the iteration loop cost the elimination loop its load scheduling: twice the
+		// short-scoreboard stalls, 1.82 against 1.57 ms on 2^18 random problems that evict
+		// nobody; and with the streaming pass behind a short window most problems are evicted.)
+		if (MODE == PASS_FIRST) {
+			if (valid && !bad && p.ps.next_list) {
+				float4 *Rp = reinterpret_cast<float4 *>(p.ps.Rs + prob * (unsigned long long)(NP * NP)) + g;
+#pragma unroll
+				for (int j = 0; j < NP; ++j)
+					Rp[j * (NP / 4)] = make_float4(S[0][j].x, S[0][j].y, S[1][j].x, S[1][j].y);
+			}
+		}
 
 		// ---- per-coordinate state: coordinates 4g..4g+3 ---------------------------------------
 		float q[4], lo[4], hi[4], z[4], u[4], x[4];
@@ -394,10 +407,27 @@ qp_bpq_kernel(const KernelArgs p)
 		};
 		// stop test (:233-253, :308), squared form as in qp_tpq.cuh; lane 0 of the group
 		// decides for everybody
+		// PASS_FIRST also notes whether the problem looks like a straggler: at the rate ||x - z||^2
+		// shrank in the last iteration of the window (d = previous / current), it needs more than
+		// 32 further iterations to get under its threshold -- rr > eps_pri^2 d^32.  Problems evicted
+		// in that state go to the list the streaming pass hands out first.  (Offline check on the
+		// condensed-MPC set, float64 restatement: with a window of 6 the rule flags 4.8 % of the
+		// problems, among them the eight slowest (321 ... 2 783 iterations), and the longest one
+		// it misses needs 315 more; windows 8 ... 24: 9 ... 24 % flagged, longest miss 213 ... 169.
+		// The dual residual and plain decay rates rank them far worse.)
+		float rr_prev = 0.f;
+		bool slow = false;
 		auto converged = [&](float rr, float ss, float nx, float nz, float nu, unsigned am) {
 			const float eps_pri = fmaf(p.reltol, sqrt_approx(fmaxf(nx, nz)), p.eps_abs);
 			const float eps_dual = fmaf(relrho, sqrt_approx(nu), p.eps_abs);
-			int conv = (rr < eps_pri * eps_pri) && (rho2 * ss < eps_dual * eps_dual);
+			const bool cp = rr < eps_pri * eps_pri, cd = rho2 * ss < eps_dual * eps_dual;
+			if (MODE == PASS_FIRST) {
+				float d = rr_prev * rcp_approx(rr);
+				d *= d, d *= d, d *= d, d *= d, d *= d;
+				slow = rr > eps_pri * eps_pri * d;
+				rr_prev = rr;
+			}
+			int conv = cp && cd;
 			if constexpr ((T & (T - 1)) != 0)
 				conv = __shfl_sync(am, conv, gbase);
 			return conv != 0;
@@ -408,6 +438,7 @@ qp_bpq_kernel(const KernelArgs p)
 		// the other groups at the __syncwarp() behind it: no ballot, no flag to test.
 		const unsigned am = (((1u << T) - 1u) << gbase);
 		bool conv = false;
+		float xnext[4] = { 0.f, 0.f, 0.f, 0.f }; // full inverse: the x-update after the last iteration done
 		if constexpr (PFI) {
 		if (active) {
 			do {
@@ -465,6 +496,7 @@ qp_bpq_kernel(const KernelArgs p)
 				conv = converged(rr, ss, nx, nz, nu, am);
 			} while (!conv && it < QPB_BPQ_IT_END);
 		}
+		xnext[0] = xr[0], xnext[1] = xr[1], xnext[2] = xr[2], xnext[3] = xr[3];
 		}
 #undef QPB_BPQ_IT_END
 		__syncwarp();
@@ -483,25 +515,43 @@ qp_bpq_kernel(const KernelArgs p)
 					const unsigned long long o4 = prob * (unsigned long long)(NP / 4) + g;
 					reinterpret_cast<float4 *>(p.ps.zs)[o4] = make_float4(z[0], z[1], z[2], z[3]);
 					reinterpret_cast<float4 *>(p.ps.us)[o4] = make_float4(u[0], u[1], u[2], u[3]);
-					if (!LIST) { // a listed problem's inverse is in place already
-						float4 *Rp = reinterpret_cast<float4 *>(
-							p.ps.Rs + prob * (unsigned long long)(NP * NP)) + g;
-#pragma unroll
-						for (int j = 0; j < NP; ++j)
-							Rp[j * (NP / 4)] = make_float4(S[0][j].x, S[0][j].y, S[1][j].x, S[1][j].y);
+					// (the inverse is in scratch already: written behind the elimination)
+					// the streaming pass starts from the x-update the pipelined loop has already
+					// computed for the next iteration: no mat-vec in its refill block
+					if (MODE == PASS_FIRST && !PFI) {
+						if (p.ps.xs)
+							reinterpret_cast<float4 *>(p.ps.xs)[o4] =
+								make_float4(xnext[0], xnext[1], xnext[2], xnext[3]);
 					}
 					if (g == 0)
 						p.ps.its[prob] = int(done0 + it);
 				}
-				unsigned slot = 0;
+				// (two lists when the streaming pass follows: expected stragglers / the others;
+				// the group's first lane decides, as for the stop test)
+				unsigned em2 = 0;
+				if (MODE == PASS_FIRST) {
+					if (p.ps.next_list2)
+						em2 = __ballot_sync(FULL, evict && g == 0 && !slow);
+				}
+				const unsigned em1 = em & ~em2;
+				unsigned slot = 0, slot2 = 0;
 				if (lane == 0) {
-					slot = atomicAdd(p.ps.next_count, unsigned(__popc(em)));
+					if (em1)
+						slot = atomicAdd(p.ps.next_count, unsigned(__popc(em1)));
+					if (em2)
+						slot2 = atomicAdd(p.ps.next_count2, unsigned(__popc(em2)));
 					if (p.ps.stats)
 						atomicAdd(p.ps.stats + (LIST ? 2 : 0), (unsigned long long)__popc(em));
 				}
 				slot = __shfl_sync(FULL, slot, 0);
-				if (evict && g == 0)
-					p.ps.next_list[slot + __popc(em & ((1u << lane) - 1u))] = unsigned(prob);
+				slot2 = __shfl_sync(FULL, slot2, 0);
+				if (evict && g == 0) {
+					const unsigned below = (1u << lane) - 1u;
+					if ((em2 >> lane) & 1u)
+						p.ps.next_list2[slot2 + __popc(em2 & below)] = unsigned(prob);
+					else
+						p.ps.next_list[slot + __popc(em1 & below)] = unsigned(prob);
+				}
 			}
 		}
 

@@ -30,7 +30,9 @@ namespace qpb {
 //   PASS_FIRST  the whole batch, `window` iterations each, the unfinished ones to next_list
 //   PASS_LIST   the problems of `list`, state from scratch, `window` more iterations each,
 //               the unfinished ones to next_list (null: the last pass runs everything out)
-constexpr int PASS_PLAIN = 0, PASS_FIRST = 1, PASS_LIST = 2;
+//   PASS_STREAM qp_bpq_stream.cuh: the problems of `list`, every one to the end, each lane group
+//               taking its next problem by ticket (stream_ctr) as soon as its current one stops
+constexpr int PASS_PLAIN = 0, PASS_FIRST = 1, PASS_LIST = 2, PASS_STREAM = 3;
 struct PassArgs {
 	unsigned long long *stats;  // null, or counters the kernels add to (qp_batch.cu reads them):
 	                            // [0] problems that outlived the first window (PASS_FIRST: evicted)
@@ -40,6 +42,8 @@ struct PassArgs {
 	                            // [3] sum of iteration counts, [4] sum over warps of (largest
 	                            // iteration count in the warp x problems in the warp) -- [3] / [4]
 	                            // is the fraction of lane-iterations that did work --, [5] problems
+	                            // PASS_STREAM, one add per lane group: [6] sum of the final iteration
+	                            // counts of the problems it finished, [7] how many those were
 	unsigned window;            // PASS_FIRST / PASS_LIST: iterations per problem in this launch
 	const unsigned *list;       // PASS_LIST: problem indices ...
 	const unsigned *list_count; // ... and how many (written by the previous launch)
@@ -48,6 +52,13 @@ struct PassArgs {
 	float *zs, *us;             // [count][n] z and u of an evicted problem
 	int *its;                   // [count]    iterations an evicted problem has done
 	float *Rs;                  // bpq: [count][n][n] its inverse (or eta file)
+	float *xs;                  // bpq, streaming pass next: [count][n] x-update of its next iteration
+	unsigned *stream_ctr;       // PASS_STREAM: tickets handed out so far (zero at launch)
+	// qp_bpq.cuh PASS_FIRST -> PASS_STREAM: a second list.  The first pass appends to next_list the
+	// problems whose residuals had almost stopped shrinking when the window closed (they will run
+	// long) and to next_list2 all the others; the streaming pass hands out `list` before `list2`.
+	unsigned *next_list2, *next_count2; // null: everything goes to next_list
+	const unsigned *list2, *list_count2;
 };
 
 // Kernel arguments: one packed batch resident in device memory.

@@ -81,6 +81,10 @@ int launch_tpq_family(const KernelArgs &a, int dev, cudaStream_t st, int mode);
 int launch_bpq_family(const KernelArgs &a, int dev, cudaStream_t st, int mode);
 int launch_gpq_family(const KernelArgs &a, int dev, cudaStream_t st);
 int launch_cpq_family(const KernelArgs &a, int dev, cudaStream_t st);
+// PASS_STREAM (qp_bpq_stream.cuh): can the second launch of a pass schedule be the streaming
+// kernel for this batch (full inverse, i.e. no product form), and its launcher
+bool bpq_stream_eligible(const KernelArgs &a);
+int launch_bpq_stream_family(const KernelArgs &a, int dev, cudaStream_t st);
 // which families have the pass modes (KernelArgs::ps)
 bool family_has_passes(int family, int n);
 

@@ -97,6 +97,7 @@ def main():
                          "iteration counts; prints SINGLE and PASSES schedules and an iteration histogram")
     ap.add_argument("--schedule", default="auto", choices=["auto", "single", "passes"])
     ap.add_argument("--kernel", default="auto", choices=["auto", "tpq", "gpq", "bpq", "cpq"])
+    ap.add_argument("--max-iter", type=int, default=10000, help="iteration cap (qp_options.max_iter)")
     ap.add_argument("--counts", default="", help="override batch sizes, e.g. 24:262144,32:262144")
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
@@ -106,7 +107,7 @@ def main():
     hbm_peak = float(json.load(open(peaks))["hbm_gbs"]) if os.path.exists(peaks) else 6650.0
     kern = {"auto": qp.KERNEL_AUTO, "tpq": qp.KERNEL_TPQ, "gpq": qp.KERNEL_GPQ, "bpq": qp.KERNEL_BPQ, "cpq": qp.KERNEL_CPQ}[args.kernel]
     sched = {"auto": qp.SCHEDULE_AUTO, "single": qp.SCHEDULE_SINGLE, "passes": qp.SCHEDULE_PASSES}[args.schedule]
-    opts = qp.Options(kernel=kern, schedule=sched)
+    opts = qp.Options(kernel=kern, schedule=sched, max_iter=args.max_iter)
     if args.refdist:
         return refdist(args, dev, kern, fp32_peak)
     counts = dict(SHAPES)
