@@ -156,25 +156,29 @@ int pick_kernel(const KernelArgs &a, uint32_t forced)
 // static too, kmalloc/kmalloc.c:37-42); solves that use it are chained by an event, so
 // callers on different streams of one device never share it in time.
 //
-// QP_SCHEDULE_AUTO follows what the device has seen: a plain launch counts the problems
-// that needed more than the first window; the counters are copied to pinned host memory
-// on a side stream behind every such solve (nobody waits for it), and the next solve looks
-// at the latest copy -- passes when more than 1 in 128 problems of the solves since the
-// last look outlived the window, a plain launch otherwise.  The schedule never changes a
-// result (bit for bit, tests/test_passes_gpu.py), only where the time goes.
+// QP_SCHEDULE_AUTO follows what the device has seen, PER DIMENSION n (a host that solves
+// well-conditioned n = 16 problems and heavy-tailed n = 40 ones on one GPU gets a schedule for
+// each): the kernels add to the counters of their n; behind every such solve the row is
+// copied to pinned host memory on a side stream (nobody waits for it), alternately into two
+// buffers, and the next solve of that n looks at the DIFFERENCE of the two -- what the most
+// recent solves did, not what the device has done since the last decision (a burst of 20
+// MPC solves would otherwise outvote the well-conditioned batch that follows it for as long
+// again).  The schedule never changes a result (bit for bit, tests/test_passes_gpu.py), only
+// where the time goes.
 constexpr int MAX_PASSES = 16;
-constexpr int STAT_WORDS = 8; // PassArgs::stats, [6..7] spare
+constexpr int STAT_WORDS = 8; // PassArgs::stats
+constexpr int STAT_ROWS = QP_MAX_DIM_BOX + 1; // one row of counters per n
 struct DevArena {
 	std::mutex mu;
 	char *base = nullptr;
 	size_t bytes = 0;
 	cudaEvent_t last = nullptr;  // recorded behind the latest solve that used the scratch
-	unsigned long long *stat_dev = nullptr;  // STAT_WORDS counters in device memory
-	unsigned long long *stat_host = nullptr; // pinned: their latest copy
+	unsigned long long *stat_dev = nullptr;  // [STAT_ROWS][STAT_WORDS] counters in device memory
+	unsigned long long *stat_host = nullptr; // pinned [2][STAT_ROWS][STAT_WORDS]: the two latest copies
 	cudaStream_t side = nullptr;             // carries the copies
 	cudaEvent_t ev_side = nullptr;
-	unsigned long long look[STAT_WORDS] = {}; // the counters at AUTO's last look
-	bool heavy = false;                      // AUTO's current belief about this device's work
+	unsigned char flip[STAT_ROWS] = {};      // which buffer the next copy of a row goes to
+	bool heavy[STAT_ROWS] = {};              // AUTO's current belief about the work of this n
 	std::chrono::steady_clock::time_point last_copy; // when the counters were last sent for
 	bool copied_once = false;
 };
@@ -212,10 +216,10 @@ int arena_stats_init(DevArena &ar)
 {
 	if (ar.stat_dev)
 		return QP_OK;
-	QP_CUDA(cudaMalloc(&ar.stat_dev, STAT_WORDS * 8));
-	QP_CUDA(cudaMemset(ar.stat_dev, 0, STAT_WORDS * 8));
-	QP_CUDA(cudaHostAlloc(&ar.stat_host, STAT_WORDS * 8, cudaHostAllocDefault));
-	std::memset(ar.stat_host, 0, STAT_WORDS * 8);
+	QP_CUDA(cudaMalloc(&ar.stat_dev, STAT_ROWS * STAT_WORDS * 8));
+	QP_CUDA(cudaMemset(ar.stat_dev, 0, STAT_ROWS * STAT_WORDS * 8));
+	QP_CUDA(cudaHostAlloc(&ar.stat_host, 2 * STAT_ROWS * STAT_WORDS * 8, cudaHostAllocDefault));
+	std::memset(ar.stat_host, 0, 2 * STAT_ROWS * STAT_WORDS * 8);
 	QP_CUDA(cudaStreamCreateWithFlags(&ar.side, cudaStreamNonBlocking));
 	QP_CUDA(cudaEventCreateWithFlags(&ar.ev_side, cudaEventDisableTiming));
 	QP_CUDA(cudaEventCreateWithFlags(&ar.last, cudaEventDisableTiming));
@@ -262,46 +266,56 @@ int launch_solver(KernelArgs a, int dev, cudaStream_t st, uint32_t forced, uint3
 	std::lock_guard<std::mutex> lk(ar.mu);
 	if (int rc = arena_stats_init(ar))
 		return rc;
+	const int row = a.n; // 1 ... QP_MAX_DIM_BOX
 	if (look) {
-		unsigned long long now[STAT_WORDS], d[STAT_WORDS];
+		// the two latest copies of this n's counters; they only grow, so the larger one is newer
+		const unsigned long long *h0 = ar.stat_host + size_t(row) * STAT_WORDS;
+		const unsigned long long *h1 = h0 + size_t(STAT_ROWS) * STAT_WORDS;
+		unsigned long long b0[STAT_WORDS], b1[STAT_WORDS], d[STAT_WORDS];
 		for (int k = 0; k < STAT_WORDS; ++k)
-			now[k] = ar.stat_host[k], d[k] = now[k] - ar.look[k];
-		if (!ar.heavy && d[5] > 0) {
-			// single launches since the last look: passes pay when the warps mostly waited for
-			// their slowest problem (less than half of the lane-iterations did work) AND the
-			// iterations are what the time goes to (a pass repeats the factorisation, or moves
-			// the inverse through HBM): mean iteration count >= 16 (thread per QP) / 64 (lane
-			// groups).  Measured both ways on the reference's distribution and the condensed
-			// MPC set, profiles/README.md "Passes".
+			b0[k] = h0[k], b1[k] = h1[k];
+		const bool newer1 = b1[1] + b1[5] >= b0[1] + b0[5];
+		for (int k = 0; k < STAT_WORDS; ++k)
+			d[k] = newer1 ? b1[k] - b0[k] : b0[k] - b1[k];
+		bool &heavy = ar.heavy[row];
+		if (!heavy && d[5] > 0) {
+			// single launches lately: passes pay when the warps mostly waited for their slowest
+			// problem (less than half of the lane-iterations did work) AND the iterations are
+			// what the time goes to (a pass repeats the factorisation, or moves the inverse
+			// through HBM): mean iteration count >= 16 (thread per QP) / 64 (lane groups).
+			// Measured both ways on the reference's distribution and the condensed MPC set,
+			// profiles/README.md "Passes".
 			const double mean = double(d[3]) / double(d[5]);
 			const double worked = d[4] ? double(d[3]) / double(d[4]) : 1.0;
 			// (the streaming pass has no list passes to pay for and no group waits in it: it is
 			// ahead as soon as a quarter of the lane-iterations wait and the iterations, not the
 			// elimination, are where the time goes -- MPC set: 0.58 worked, mean 36)
-			ar.heavy = stream ? (worked < 0.75 && mean >= 24.0)
-					  : (worked < 0.5 && mean >= (fam == QP_KERNEL_TPQ ? 16.0 : 64.0));
-			std::memcpy(ar.look, now, sizeof(now));
-		} else if (ar.heavy && d[1] > 0) {
-			// passes since the last look: back to single launches when fewer than 1 problem in
-			// 128 outlived the first window -- or, with the streaming pass (whose first window
-			// nearly everything outlives), when the streamed problems needed fewer than 20
-			// iterations on average
-			ar.heavy = stream ? (d[7] == 0 || d[6] >= 20ull * d[7]) : d[0] * 128ull > d[1];
-			std::memcpy(ar.look, now, sizeof(now));
+			heavy = stream ? (worked < 0.75 && mean >= 24.0)
+				       : (worked < 0.5 && mean >= (fam == QP_KERNEL_TPQ ? 16.0 : 64.0));
+		} else if (heavy && d[1] > 0) {
+			// passes lately: back to single launches when fewer than 1 problem in 128 outlived
+			// the first window -- or, with the streaming pass (whose first window nearly
+			// everything outlives), when the streamed problems needed fewer than 20 iterations
+			// on average
+			heavy = stream ? (d[7] == 0 || d[6] >= 20ull * d[7]) : d[0] * 128ull > d[1];
 		}
-		passes = ar.heavy;
+		passes = heavy;
 	}
-	a.ps.stats = ar.stat_dev;
+	a.ps.stats = ar.stat_dev + size_t(row) * STAT_WORDS;
 	auto copy_stats = [&]() -> int {
 		// an event between back-to-back launches costs a microsecond or two of the stream's
-		// time: behind short solves that follow each other closely, copy every 200 us only
+		// time: behind SHORT solves that are enqueued closely after each other, copy every
+		// 200 us (of the host's time) only; a solve of a millisecond always gets its copy
 		const auto now = std::chrono::steady_clock::now();
-		if (ar.copied_once && now - ar.last_copy < std::chrono::microseconds(200))
+		const bool small = a.count * (unsigned long long)(a.n * a.n) < (1ull << 24);
+		if (small && ar.copied_once && now - ar.last_copy < std::chrono::microseconds(200))
 			return QP_OK;
 		ar.last_copy = now, ar.copied_once = true;
 		QP_CUDA(cudaEventRecord(ar.ev_side, st));
 		QP_CUDA(cudaStreamWaitEvent(ar.side, ar.ev_side, 0));
-		QP_CUDA(cudaMemcpyAsync(ar.stat_host, ar.stat_dev, STAT_WORDS * 8, cudaMemcpyDeviceToHost, ar.side));
+		unsigned long long *dst = ar.stat_host + (size_t(ar.flip[row]) * STAT_ROWS + row) * STAT_WORDS;
+		ar.flip[row] ^= 1;
+		QP_CUDA(cudaMemcpyAsync(dst, a.ps.stats, STAT_WORDS * 8, cudaMemcpyDeviceToHost, ar.side));
 		return QP_OK;
 	};
 	if (!passes) {
@@ -388,7 +402,7 @@ extern "C" int qp_schedule_stats(int device, unsigned long long stats[6])
 	const int dev = resolve_device(device);
 	if (dev < 0 || !stats)
 		return QP_ERR_INVALID;
-	unsigned long long v[STAT_WORDS] = {};
+	std::vector<unsigned long long> v(size_t(STAT_ROWS) * STAT_WORDS, 0ull);
 	DevArena &ar = g_arena[dev];
 	std::lock_guard<std::mutex> lk(ar.mu);
 	if (ar.stat_dev) {
@@ -396,10 +410,13 @@ extern "C" int qp_schedule_stats(int device, unsigned long long stats[6])
 		if (g.enter(dev) != QP_OK)
 			return QP_ERR_NO_DEVICE;
 		QP_CUDA(cudaDeviceSynchronize());
-		QP_CUDA(cudaMemcpy(v, ar.stat_dev, sizeof(v), cudaMemcpyDeviceToHost));
+		QP_CUDA(cudaMemcpy(v.data(), ar.stat_dev, v.size() * 8, cudaMemcpyDeviceToHost));
 	}
-	for (int k = 0; k < 6; ++k)
-		stats[k] = v[k];
+	for (int k = 0; k < 6; ++k) { // (the counters are kept per dimension: their sums)
+		stats[k] = 0;
+		for (int r = 0; r < STAT_ROWS; ++r)
+			stats[k] += v[size_t(r) * STAT_WORDS + k];
+	}
 	return QP_OK;
 }
 
