@@ -941,6 +941,76 @@ int run_shard_body(qp_workspace *ws, DeviceCtx &ctx, const qp_batch &pb, const q
 	const bool upper_in = pb.p_layout == QP_P_UPPER; // the caller's P is packed already
 	const int pk = tpq_packed_stride(int(n));
 	const size_t p_per = upper_in ? size_t(pk) : size_t(n) * n; // floats of P per problem
+
+	// ---- a handful of problems: latency is what counts (the drop-in replaces a CPU call of
+	// ~20 us, test/test.c:89-106).  One staging copy in, one launch, one copy out, one wait:
+	// every array of the call is laid out back to back (16-byte aligned pieces) in the slot's
+	// pinned buffer and in its device buffer, whatever memory the caller's pointers are in (no
+	// cudaPointerGetAttributes on twelve pointers, no events, no worker threads).
+	const size_t small_c = hi - lo;
+	// (the pieces are rounded up to 16 bytes: a count that is a multiple of four, as a full slot
+	// is, needs no rounding, any other count has two problems' worth of room to spare)
+	if (small_c > 0 && (small_c + 2 <= cap || (small_c == cap && small_c % 4 == 0)) && n >= 3 &&
+	    small_c * (in_floats(n) + out_floats(n)) * 4 <= (256u << 10)) {
+		Slot &s = ctx.slot[0];
+		if (s.busy) { // (a failed earlier call leaves nothing in flight, see quiesce)
+			QP_CUDA(cudaEventSynchronize(s.done));
+			s.busy = false;
+		}
+		if (!s.hin)
+			QP_CUDA(cudaMallocHost(&s.hin, cap * in_floats(n) * 4));
+		if (!s.hout)
+			QP_CUDA(cudaMallocHost(&s.hout, cap * out_floats(n) * 4));
+		const size_t c = small_c;
+		auto up4 = [](size_t v) { return (v + 3) / 4 * 4; };
+		struct Piece {
+			const float *src;
+			size_t per;
+			size_t off;
+		} in[] = { { pb.P, p_per, 0 }, { pb.q, n, 0 },  { pb.lb, n, 0 }, { pb.ub, n, 0 },
+			   { pb.z0, n, 0 },    { pb.u0, n, 0 }, { pb.rho, 1, 0 } };
+		size_t tot = 0;
+		for (Piece &pc : in)
+			if (pc.src) {
+				pc.off = tot;
+				std::memcpy(s.hin + tot, pc.src + lo * pc.per, c * pc.per * 4);
+				tot += up4(c * pc.per);
+			}
+		cudaStream_t st = s.stream;
+		float *din = s.dP; // the slot's one device allocation, inputs first
+		QP_CUDA(cudaMemcpyAsync(din, s.hin, tot * 4, cudaMemcpyHostToDevice, st));
+		g_h2d_bytes.fetch_add(tot * 4);
+		qp_batch dpb = pb;
+		dpb.mem = QP_MEM_DEVICE;
+		dpb.count = c;
+		dpb.P = din + in[0].off, dpb.q = din + in[1].off;
+		dpb.lb = pb.lb ? din + in[2].off : nullptr, dpb.ub = pb.ub ? din + in[3].off : nullptr;
+		dpb.z0 = pb.z0 ? din + in[4].off : nullptr, dpb.u0 = pb.u0 ? din + in[5].off : nullptr;
+		dpb.rho = pb.rho ? din + in[6].off : nullptr;
+		float *dout = din + up4(tot);
+		const size_t ov = up4(c * n), oi = up4(c);
+		qp_batch_solution dsol;
+		dsol.x = sol.x ? dout : nullptr, dsol.z = sol.z ? dout + ov : nullptr;
+		dsol.lambda = sol.lambda ? dout + 2 * ov : nullptr;
+		dsol.status = sol.status ? reinterpret_cast<int32_t *>(dout + 3 * ov) : nullptr;
+		dsol.iters = sol.iters ? reinterpret_cast<int32_t *>(dout + 3 * ov + oi) : nullptr;
+		if (int rc = launch_solver(make_args(dpb, dsol, opt), ctx.dev, st, opt.kernel, opt.schedule))
+			return rc;
+		QP_CUDA(cudaMemcpyAsync(s.hout, dout, (3 * ov + 2 * oi) * 4, cudaMemcpyDeviceToHost, st));
+		QP_CUDA(cudaStreamSynchronize(st));
+		if (sol.x)
+			std::memcpy(sol.x + lo * n, s.hout, c * n * 4);
+		if (sol.z)
+			std::memcpy(sol.z + lo * n, s.hout + ov, c * n * 4);
+		if (sol.lambda)
+			std::memcpy(sol.lambda + lo * n, s.hout + 2 * ov, c * n * 4);
+		if (sol.status)
+			std::memcpy(sol.status + lo, s.hout + 3 * ov, c * 4);
+		if (sol.iters)
+			std::memcpy(sol.iters + lo, s.hout + 3 * ov + oi, c * 4);
+		return QP_OK;
+	}
+
 	const bool pin_in = is_pinned(pb.P) && is_pinned(pb.q) && is_pinned(pb.lb) &&
 			    is_pinned(pb.ub) && is_pinned(pb.z0) && is_pinned(pb.u0) &&
 			    is_pinned(pb.rho);

@@ -572,6 +572,40 @@ def test_host_path_equals_device_path(qp, n):
     assert np.array_equal(hw["x"], dw["x"]) and np.array_equal(hw["iters"], dw["iters"])
 
 
+@pytest.mark.parametrize("n", [3, 4, 5, 7, 16, 24, 40, 64, 96])
+def test_small_host_batches_take_the_one_copy_path(qp, n):
+    """A handful of problems in host memory (what the drop-in admm_b200() hands over: one) go
+    through one staging copy in, one launch, one copy out.  Same bits as the device path for
+    every count around the piece-alignment and slot-capacity edges, with every optional array,
+    pageable and pinned, and with outputs left out."""
+    rng = np.random.default_rng(n)
+    for count in (1, 2, 3, 5, 30, 31, 32, 33, 100):
+        P, q, lb, ub = problems.wellcond(count, n, seed=900 + n + count, beta=0.5)
+        lb = (lb - rng.random((count, n))).astype(np.float32)
+        z0 = (0.1 * rng.standard_normal((count, n))).astype(np.float32)
+        u0 = (0.1 * rng.standard_normal((count, n))).astype(np.float32)
+        rho = (0.5 + rng.random(count)).astype(np.float32)
+        for kw in (dict(), dict(z0=z0, u0=u0), dict(rho=rho), dict(z0=z0, u0=u0, rho=rho)):
+            dkw = {k: (torch.from_numpy(v).cuda() if k == "rho" else v) for k, v in kw.items()}
+            d = solve_dev(qp, P, q, lb, ub, **dkw)
+            h = qp.solve_batch(P, q, lb, ub, **kw)
+            for k in ("x", "z", "lam", "iters", "status"):
+                assert np.array_equal(h[k], d[k]), (n, count, sorted(kw), k)
+        d = solve_dev(qp, P, q, lb, ub)
+        hs = qp.solve_batch(P, q, -0.5, 0.5)                       # scalar box
+        tP, tq = dev(P, q)
+        ds = {k: v.cpu().numpy() for k, v in qp.solve_batch(tP, tq, -0.5, 0.5).items()}
+        assert np.array_equal(hs["x"], ds["x"]) and np.array_equal(hs["iters"], ds["iters"])
+        hx = qp.solve_batch(P, q, lb, ub, want=("x", "iters"))     # z, lambda, status left out
+        assert sorted(hx) == ["iters", "x"] and np.array_equal(hx["x"], d["x"])
+        tP, tq = torch.from_numpy(P).pin_memory(), torch.from_numpy(q).pin_memory()
+        hp = qp.solve_batch(tP, tq, lb, ub)                        # pinned in, pageable bounds
+        assert np.array_equal(np.asarray(hp["x"]), d["x"])
+    if n in (8, 12, 16):
+        hu = qp.solve_batch(qp.pack_upper(P), q, lb, ub, p_layout=qp.P_UPPER)
+        assert np.array_equal(hu["iters"], d["iters"])
+
+
 # ---- per-problem rho (qp_batch.rho, SURVEY.md section 8(f) rank 1) -----------------------------
 
 @pytest.mark.parametrize("n", [4, 12, 16, 20, 40, 64])
