@@ -367,6 +367,7 @@ def parse():
     ap.add_argument("--no-shapes", action="store_true", help="skip the other BASELINE shapes (N = 1)")
     ap.add_argument("--shape-steps", type=int, default=10)
     ap.add_argument("--sustained-s", type=float, default=2.5, help="0 = skip the sustained run")
+    ap.add_argument("--no-shared", action="store_true", help="skip the shared-P leg beside the line")
     ap.add_argument("--no-device-mask", action="store_true", help="skip e2e_device_mask (N > 1)")
     ap.add_argument("--no-cpu", action="store_true")
     return ap.parse_args()
@@ -630,6 +631,41 @@ def run_ours(args, rank, local_rank, world):
                "pageable": pageable, "caller_packed_upper_layout": upper, "x_status_iters_only": xonly}
         del hP, hq, hout
 
+    # ---- beside the metric: one model, many right-hand sides (qp_batch.p_share) -----------------
+    # The same 2^20 problems' q with ONE matrix per 1024 problems: what an MPC host does with the
+    # reference (the same qf->p, a new qf->q per state).  Not BASELINE.json's workload -- every
+    # problem there has its own P -- so it is reported beside the line, never as `value` or `e2e`.
+    shared = None
+    if world == 1 and not args.no_e2e and not args.no_shared:
+        share = 1024
+        Ps = P[::share].contiguous()
+        so = qp.solve_batch(Ps, q, -args.beta, args.beta, p_share=share)
+        sms_ = time_steps(torch, lambda i: qp.solve_batch(Ps, q, -args.beta, args.beta, out=so, p_share=share),
+                          min(args.steps, 50))
+        hPs, hq2 = Ps.cpu().pin_memory(), q.cpu().pin_memory()
+        hso = {k: torch.empty((count, n)).pin_memory() for k in ("x", "z", "lam")}
+        hso.update({k: torch.empty(count, dtype=torch.int32).pin_memory() for k in ("status", "iters")})
+        res = {}
+        for tag, want in (("all_outputs", ("x", "z", "lam", "status", "iters")), ("x_status_iters", ("x", "status", "iters"))):
+            o_ = {k: hso[k] for k in want}
+            for _ in range(3):
+                qp.solve_batch(hPs, hq2, -args.beta, args.beta, out=o_, want=want, p_share=share,
+                               options=qp.Options(device=local_rank))
+            ts0 = time.perf_counter()
+            for _ in range(10):
+                qp.solve_batch(hPs, hq2, -args.beta, args.beta, out=o_, want=want, p_share=share,
+                               options=qp.Options(device=local_rank))
+            torch.cuda.synchronize()
+            sdt = (time.perf_counter() - ts0) / 10
+            res[tag] = {"value": count / sdt, "unit": UNIT, "ms_per_step": sdt * 1e3,
+                        "h2d_bytes_per_step": (n * n * (count // share) + n * count) * 4,
+                        "d2h_bytes_per_step": sum((n if k in ("x", "z", "lam") else 1) for k in want) * 4 * count}
+        shared = {"workload": f"{count} problems, n={n}: the q of the timed batch, one P per {share} problems",
+                  "p_share": share, "device_resident": {"value": count / (sms_ * 1e-3), "unit": UNIT, "ms_per_step": sms_},
+                  "e2e": res, "mean_iters": float(so["iters"].float().mean()),
+                  "not_converged": int((so["status"] != 0).sum())}
+        del Ps, so, hPs, hq2, hso
+
     # ---- the library's own multi-GPU entry: ONE qp_solve_batch call over all N GPUs ----------
     e2e_mask = None
     if world > 1 and not args.no_e2e and not args.no_device_mask:
@@ -763,6 +799,8 @@ def run_ours(args, rank, local_rank, world):
             "sustained": sustained, "shapes": shapes}
     if e2e_mask is not None:
         line["e2e_device_mask"] = e2e_mask
+    if shared is not None:
+        line["shared_p"] = shared
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

@@ -40,7 +40,7 @@ class qp_batch(C.Structure):
                 ("P", C.c_void_p), ("q", C.c_void_p), ("lb", C.c_void_p), ("ub", C.c_void_p),
                 ("lb_scalar", C.c_float), ("ub_scalar", C.c_float),
                 ("z0", C.c_void_p), ("u0", C.c_void_p), ("rho", C.c_void_p),
-                ("p_layout", C.c_uint32), ("reserved", C.c_uint32)]
+                ("p_layout", C.c_uint32), ("p_share", C.c_uint32)]
 
 
 class qp_batch_solution(C.Structure):
@@ -230,7 +230,8 @@ def _as_f32(a, shape, what):
 
 def solve_batch(P, q, lb=None, ub=None, z0=None, u0=None, options: Optional[Options] = None,
                 out: Optional[dict] = None, workspace: Optional["Workspace"] = None,
-                want=("x", "z", "lam", "status", "iters"), rho=None, p_layout: int = P_DENSE) -> dict:
+                want=("x", "z", "lam", "status", "iters"), rho=None, p_layout: int = P_DENSE,
+                p_share: int = 1) -> dict:
     """Solve ``count`` box QPs: the batched replacement of a loop of the
     reference's ``admm(x0, iterations, qf)`` (qp_solvers.c:255-319).
 
@@ -240,6 +241,8 @@ def solve_batch(P, q, lb=None, ub=None, z0=None, u0=None, options: Optional[Opti
     an array [count] of per-problem penalties.
     p_layout=P_UPPER: P is [count, packed_stride(n)], the row-major upper triangle of every
     matrix (``pack_upper``), n = 8, 12, 16.
+    p_share=k > 1: problems i*k .. i*k+k-1 share P[i] (``qp_batch.p_share``: one model, many
+    right-hand sides); P then holds ceil(count / k) matrices and count is q's.
     CUDA torch tensors take the device path (kernel launched on the current
     torch stream, no synchronisation, outputs are torch tensors on that
     device); numpy arrays / CPU tensors take the host path (copies, sharded
@@ -247,13 +250,15 @@ def solve_batch(P, q, lb=None, ub=None, z0=None, u0=None, options: Optional[Opti
     """
     lib = load_library()
     opt = options or Options()
-    count = int(P.shape[0])
+    p_share = max(1, int(p_share))
+    count = int(q.shape[0]) if p_share > 1 else int(P.shape[0])
+    nmat = (count + p_share - 1) // p_share
     if p_layout == P_UPPER:
         n = int(q.shape[1])
-        pshape = (count, packed_stride(n))
+        pshape = (nmat, packed_stride(n))
     else:
         n = int(P.shape[1])
-        pshape = (count, n, n)
+        pshape = (nmat, n, n)
     if tuple(P.shape) != pshape:
         raise ValueError(f"P must be {pshape}")
     hP, aP, dev = _as_f32(P, pshape, "P")
@@ -264,6 +269,7 @@ def solve_batch(P, q, lb=None, ub=None, z0=None, u0=None, options: Optional[Opti
     pb = qp_batch()
     pb.n, pb.count = n, count
     pb.p_layout = int(p_layout)
+    pb.p_share = p_share
     pb.mem = MEM_DEVICE if dev else MEM_HOST
     pb.P, pb.q = aP, aq
     pb.lb_scalar, pb.ub_scalar = -1e12, 1e12

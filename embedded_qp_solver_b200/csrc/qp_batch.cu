@@ -469,6 +469,8 @@ KernelArgs make_args(const qp_batch &pb, const qp_batch_solution &sol, const qp_
 	a.reltol = o.reltol;
 	a.max_iter = o.max_iter;
 	a.p_packed = pb.p_layout == QP_P_UPPER ? 1 : 0;
+	a.p_share = pb.p_share > 1u ? pb.p_share : 1u;
+	a.p_share_off = 0;
 	return a;
 }
 
@@ -941,6 +943,7 @@ int run_shard_body(qp_workspace *ws, DeviceCtx &ctx, const qp_batch &pb, const q
 	const bool upper_in = pb.p_layout == QP_P_UPPER; // the caller's P is packed already
 	const int pk = tpq_packed_stride(int(n));
 	const size_t p_per = upper_in ? size_t(pk) : size_t(n) * n; // floats of P per problem
+	const size_t share = pb.p_share > 1u ? pb.p_share : 1u;     // problems per matrix
 
 	// ---- a handful of problems: latency is what counts (the drop-in replaces a CPU call of
 	// ~20 us, test/test.c:89-106).  One staging copy in, one launch, one copy out, one wait:
@@ -969,12 +972,16 @@ int run_shard_body(qp_workspace *ws, DeviceCtx &ctx, const qp_batch &pb, const q
 			size_t off;
 		} in[] = { { pb.P, p_per, 0 }, { pb.q, n, 0 },  { pb.lb, n, 0 }, { pb.ub, n, 0 },
 			   { pb.z0, n, 0 },    { pb.u0, n, 0 }, { pb.rho, 1, 0 } };
+		// (shared matrices, qp_batch.p_share: the groups these problems belong to)
+		const size_t g_first = lo / share, g_count = (hi - 1) / share - g_first + 1;
 		size_t tot = 0;
 		for (Piece &pc : in)
 			if (pc.src) {
+				const bool isP = pc.src == pb.P;
+				const size_t from = isP ? g_first : lo, cnt_ = isP ? g_count : c;
 				pc.off = tot;
-				std::memcpy(s.hin + tot, pc.src + lo * pc.per, c * pc.per * 4);
-				tot += up4(c * pc.per);
+				std::memcpy(s.hin + tot, pc.src + from * pc.per, cnt_ * pc.per * 4);
+				tot += up4(cnt_ * pc.per);
 			}
 		cudaStream_t st = s.stream;
 		float *din = s.dP; // the slot's one device allocation, inputs first
@@ -994,7 +1001,9 @@ int run_shard_body(qp_workspace *ws, DeviceCtx &ctx, const qp_batch &pb, const q
 		dsol.lambda = sol.lambda ? dout + 2 * ov : nullptr;
 		dsol.status = sol.status ? reinterpret_cast<int32_t *>(dout + 3 * ov) : nullptr;
 		dsol.iters = sol.iters ? reinterpret_cast<int32_t *>(dout + 3 * ov + oi) : nullptr;
-		if (int rc = launch_solver(make_args(dpb, dsol, opt), ctx.dev, st, opt.kernel, opt.schedule))
+		KernelArgs ka = make_args(dpb, dsol, opt);
+		ka.p_share_off = lo - g_first * share;
+		if (int rc = launch_solver(ka, ctx.dev, st, opt.kernel, opt.schedule))
 			return rc;
 		QP_CUDA(cudaMemcpyAsync(s.hout, dout, (3 * ov + 2 * oi) * 4, cudaMemcpyDeviceToHost, st));
 		QP_CUDA(cudaStreamSynchronize(st));
@@ -1048,7 +1057,7 @@ int run_shard_body(qp_workspace *ws, DeviceCtx &ctx, const qp_batch &pb, const q
 
 	// pack the upper triangles of P on the host when the thread-per-QP kernel will run
 	const unsigned tpg = host_threads_per_gpu(unsigned(ws->devs.size()));
-	const bool pack0 = !upper_in && !ctx.pack_off && qp_host_path_packs(n) && tpg >= 12 &&
+	const bool pack0 = !upper_in && share == 1 && !ctx.pack_off && qp_host_path_packs(n) && tpg >= 12 &&
 			  (opt.kernel == QP_KERNEL_AUTO || opt.kernel == QP_KERNEL_TPQ) &&
 			  ((pb.lb == nullptr) == (pb.ub == nullptr)) && ((pb.z0 == nullptr) == (pb.u0 == nullptr));
 	if (pack0 && !ctx.pool)
@@ -1181,18 +1190,21 @@ int run_shard_body(qp_workspace *ws, DeviceCtx &ctx, const qp_batch &pb, const q
 		cudaStream_t st = s.stream;
 
 		// ---- inputs ----
+		// (with shared matrices, qp_batch.p_share, P is copied per group: from / cnt)
+		const size_t g_first = first / share, g_count = (first + c - 1) / share - g_first + 1;
 		struct In {
 			const float *src;
 			float *dst;
-			size_t per;
-		} ins[] = { { pb.P, s.dP, p_per },   { pb.q, s.dq, n },   { pb.lb, s.dlb, n },
-			    { pb.ub, s.dub, n },     { pb.z0, s.dz0, n }, { pb.u0, s.du0, n },
-			    { pb.rho, s.drho, 1 } };
+			size_t per, from, cnt;
+		} ins[] = { { pb.P, s.dP, p_per, g_first, g_count }, { pb.q, s.dq, n, first, c },
+			    { pb.lb, s.dlb, n, first, c },           { pb.ub, s.dub, n, first, c },
+			    { pb.z0, s.dz0, n, first, c },           { pb.u0, s.du0, n, first, c },
+			    { pb.rho, s.drho, 1, first, c } };
 		{
 			size_t wire = pack ? c * size_t(pk) * 4 : 0;
 			for (const In &i : ins)
 				if (i.src && !(pack && i.src == pb.P))
-					wire += c * i.per * 4;
+					wire += i.cnt * i.per * 4;
 			g_h2d_bytes.fetch_add(wire);
 		}
 		if (pack) {
@@ -1206,7 +1218,7 @@ int run_shard_body(qp_workspace *ws, DeviceCtx &ctx, const qp_batch &pb, const q
 		if (pin_in) {
 			for (const In &i : ins)
 				if (i.src && !(pack && i.src == pb.P))
-					QP_CUDA(cudaMemcpyAsync(i.dst, i.src + first * i.per, c * i.per * 4,
+					QP_CUDA(cudaMemcpyAsync(i.dst, i.src + i.from * i.per, i.cnt * i.per * 4,
 								cudaMemcpyHostToDevice, st));
 		} else {
 			if (!s.hin)
@@ -1214,8 +1226,8 @@ int run_shard_body(qp_workspace *ws, DeviceCtx &ctx, const qp_batch &pb, const q
 			size_t off = 0;
 			for (const In &i : ins) {
 				if (i.src && !(pack && i.src == pb.P)) {
-					std::memcpy(s.hin + off, i.src + first * i.per, c * i.per * 4);
-					QP_CUDA(cudaMemcpyAsync(i.dst, s.hin + off, c * i.per * 4,
+					std::memcpy(s.hin + off, i.src + i.from * i.per, i.cnt * i.per * 4);
+					QP_CUDA(cudaMemcpyAsync(i.dst, s.hin + off, i.cnt * i.per * 4,
 								cudaMemcpyHostToDevice, st));
 				}
 				off += cap * (i.src == pb.P ? size_t(n) * n : i.per);
@@ -1236,8 +1248,9 @@ int run_shard_body(qp_workspace *ws, DeviceCtx &ctx, const qp_batch &pb, const q
 		dsol.lambda = sol.lambda ? s.dlam : nullptr;
 		dsol.status = sol.status ? s.dstatus : nullptr;
 		dsol.iters = sol.iters ? s.diters : nullptr;
-		rc = launch_solver(make_args(dpb, dsol, opt), ctx.dev, st,
-				   pack ? uint32_t(QP_KERNEL_TPQ) : opt.kernel, opt.schedule);
+		KernelArgs ka = make_args(dpb, dsol, opt);
+		ka.p_share_off = first - g_first * share;
+		rc = launch_solver(ka, ctx.dev, st, pack ? uint32_t(QP_KERNEL_TPQ) : opt.kernel, opt.schedule);
 		if (rc != QP_OK)
 			return rc;
 
@@ -1526,6 +1539,8 @@ extern "C" int qp_eval_batch(const qp_batch *pb, const float *x, float r, float 
 {
 	if (!pb || !x || !f || !pb->P || !pb->q || pb->n == 0)
 		return QP_ERR_INVALID;
+	if (pb->p_share > 1u) // shared matrices: qp_solve_batch() only
+		return QP_ERR_UNSUPPORTED;
 	if (pb->count == 0)
 		return QP_OK;
 	qp_options opt;
@@ -1579,6 +1594,8 @@ static int descent_batch(int gradient, const qp_batch *pb, const float *x0, unsi
 		return QP_ERR_UNSUPPORTED;
 	if (pb->mem != QP_MEM_HOST && pb->mem != QP_MEM_DEVICE)
 		return QP_ERR_INVALID;
+	if (pb->p_share > 1u) // shared matrices: qp_solve_batch() only
+		return QP_ERR_UNSUPPORTED;
 	if (pb->count == 0)
 		return QP_OK;
 	if (!pb->P || !pb->q)
@@ -1768,7 +1785,23 @@ extern "C" int qp_admm_qf_batch(const struct qp_ref_quadratic_form *const *qfs, 
 		    ref_rows(qfs[i]->q) * ref_cols(qfs[i]->q) != n)
 			return QP_ERR_INVALID;
 
-	std::vector<float> P(count * n * n), q(count * n), x(count * n);
+	// A host that solves for many right-hand sides with one model hands over the SAME qf->p
+	// in runs of consecutive structs (struct _quadratic_form keeps p and q apart,
+	// qp_solvers/qp.h:8-13): when all runs have the same length k > 1 -- the last one may be
+	// shorter -- each matrix is converted and sent once (qp_batch.p_share = k)
+	size_t share = 1;
+	{
+		size_t run = 1;
+		while (run < count && qfs[run]->p == qfs[0]->p)
+			++run;
+		bool uniform = run > 1 && run <= 0xffffffffull;
+		for (size_t i = 0; uniform && i < count; ++i)
+			uniform = qfs[i]->p == qfs[i / run * run]->p;
+		if (uniform)
+			share = run;
+	}
+	const size_t nP = (count + share - 1) / share;
+	std::vector<float> P(nP * n * n), q(count * n), x(count * n);
 	std::vector<int32_t> st(count), it(count);
 	// gather + binary64 -> binary32, split over the host cores for large batches (the
 	// structs are scattered in the caller's pools, so this cannot be a device-side copy)
@@ -1788,8 +1821,9 @@ extern "C" int qp_admm_qf_batch(const struct qp_ref_quadratic_form *const *qfs, 
 	for_ranges([&](size_t lo, size_t hi) {
 		for (size_t i = lo; i < hi; ++i) {
 			const double *pe = qfs[i]->p->elements, *qe = qfs[i]->q->elements;
-			for (size_t k = 0; k < size_t(n) * n; ++k)
-				P[i * n * n + k] = float(pe[k]);
+			if (i % share == 0)
+				for (size_t k = 0; k < size_t(n) * n; ++k)
+					P[i / share * n * n + k] = float(pe[k]);
 			for (size_t k = 0; k < n; ++k)
 				q[i * n + k] = float(qe[k]);
 		}
@@ -1798,6 +1832,7 @@ extern "C" int qp_admm_qf_batch(const struct qp_ref_quadratic_form *const *qfs, 
 	std::memset(&pb, 0, sizeof(pb));
 	pb.n = n, pb.mem = QP_MEM_HOST, pb.count = count;
 	pb.P = P.data(), pb.q = q.data();
+	pb.p_share = uint32_t(share);
 	pb.lb_scalar = float(lb), pb.ub_scalar = float(ub);
 	qp_batch_solution sol;
 	std::memset(&sol, 0, sizeof(sol));

@@ -159,7 +159,8 @@ qp_bpq_kernel(const KernelArgs p)
 		{
 			// (a listed problem brings its inverse: same layout, written by an earlier launch)
 			const float4 *Pp = reinterpret_cast<const float4 *>(
-				(LIST ? p.ps.Rs : p.P) + (valid ? prob : 0ull) * (unsigned long long)(NP * NP)) + g;
+				(LIST ? p.ps.Rs + (valid ? prob : 0ull) * (unsigned long long)(NP * NP)
+				      : p.P + (valid ? p_index(p, prob) : 0ull) * (unsigned long long)(NP * NP))) + g;
 #pragma unroll
 			for (int j = 0; j < NP; ++j) {
 				float4 v = valid ? __ldg(Pp + j * (NP / 4)) : make_float4(0.f, 0.f, 0.f, 0.f);

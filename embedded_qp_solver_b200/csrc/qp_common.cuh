@@ -76,8 +76,16 @@ struct KernelArgs {
 	float reltol;
 	unsigned max_iter;
 	int p_packed;          // tpq: P holds packed upper triangles, tpq_packed_stride(n) floats each
+	unsigned p_share;      // >= 1: problems (i + p_share_off) / p_share share one P (qp_batch.p_share)
+	unsigned long long p_share_off; // position of problem 0 of this launch inside its group (host chunks)
 	PassArgs ps;           // passes for heavy-tailed iteration counts (see above)
 };
+
+// which matrix of KernelArgs::P problem `prob` of the launch uses
+__device__ __forceinline__ unsigned long long p_index(const KernelArgs &p, unsigned long long prob)
+{
+	return p.p_share > 1u ? (prob + p.p_share_off) / p.p_share : prob;
+}
 
 // floats per problem of the packed upper triangle (row-major, i <= j), padded to 16 bytes
 __host__ __device__ constexpr int tpq_packed_stride(int n)

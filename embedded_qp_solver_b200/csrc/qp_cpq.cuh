@@ -54,7 +54,7 @@ __global__ void __launch_bounds__(CPQ_THREADS, 2) qp_cpq_kernel(const KernelArgs
 
 		// ---- load the tile of P + rho I --------------------------------------------------
 		float A[TT][TT];
-		const float *Pp = p.P + prob * (unsigned long long)n * n;
+		const float *Pp = p.P + p_index(p, prob) * (unsigned long long)n * n;
 #pragma unroll
 		for (int a = 0; a < TT; ++a) {
 			const int i = ty + 16 * a;

@@ -182,7 +182,7 @@ qp_gpq_kernel(const KernelArgs p)
 		// ---- load: the owner of row r takes column r of the symmetric P ------------------
 		// S[s][h] = (row element 2h, row element 2h+1) of row g + T*s
 		float2 S[RPL][NH];
-		const float *Pp = p.P + (valid ? prob : 0ull) * (unsigned long long)n * n;
+		const float *Pp = p.P + (valid ? p_index(p, prob) : 0ull) * (unsigned long long)n * n;
 		if (n == NP) {
 			// no padding: offsets are compile-time, no per-element bounds tests
 #pragma unroll

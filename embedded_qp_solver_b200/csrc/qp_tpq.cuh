@@ -198,17 +198,19 @@ qp_tpq_kernel(const KernelArgs p)
 			mbar_expect_tx(&full_bar[s],
 				       uint32_t(cnt) * ((PACKED_IN ? L::PK : N * N) + L::NVEC_STAGE * N) * 4u);
 		__syncwarp();
+		// (one copy per lane where the slots are padded, and where problems share their
+		// matrices -- qp_batch.p_share: the lanes of a group then copy the same 1 KB out of L2)
 		if (PACKED_IN) {
-			if (L::PKSLOT != L::PK) {
+			if (L::PKSLOT != L::PK || p.p_share > 1u) {
 				if (lane < cnt)
-					bulk_g2s(st + lane * L::PKSLOT, p.P + (first + lane) * L::PK,
+					bulk_g2s(st + lane * L::PKSLOT, p.P + p_index(p, first + lane) * L::PK,
 						 L::PK * 4, &full_bar[s]);
 			} else if (lane == 0) {
 				bulk_g2s(st, p.P + first * L::PK, uint32_t(cnt) * L::PK * 4, &full_bar[s]);
 			}
-		} else if (L::PAD > 0) {
+		} else if (L::PAD > 0 || p.p_share > 1u) {
 			if (lane < cnt)
-				bulk_g2s(st + lane * L::PSLOT, p.P + (first + lane) * (N * N),
+				bulk_g2s(st + lane * L::PSLOT, p.P + p_index(p, first + lane) * (N * N),
 					 N * N * 4, &full_bar[s]);
 		} else if (lane == 0) {
 			bulk_g2s(st, p.P + first * (N * N), uint32_t(cnt) * N * N * 4,
@@ -357,7 +359,7 @@ qp_tpq_kernel(const KernelArgs p)
 		} else {
 			// ---- listed problems: data straight from global memory, state from scratch ------
 			const float4 *src4 = reinterpret_cast<const float4 *>(
-				p.P + gidx * (unsigned long long)(PACKED_IN ? L::PK : N * N));
+				p.P + p_index(p, gidx) * (unsigned long long)(PACKED_IN ? L::PK : N * N));
 			fill_a([&](int k) { return __ldg(src4 + k); });
 			const float4 *q4 = reinterpret_cast<const float4 *>(p.q) + gidx * NQ;
 #pragma unroll

@@ -102,7 +102,15 @@ typedef struct qp_batch {
 	                        qp_solvers.c:281).  A problem whose entry is not a
 	                        positive finite number ends with QP_STATUS_SINGULAR */
 	uint32_t p_layout;   /* QP_P_DENSE (the reference's layout) or QP_P_UPPER   */
-	uint32_t reserved;   /* 0                                                   */
+	uint32_t p_share;    /* 0 or 1: every problem has its own P.  k > 1: problems
+	                        i*k .. i*k+k-1 share P[i] (P holds ceil(count / k)
+	                        matrices): one model, many right-hand sides -- an MPC
+	                        host that calls admm() with the same qf->p and a new
+	                        qf->q per state (struct _quadratic_form keeps them
+	                        apart, qp_solvers/qp.h:8-13).  Only q, the bounds, the
+	                        warm start and rho are per problem then: 64 instead of
+	                        1 088 bytes per problem at n = 16.  qp_solve_batch()
+	                        only (QP_ERR_UNSUPPORTED elsewhere)                    */
 } qp_batch;
 
 /* Layout of qp_batch.P. */
