@@ -327,6 +327,17 @@ def run_shapes(args, qp, torch, device, hbm_peak, fp32_peak, traffic, sm_mhz):
     ms = time_steps(torch, lambda i: qp.solve_batch(P, q, -args.beta, args.beta, out=out), steps)
     st1 = qp.schedule_stats()
     entry("n=40,m=80 random", n, count, ms, out, False, {"inputs": "1.7 GB > L2", "issue_ok": True})
+    # beside BASELINE.json's shapes: the same q with one matrix per 1024 problems (qp_batch.p_share)
+    Ps = P[::1024].contiguous()
+    outs = qp.solve_batch(Ps, q, -args.beta, args.beta, p_share=1024)
+    mss = time_steps(torch, lambda i: qp.solve_batch(Ps, q, -args.beta, args.beta, out=outs, p_share=1024), steps)
+    shared_line = {"shape": "n=40,m=80 random, one P per 1024 problems (qp_batch.p_share; not a BASELINE shape)",
+                   "n": n, "count": count, "qp_per_s": count / (mss * 1e-3), "ms_per_step": mss,
+                   "mean_iters": float(outs["iters"].float().mean()),
+                   "not_converged": int((outs["status"] != 0).sum()),
+                   "note": "each matrix is eliminated once (qp_bpq.cuh PASS_SETUP), every problem is then "
+                           "solved by the streaming kernel with the inverse of its group"}
+    del Ps, outs
     lines[-1]["schedule"] = {"options": "default (AUTO)",
                              "solves_in_passes": (st1["seen"] - st0["seen"]) // count,
                              "solves_single": (st1["probe_problems"] - st0["probe_problems"]) // count}
@@ -347,6 +358,7 @@ def run_shapes(args, qp, torch, device, hbm_peak, fp32_peak, traffic, sm_mhz):
           {"inputs": "1.07 GB > L2", "issue_ok": True})
     del P, q, q2, out, first, z0, u0
     torch.cuda.empty_cache()
+    run_shapes.beside = [shared_line]
     return lines
 
 # ------------------------------------------------------------------------------------------
@@ -801,6 +813,8 @@ def run_ours(args, rank, local_rank, world):
         line["e2e_device_mask"] = e2e_mask
     if shared is not None:
         line["shared_p"] = shared
+    if getattr(run_shapes, "beside", None):
+        line["shapes_beside_baseline"] = run_shapes.beside
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

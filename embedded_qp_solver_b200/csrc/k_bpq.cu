@@ -61,6 +61,10 @@ template <int NP, bool PFI> int launch_bpq_form(const KernelArgs &a, int dev, cu
 	switch (mode) {
 	case PASS_FIRST: return launch_bpq_m<NP, PFI, PASS_FIRST>(a, dev, st);
 	case PASS_LIST:  return launch_bpq_m<NP, PFI, PASS_LIST>(a, dev, st);
+	case PASS_SETUP:
+		if constexpr (!PFI)
+			return launch_bpq_m<NP, false, PASS_SETUP>(a, dev, st);
+		return QP_ERR_UNSUPPORTED;
 	}
 	return launch_bpq_m<NP, PFI, PASS_PLAIN>(a, dev, st);
 }

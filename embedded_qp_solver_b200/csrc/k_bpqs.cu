@@ -9,10 +9,10 @@ namespace qpb {
 
 namespace {
 
-template <int NP, bool BOUNDS> int launch_bpq_stream_b(const KernelArgs &a, int dev, cudaStream_t st)
+template <int NP, bool BOUNDS, bool FRESH> int launch_bpq_stream_b(const KernelArgs &a, int dev, cudaStream_t st)
 {
 	using SC = BpqStreamCfg<NP>;
-	auto kern = qp_bpq_stream_kernel<NP, BOUNDS>;
+	auto kern = qp_bpq_stream_kernel<NP, BOUNDS, FRESH>;
 	static PerDeviceOnce per_sm;
 	int b = per_sm.get(dev);
 	if (!b) {
@@ -33,21 +33,24 @@ template <int NP, bool BOUNDS> int launch_bpq_stream_b(const KernelArgs &a, int 
 }
 
 // (bpq_stream_eligible: lb and ub are both arrays or both absent)
-template <int NP> int launch_bpq_stream(const KernelArgs &a, int dev, cudaStream_t st)
+template <int NP> int launch_bpq_stream(const KernelArgs &a, int dev, cudaStream_t st, bool fresh)
 {
-	return (a.lb && a.ub) ? launch_bpq_stream_b<NP, true>(a, dev, st) : launch_bpq_stream_b<NP, false>(a, dev, st);
+	const bool b = a.lb && a.ub;
+	if (fresh)
+		return b ? launch_bpq_stream_b<NP, true, true>(a, dev, st) : launch_bpq_stream_b<NP, false, true>(a, dev, st);
+	return b ? launch_bpq_stream_b<NP, true, false>(a, dev, st) : launch_bpq_stream_b<NP, false, false>(a, dev, st);
 }
 
 } // namespace
 
-int launch_bpq_stream_family(const KernelArgs &a, int dev, cudaStream_t st)
+int launch_bpq_stream_family(const KernelArgs &a, int dev, cudaStream_t st, bool fresh)
 {
 	switch (a.n) {
-	case 8:  return launch_bpq_stream<8>(a, dev, st);
-	case 16: return launch_bpq_stream<16>(a, dev, st);
-	case 24: return launch_bpq_stream<24>(a, dev, st);
-	case 32: return launch_bpq_stream<32>(a, dev, st);
-	case 40: return launch_bpq_stream<40>(a, dev, st);
+	case 8:  return launch_bpq_stream<8>(a, dev, st, fresh);
+	case 16: return launch_bpq_stream<16>(a, dev, st, fresh);
+	case 24: return launch_bpq_stream<24>(a, dev, st, fresh);
+	case 32: return launch_bpq_stream<32>(a, dev, st, fresh);
+	case 40: return launch_bpq_stream<40>(a, dev, st, fresh);
 	}
 	return QP_ERR_UNSUPPORTED;
 }

@@ -248,6 +248,56 @@ int launch_solver(KernelArgs a, int dev, cudaStream_t st, uint32_t forced, uint3
 	const char *se = std::getenv("QPB200_BPQ_STREAM"); // =0: list passes instead of the streaming pass
 	const bool stream = fam == QP_KERNEL_BPQ && !(se && se[0] == '0') && bpq_stream_eligible(a);
 	const PassPolicy pol = pass_policy(fam, stream);
+
+	// Shared matrices (qp_batch.p_share) in the lane-group kernels, where the elimination is
+	// most of a solve: eliminate each MATRIX once (qp_bpq.cuh, PASS_SETUP), then the streaming
+	// kernel solves every problem from scratch with the inverse of its group.  Not with
+	// per-problem rho (the inverse depends on it) and not when the caller forces single launches.
+	// Measured on random problems (K = 10), 2^18 of them, matrix per problem -> one per 2 / 16 / 1024
+	// problems: n = 40 170 -> 194 / 312 / 343 M QP/s, n = 32 313 -> 301 / 429 / 458 M, n = 24
+	// 550 -> 418 / 518 / 539 M (the elimination is too small a part there: plain kernel).
+	const bool shared_pays = (a.n == 40 && a.p_share >= 2u) || (a.n == 32 && a.p_share >= 4u);
+	if (stream && shared_pays && schedule != QP_SCHEDULE_SINGLE && !a.rho_v && a.count < 0x7ffffff0ull) {
+		cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+		const bool capturing = cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone;
+		if (capturing)
+			cudaGetLastError();
+		DevArena &ar = g_arena[dev];
+		std::lock_guard<std::mutex> lk(ar.mu);
+		if (int rc = arena_stats_init(ar))
+			return rc;
+		const size_t nmat = size_t((a.count + a.p_share_off + a.p_share - 1) / a.p_share), nn = size_t(a.n) * a.n;
+		const size_t o_its = 256, o_R = o_its + up256(nmat * 4), need = o_R + up256(nmat * nn * 4);
+		if (ar.bytes < need) {
+			if (capturing)
+				return QP_ERR_UNSUPPORTED; // (no allocation inside a capture: warm the arena up first)
+			QP_CUDA(cudaEventSynchronize(ar.last));
+			if (ar.base)
+				cudaFree(ar.base);
+			ar.base = nullptr, ar.bytes = 0;
+			QP_CUDA(cudaMalloc(&ar.base, need));
+			ar.bytes = need;
+		}
+		QP_CUDA(cudaStreamWaitEvent(st, ar.last, 0));
+		unsigned *cnt = reinterpret_cast<unsigned *>(ar.base);
+		QP_CUDA(cudaMemsetAsync(cnt, 0, MAX_PASSES * 4, st));
+		KernelArgs su = a; // the matrices as a batch of their own
+		su.count = nmat, su.p_share = 1u, su.p_share_off = 0;
+		su.z0 = su.u0 = nullptr, su.rho_v = nullptr;
+		su.x = su.z = su.lam = nullptr, su.status = su.iters = nullptr;
+		su.ps = PassArgs{};
+		su.ps.its = reinterpret_cast<int *>(ar.base + o_its);
+		su.ps.Rs = reinterpret_cast<float *>(ar.base + o_R);
+		if (int rc = launch_bpq_family(su, dev, st, PASS_SETUP))
+			return rc;
+		a.ps = PassArgs{};
+		a.ps.its = su.ps.its, a.ps.Rs = su.ps.Rs;
+		a.ps.stream_ctr = cnt + (MAX_PASSES - 1);
+		if (int rc = launch_bpq_stream_family(a, dev, st, true))
+			return rc;
+		QP_CUDA(cudaEventRecord(ar.last, st));
+		return QP_OK;
+	}
 	const bool can = family_has_passes(fam, a.n) && a.count < 0xfffffff0ull && a.max_iter > pol.w0;
 	bool passes = can && schedule == QP_SCHEDULE_PASSES;
 	// (the probe adds iteration counts per lane in 32 bits: with 148 SMs a lane sees fewer than
@@ -376,7 +426,7 @@ int launch_solver(KernelArgs a, int dev, cudaStream_t st, uint32_t forced, uint3
 		a.ps.next_list = nullptr, a.ps.next_count = nullptr;
 		a.ps.next_list2 = nullptr, a.ps.next_count2 = nullptr;
 		a.ps.stream_ctr = cnt + (MAX_PASSES - 1);
-		if (int rc = launch_bpq_stream_family(a, dev, st))
+		if (int rc = launch_bpq_stream_family(a, dev, st, false))
 			return rc;
 		QP_CUDA(cudaEventRecord(ar.last, st));
 		return copy_stats();

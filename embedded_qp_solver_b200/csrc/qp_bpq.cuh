@@ -307,13 +307,19 @@ qp_bpq_kernel(const KernelArgs p)
 		// behind the iteration loop cost the elimination loop its load scheduling: twice the
 		// short-scoreboard stalls, 1.82 against 1.57 ms on 2^18 random problems that evict
 		// nobody; and with the streaming pass behind a short window most problems are evicted.)
-		if (MODE == PASS_FIRST) {
-			if (valid && !bad && p.ps.next_list) {
+		if (MODE == PASS_FIRST || MODE == PASS_SETUP) {
+			if (valid && !bad && (MODE == PASS_SETUP || p.ps.next_list)) {
 				float4 *Rp = reinterpret_cast<float4 *>(p.ps.Rs + prob * (unsigned long long)(NP * NP)) + g;
 #pragma unroll
 				for (int j = 0; j < NP; ++j)
 					Rp[j * (NP / 4)] = make_float4(S[0][j].x, S[0][j].y, S[1][j].x, S[1][j].y);
 			}
+		}
+		if constexpr (MODE == PASS_SETUP) {
+			// the launch's problems are matrices: inverse stored, verdict stored, next
+			if (valid && g == 0)
+				p.ps.its[prob] = bad ? 1 : 0;
+			continue;
 		}
 
 		// ---- per-coordinate state: coordinates 4g..4g+3 ---------------------------------------

@@ -58,7 +58,11 @@ template <int NP> struct BpqStreamCfg {
 // BOUNDS: lb / ub are arrays (eight registers per lane); otherwise the scalar box is read from
 // the constant bank where it is used -- the loop sits at the register limit, and with those
 // eight registers free the compiler schedules it noticeably better.
-template <int NP, bool BOUNDS>
+// FRESH: shared matrices (qp_batch.p_share).  There was no first pass over the problems, only
+// one over the matrices (qp_bpq.cuh, PASS_SETUP): every problem of the batch is taken by ticket
+// (no list), starts from its warm start or from zero with the inverse of its group, and the
+// x-update of its first iteration is computed in the refill block.
+template <int NP, bool BOUNDS, bool FRESH>
 __global__ void __launch_bounds__(BPQ_WARPS * 32, BpqStreamCfg<NP>::MINB)
 qp_bpq_stream_kernel(const KernelArgs p)
 {
@@ -94,26 +98,37 @@ qp_bpq_stream_kernel(const KernelArgs p)
 	// two lists: the problems the first pass expects to run long (their residuals had almost
 	// stopped shrinking when the window closed) are handed out first, so that the longest
 	// dependent chain of the batch starts at once instead of whenever its ticket comes up
-	const unsigned total1 = __ldcg(p.ps.list_count);
-	const unsigned total = total1 + (p.ps.list2 ? __ldcg(p.ps.list_count2) : 0u);
+	const unsigned total1 = FRESH ? 0u : __ldcg(p.ps.list_count);
+	const unsigned total = FRESH ? unsigned(p.count) : total1 + (p.ps.list2 ? __ldcg(p.ps.list_count2) : 0u);
 	const unsigned ngroups = gridDim.x * BPQ_WARPS * G;
 	// the first three problems of a group are dealt (warp-major, as everywhere); after that tickets
 	const unsigned gid = (warp * gridDim.x + blockIdx.x) * G + grp;
-	constexpr uint32_t tx = uint32_t(NP * NP + 4 * NP + (BOUNDS ? 2 * NP : 0)) * 4u;
+	// bytes of one slot fill: R, q, (lb, ub), z, u, (x) -- a fresh problem without a warm start
+	// brings neither z nor u
+	const uint32_t tx = uint32_t(NP * NP + NP + (BOUNDS ? 2 * NP : 0) +
+				     (FRESH ? (p.z0 ? 2 * NP : 0) : 3 * NP)) * 4u;
 
 	// start the copy of problem `prob` into the slot (the group's first lane)
 	auto issue = [&](unsigned prob) {
 		const unsigned long long o = (unsigned long long)prob * NP;
 		mbar_expect_tx(bar, tx);
-		bulk_g2s(sR, p.ps.Rs + o * NP, NP * NP * 4, bar);
+		bulk_g2s(sR, p.ps.Rs + (FRESH ? p_index(p, prob) : (unsigned long long)prob) * (NP * NP),
+			 NP * NP * 4, bar);
 		bulk_g2s(sq, p.q + o, NP * 4, bar);
 		if (BOUNDS) {
 			bulk_g2s(slb, p.lb + o, NP * 4, bar);
 			bulk_g2s(sub, p.ub + o, NP * 4, bar);
 		}
-		bulk_g2s(sz, p.ps.zs + o, NP * 4, bar);
-		bulk_g2s(su, p.ps.us + o, NP * 4, bar);
-		bulk_g2s(sx, p.ps.xs + o, NP * 4, bar);
+		if (FRESH) {
+			if (p.z0) {
+				bulk_g2s(sz, p.z0 + o, NP * 4, bar);
+				bulk_g2s(su, p.u0 + o, NP * 4, bar);
+			}
+		} else {
+			bulk_g2s(sz, p.ps.zs + o, NP * 4, bar);
+			bulk_g2s(su, p.ps.us + o, NP * 4, bar);
+			bulk_g2s(sx, p.ps.xs + o, NP * 4, bar);
+		}
 	};
 
 	// The look-ahead of a group (every value is uniform inside the group unless noted):
@@ -146,6 +161,8 @@ qp_bpq_stream_kernel(const KernelArgs p)
 			return NONE;
 		}
 		t_req = NO_TICKET;
+		if (FRESH)
+			return t | SHORT; // no list, and nothing is known about anybody: look ahead
 		return t < total1 ? __ldcg(p.ps.list + t) : (__ldcg(p.ps.list2 + (t - total1)) | SHORT);
 	};
 	// the next problem in line: the list entry read at the last refill, else a ticket's
@@ -160,8 +177,9 @@ qp_bpq_stream_kernel(const KernelArgs p)
 		const unsigned idx = tagged & ~SHORT;
 		if (g == 0)
 			issue(idx);
-		rho_nxt = p.rho_v ? __ldg(p.rho_v + idx) : p.rho;
-		its_nxt = __ldcg(p.ps.its + idx);
+		rho_nxt = (!FRESH && p.rho_v) ? __ldg(p.rho_v + idx) : p.rho;
+		// (FRESH: its[] holds the verdict on the group's matrix, 1 = not positive definite)
+		its_nxt = __ldcg(p.ps.its + (FRESH ? p_index(p, idx) : (unsigned long long)idx));
 		slot_prob = tagged;
 	};
 
@@ -352,6 +370,9 @@ qp_bpq_stream_kernel(const KernelArgs p)
 					st_it += done0 + it, ++st_n;
 				}
 				// ---- the next problem: slot -> registers ---------------------------------------
+				// (a loop only for FRESH: a problem whose matrix is not positive definite gets
+				// its verdict here and the group takes another one)
+				for (;;) {
 				if (slot_prob == NONE) {
 					const unsigned nx = next_problem();
 					if (nx != NONE)
@@ -360,7 +381,9 @@ qp_bpq_stream_kernel(const KernelArgs p)
 				const bool cur_short = (slot_prob & SHORT) != 0u && slot_prob != NONE;
 				cur = slot_prob == NONE ? NONE : (slot_prob & ~SHORT);
 				slot_prob = NONE;
-				if (cur != NONE) {
+				if (cur == NONE)
+					break;
+				{
 					mbar_wait(bar, ph);
 					ph ^= 1u;
 					const float4 *R4 = reinterpret_cast<const float4 *>(sR) + g;
@@ -370,12 +393,16 @@ qp_bpq_stream_kernel(const KernelArgs p)
 						S[0][j] = make_float2(v.x, v.y), S[1][j] = make_float2(v.z, v.w);
 					}
 					const float4 vq = reinterpret_cast<const float4 *>(sq)[g];
-					const float4 vz = reinterpret_cast<const float4 *>(sz)[g];
-					const float4 vu = reinterpret_cast<const float4 *>(su)[g];
-					// the x-update of the problem's next iteration: the first pass had it already
-					// (its loop is software-pipelined like the one below)
-					const float4 vx = reinterpret_cast<const float4 *>(sx)[g];
-					xr[0] = vx.x, xr[1] = vx.y, xr[2] = vx.z, xr[3] = vx.w;
+					const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+					const bool have_zu = !FRESH || p.z0 != nullptr;
+					const float4 vz = have_zu ? reinterpret_cast<const float4 *>(sz)[g] : zero4;
+					const float4 vu = have_zu ? reinterpret_cast<const float4 *>(su)[g] : zero4;
+					if constexpr (!FRESH) {
+						// the x-update of the problem's next iteration: the first pass had it
+						// already (its loop is software-pipelined like the one below)
+						const float4 vx = reinterpret_cast<const float4 *>(sx)[g];
+						xr[0] = vx.x, xr[1] = vx.y, xr[2] = vx.z, xr[3] = vx.w;
+					}
 					q[0] = vq.x, q[1] = vq.y, q[2] = vq.z, q[3] = vq.w;
 					if constexpr (BOUNDS) {
 						const float4 vl = reinterpret_cast<const float4 *>(slb)[g];
@@ -388,7 +415,8 @@ qp_bpq_stream_kernel(const KernelArgs p)
 					x[0] = x[1] = x[2] = x[3] = 0.0f;
 					rho = rho_nxt;
 					rho2 = rho * rho, relrho = p.reltol * rho;
-					done0 = unsigned(its_nxt); // < max_iter
+					const bool bad_matrix = FRESH && its_nxt != 0;
+					done0 = FRESH ? 0u : unsigned(its_nxt); // < max_iter
 					it = 0;
 					conv = false;
 					// the slot is free: order the reads above before the next copy's writes
@@ -408,6 +436,34 @@ qp_bpq_stream_kernel(const KernelArgs p)
 								t_req = 0u; // "requested": the first lane holds it
 						}
 					}
+					if constexpr (FRESH) {
+						if (bad_matrix || p.max_iter == 0) {
+							// what the plain kernel hands back for such a problem: x = 0, the
+							// starting z and u, no iteration
+							const unsigned long long o4 = (unsigned long long)cur * (NP / 4) + g;
+							if (p.x)
+								reinterpret_cast<float4 *>(p.x)[o4] = zero4;
+							if (p.z)
+								reinterpret_cast<float4 *>(p.z)[o4] = vz;
+							if (p.lam)
+								reinterpret_cast<float4 *>(p.lam)[o4] =
+									make_float4(rho * vu.x, rho * vu.y, rho * vu.z, rho * vu.w);
+							if (g == 0) {
+								if (p.status)
+									p.status[cur] = bad_matrix ? QP_STATUS_SINGULAR : QP_STATUS_MAX_ITER;
+								if (p.iters)
+									p.iters[cur] = 0;
+							}
+							continue;
+						}
+						// the x-update of the first iteration (the loop below is software-pipelined)
+						float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f, d4 = 0.f;
+						publish_y(ybuf);
+						__syncwarp(am);
+						matvec_and_sums(ybuf, xr, d0, d1, d2, d3, d4);
+					}
+				}
+				break;
 				}
 				fin = false;
 			}

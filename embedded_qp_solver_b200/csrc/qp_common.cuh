@@ -32,7 +32,11 @@ namespace qpb {
 //               the unfinished ones to next_list (null: the last pass runs everything out)
 //   PASS_STREAM qp_bpq_stream.cuh: the problems of `list`, every one to the end, each lane group
 //               taking its next problem by ticket (stream_ctr) as soon as its current one stops
-constexpr int PASS_PLAIN = 0, PASS_FIRST = 1, PASS_LIST = 2, PASS_STREAM = 3;
+//   PASS_SETUP  qp_bpq.cuh, shared matrices (qp_batch.p_share): the "problems" of the launch are the
+//               MATRICES; each is eliminated once, its inverse goes to Rs, "not positive definite"
+//               to its[]; no iteration.  The streaming kernel then solves every problem from
+//               scratch with the inverse of its group.
+constexpr int PASS_PLAIN = 0, PASS_FIRST = 1, PASS_LIST = 2, PASS_STREAM = 3, PASS_SETUP = 4;
 struct PassArgs {
 	unsigned long long *stats;  // null, or counters the kernels add to (qp_batch.cu reads them):
 	                            // [0] problems that outlived the first window (PASS_FIRST: evicted)

@@ -84,7 +84,9 @@ int launch_cpq_family(const KernelArgs &a, int dev, cudaStream_t st);
 // PASS_STREAM (qp_bpq_stream.cuh): can the second launch of a pass schedule be the streaming
 // kernel for this batch (full inverse, i.e. no product form), and its launcher
 bool bpq_stream_eligible(const KernelArgs &a);
-int launch_bpq_stream_family(const KernelArgs &a, int dev, cudaStream_t st);
+// fresh: shared matrices -- every problem of the batch, from scratch, with the inverse that a
+// PASS_SETUP launch of qp_bpq.cuh left for its group
+int launch_bpq_stream_family(const KernelArgs &a, int dev, cudaStream_t st, bool fresh);
 // which families have the pass modes (KernelArgs::ps)
 bool family_has_passes(int family, int n);
 

@@ -98,6 +98,8 @@ def main():
     ap.add_argument("--schedule", default="auto", choices=["auto", "single", "passes"])
     ap.add_argument("--kernel", default="auto", choices=["auto", "tpq", "gpq", "bpq", "cpq"])
     ap.add_argument("--max-iter", type=int, default=10000, help="iteration cap (qp_options.max_iter)")
+    ap.add_argument("--share", type=int, default=1,
+                    help="qp_batch.p_share: every K consecutive problems use the matrix of the first of them")
     ap.add_argument("--counts", default="", help="override batch sizes, e.g. 24:262144,32:262144")
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
@@ -129,6 +131,9 @@ def main():
             P, q = make_batch(count, n, 2026, dev)
         warm = n == 64 and not args.cold
         kw = {}
+        if args.share > 1:
+            P = P[::args.share].contiguous()
+            kw["p_share"] = args.share
         if warm:
             first = qp.solve_batch(P, q, -beta, beta, options=opts)
             q = q + 0.01 * torch.randn_like(q)
@@ -149,7 +154,7 @@ def main():
         flops_per = qp.algorithmic_flops(n, k)
         rate = count / (ms * 1e-3)
         line = {"shape": f"n={n},m={2 * n}" + (" mpc" if args.mpc and n == 40 else ""), "count": count, "kernel": qp.kernel_for(n) if args.kernel == "auto" else f"{args.kernel}<{n}>",
-                "warm_start": warm, "schedule": args.schedule, "qp_per_s": rate, "ms_per_step": ms, "mean_iters": k,
+                "warm_start": warm, "schedule": args.schedule, "p_share": args.share, "qp_per_s": rate, "ms_per_step": ms, "mean_iters": k,
                 "not_converged": int((out["status"] != 0).sum()),
                 "hbm": {"achieved_gbs": bytes_per * rate / 1e9, "peak": hbm_peak,
                         "frac": bytes_per * rate / 1e9 / hbm_peak, "bytes_per_problem": bytes_per},
