@@ -191,3 +191,21 @@ def test_error_in_the_middle_leaves_the_workspace_usable(qp):
         qp.solve_batch(P[:, :12, :12].copy(), q[:, :12].copy(), -0.5, 0.5,
                        options=qp.Options(kernel=qp.KERNEL_BPQ))   # bpq takes n % 8 == 0 only
     same(qp.solve_batch(P, q, -0.5, 0.5), ref, "after the failures")
+
+
+@pytest.mark.parametrize("n", [16, 40])
+def test_shared_matrices_over_several_gpus(qp, n):
+    """qp_batch.p_share with device_mask: the shards start in the middle of a group of problems
+    that share a matrix (count and shard sizes are not multiples of the group size)."""
+    nd = ngpu(qp)
+    if nd < 2:
+        pytest.skip("needs at least two GPUs")
+    count, share = 30_011, 1000
+    nmat = (count + share - 1) // share
+    Pm = problems.wellcond(nmat, n, seed=5, beta=0.5)[0]
+    q = problems.wellcond(count, n, seed=6, beta=0.5)[1]
+    P = np.repeat(Pm, share, axis=0)[:count]
+    ref = qp.solve_batch(P, q, -0.5, 0.5, options=qp.Options(device=0))
+    for mask in (0x3, (1 << nd) - 1):
+        got = qp.solve_batch(Pm, q, -0.5, 0.5, options=qp.Options(device_mask=mask, chunk=4096), p_share=share)
+        same(got, ref, f"shared, n {n}, mask {mask:#x}")
