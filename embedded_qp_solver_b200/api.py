@@ -35,6 +35,9 @@ _fp = C.POINTER(C.c_float)
 _ip = C.POINTER(C.c_int32)
 
 
+PRECISION_F32, PRECISION_F64 = 0, 1
+
+
 class qp_batch(C.Structure):
     _fields_ = [("n", C.c_uint32), ("mem", C.c_uint32), ("count", C.c_size_t),
                 ("P", C.c_void_p), ("q", C.c_void_p), ("lb", C.c_void_p), ("ub", C.c_void_p),
@@ -63,7 +66,7 @@ class qp_options(C.Structure):
     _fields_ = [("rho", C.c_float), ("alpha", C.c_float), ("abstol", C.c_float),
                 ("reltol", C.c_float), ("max_iter", C.c_uint32), ("device_mask", C.c_uint32),
                 ("device", C.c_int32), ("stream", C.c_void_p), ("chunk", C.c_uint32),
-                ("kernel", C.c_uint32), ("schedule", C.c_uint32), ("reserved", C.c_uint32)]
+                ("kernel", C.c_uint32), ("schedule", C.c_uint32), ("precision", C.c_uint32)]
 
 
 class qp_ref_matrix(C.Structure):
@@ -200,11 +203,12 @@ class Options:
     chunk: int = 0
     kernel: int = 0   # KERNEL_AUTO / KERNEL_TPQ / KERNEL_GPQ / KERNEL_BPQ / KERNEL_CPQ
     schedule: int = 0  # SCHEDULE_AUTO / SCHEDULE_SINGLE / SCHEDULE_PASSES
+    precision: int = 0  # PRECISION_F32 / PRECISION_F64 (qf entry points only)
 
     def to_c(self) -> qp_options:
         return qp_options(self.rho, self.alpha, self.abstol, self.reltol, int(self.max_iter),
                           int(self.device_mask), int(self.device), C.c_void_p(self.stream or None),
-                          int(self.chunk), int(self.kernel), int(self.schedule), 0)
+                          int(self.chunk), int(self.kernel), int(self.schedule), int(self.precision))
 
 
 def _is_torch(t) -> bool:
@@ -574,9 +578,10 @@ def newton_method_with_line_search(x0, iterations: int, qf: QuadraticForm,
     return x
 
 
-def admm_many(qfs, iterations: int, lb: float = -1e12, ub: float = 1e12):
+def admm_many(qfs, iterations: int, lb: float = -1e12, ub: float = 1e12, options: Optional[Options] = None):
     """Array-of-structs entry (``qp_admm_qf_batch``): a list of QuadraticForm
-    solved as one batch.  Returns (x [count,n] float64, status, iters)."""
+    solved as one batch.  Returns (x [count,n] float64, status, iters).
+    ``options.precision = PRECISION_F64`` solves in the reference's own binary64."""
     lib = load_library()
     count = len(qfs)
     n = qfs[0].p.array.shape[0]
@@ -586,8 +591,10 @@ def admm_many(qfs, iterations: int, lb: float = -1e12, ub: float = 1e12):
         *[x[i].ctypes.data_as(C.POINTER(C.c_double)) for i in range(count)])
     st = np.zeros(count, np.int32)
     it = np.zeros(count, np.int32)
+    copt = options.to_c() if options is not None else None
     rc = lib.qp_admm_qf_batch(arr, count, int(iterations), float(lb), float(ub), xp,
-                              st.ctypes.data_as(_ip), it.ctypes.data_as(_ip), None)
+                              st.ctypes.data_as(_ip), it.ctypes.data_as(_ip),
+                              C.byref(copt) if copt is not None else None)
     if rc != QP_OK:
         raise QpError(rc, "qp_admm_qf_batch")
     return x, st, it

@@ -48,6 +48,38 @@ struct _matrix *admm_b200(struct _matrix *x0, unsigned iterations,
 }
 
 /*
+ * The same in the reference's own arithmetic: binary64 on the GPU
+ * (qp_options.precision = QP_PRECISION_F64, csrc/qp_f64.cuh).  Reproduces the
+ * reference's iteration count -- hence its x to ~1e-10 -- on its ill-conditioned
+ * test problems, where the binary32 product path stops an iteration early or
+ * late on one problem in three:
+ *
+ *     test_optimizer(qf, ADMM_ITERATIONS, x0, "admm_b200_f64", admm_b200_f64);
+ */
+struct _matrix *admm_b200_f64(struct _matrix *x0, unsigned iterations,
+			      struct _quadratic_form *qf)
+{
+	(void)x0;
+	struct _matrix *x = matrix_alloc(Nx1);
+	if (!x)
+		return 0;
+	qp_options opt;
+	qp_options_default(&opt);
+	opt.precision = QP_PRECISION_F64;
+	const struct qp_ref_quadratic_form *one[1] = { (const struct qp_ref_quadratic_form *)qf };
+	double *xo[1] = { x->elements };
+	int rc = qp_admm_qf_batch(one, 1, iterations, ADMM_BOX_CONSTRAINT_MIN,
+				  ADMM_BOX_CONSTRAINT_MAX, xo, 0, 0, &opt);
+	if (rc != QP_OK) {
+		fprintf(stderr, "admm_b200_f64: qp_admm_qf_batch failed (%d) %s\n", rc,
+			qp_last_error());
+		matrix_free(x);
+		return 0;
+	}
+	return x;
+}
+
+/*
  * Drop-in for newton_method_with_line_search() (qp_solvers/qp_solvers.h:9-12,
  * qp_solvers.c:103-144), same signature, same ownership of the result:
  *

@@ -67,4 +67,27 @@ __host__ __device__ inline size_t gen_smem_floats_per_group(int n, int m, int T)
 	return need + (want + 32 - r) % 32;
 }
 
+// ---- qp_f64.cuh: the box ADMM in binary64 (qf entry points, qp_options.precision) -----------
+constexpr int F64_WARPS = 4;
+
+struct Admm64Args {
+	const double *P, *q;       // [count][n][n], [count][n]
+	double lb, ub;             // the scalar box (config.h:29-30)
+	double *x;                 // [count][n]
+	int32_t *status, *iters;   // may be null
+	unsigned long long count;
+	int n;
+	double rho, alpha, eps_abs, reltol; // eps_abs = sqrt(n) * abstol (:242)
+	unsigned max_iter;
+};
+
+__host__ __device__ inline int f64_ld(int n)
+{
+	return n | 1;
+}
+__host__ __device__ inline size_t f64_smem_doubles_per_warp(int n)
+{
+	return size_t(n) * f64_ld(n) + 2 * 64;
+}
+
 } // namespace qpb

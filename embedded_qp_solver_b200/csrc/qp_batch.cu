@@ -501,6 +501,8 @@ int check_options(const qp_options &o)
 		return QP_ERR_INVALID;
 	if (o.schedule > QP_SCHEDULE_PASSES)
 		return QP_ERR_INVALID;
+	if (o.precision > QP_PRECISION_F64)
+		return QP_ERR_INVALID;
 	return QP_OK;
 }
 
@@ -1473,6 +1475,8 @@ extern "C" int qp_solve_batch_ws(qp_workspace *ws, const qp_batch *pb,
 	rc = resolve_options(opt_in, opt);
 	if (rc != QP_OK)
 		return rc;
+	if (opt.precision != QP_PRECISION_F32) // binary64: the qf entry points only
+		return QP_ERR_UNSUPPORTED;
 	if (pb->count == 0)
 		return QP_OK;
 
@@ -1562,6 +1566,8 @@ extern "C" int qp_solve_batch(const qp_batch *pb, const qp_batch_solution *sol,
 	rc = resolve_options(opt_in, opt);
 	if (rc != QP_OK)
 		return rc;
+	if (opt.precision != QP_PRECISION_F32)
+		return QP_ERR_UNSUPPORTED;
 	const int dev = resolve_device(opt.device);
 	if (dev < 0)
 		return QP_ERR_NO_DEVICE;
@@ -1834,6 +1840,70 @@ extern "C" int qp_admm_qf_batch(const struct qp_ref_quadratic_form *const *qfs, 
 		if (ref_rows(qfs[i]->p) != n || ref_cols(qfs[i]->p) != n ||
 		    ref_rows(qfs[i]->q) * ref_cols(qfs[i]->q) != n)
 			return QP_ERR_INVALID;
+
+	if (opt_in && opt_in->precision == QP_PRECISION_F64) {
+		// ---- the reference's own arithmetic (qp_f64.cuh): doubles in, doubles out ------------
+		if (n > QP_MAX_DIM)
+			return QP_ERR_UNSUPPORTED;
+		qp_options opt = *opt_in;
+		if (int rc = check_options(opt))
+			return rc;
+		const int dev = resolve_device(opt.device);
+		if (dev < 0)
+			return QP_ERR_NO_DEVICE;
+		DeviceGuard g;
+		if (g.enter(dev) != QP_OK)
+			return QP_ERR_NO_DEVICE;
+		const size_t nn = size_t(n) * n;
+		std::vector<double> hP(count * nn), hq(count * n), hx(count * n);
+		std::vector<int32_t> hs(count), hi(count);
+		for (size_t i = 0; i < count; ++i) {
+			std::memcpy(hP.data() + i * nn, qfs[i]->p->elements, nn * 8);
+			std::memcpy(hq.data() + i * n, qfs[i]->q->elements, size_t(n) * 8);
+		}
+		char *d = nullptr;
+		const size_t oP = 0, oq = oP + count * nn * 8, ox = oq + count * n * 8, os = ox + count * n * 8,
+			     oi = os + up256(count * 4), tot = oi + up256(count * 4);
+		QP_CUDA(cudaMalloc(&d, tot));
+		auto fail = [&](cudaError_t e, const char *what) {
+			g_err = std::string(what) + ": " + cudaGetErrorString(e);
+			cudaFree(d);
+			return QP_ERR_CUDA;
+		};
+		cudaStream_t st = static_cast<cudaStream_t>(opt.stream);
+		cudaError_t e;
+		if ((e = cudaMemcpyAsync(d + oP, hP.data(), count * nn * 8, cudaMemcpyHostToDevice, st)) != cudaSuccess)
+			return fail(e, "cudaMemcpyAsync");
+		if ((e = cudaMemcpyAsync(d + oq, hq.data(), count * n * 8, cudaMemcpyHostToDevice, st)) != cudaSuccess)
+			return fail(e, "cudaMemcpyAsync");
+		Admm64Args a = {};
+		a.P = reinterpret_cast<const double *>(d + oP), a.q = reinterpret_cast<const double *>(d + oq);
+		a.lb = lb, a.ub = ub;
+		a.x = reinterpret_cast<double *>(d + ox);
+		a.status = reinterpret_cast<int32_t *>(d + os), a.iters = reinterpret_cast<int32_t *>(d + oi);
+		a.count = count, a.n = int(n);
+		a.rho = double(opt.rho), a.alpha = double(opt.alpha);
+		a.eps_abs = std::sqrt(double(n)) * double(opt.abstol), a.reltol = double(opt.reltol);
+		a.max_iter = iterations;
+		if (int rc = launch_admm64(a, dev, st)) {
+			cudaFree(d);
+			return rc;
+		}
+		if ((e = cudaMemcpyAsync(hx.data(), d + ox, count * n * 8, cudaMemcpyDeviceToHost, st)) != cudaSuccess ||
+		    (e = cudaMemcpyAsync(hs.data(), d + os, count * 4, cudaMemcpyDeviceToHost, st)) != cudaSuccess ||
+		    (e = cudaMemcpyAsync(hi.data(), d + oi, count * 4, cudaMemcpyDeviceToHost, st)) != cudaSuccess ||
+		    (e = cudaStreamSynchronize(st)) != cudaSuccess)
+			return fail(e, "copy back");
+		cudaFree(d);
+		for (size_t i = 0; i < count; ++i) {
+			std::memcpy(x_out[i], hx.data() + i * n, size_t(n) * 8);
+			if (status)
+				status[i] = hs[i];
+			if (iters)
+				iters[i] = hi[i];
+		}
+		return QP_OK;
+	}
 
 	// A host that solves for many right-hand sides with one model hands over the SAME qf->p
 	// in runs of consecutive structs (struct _quadratic_form keeps p and q apart,

@@ -150,8 +150,16 @@ typedef struct qp_options {
 	                         batch returns QP_ERR_UNSUPPORTED                   */
 	uint32_t schedule;    /* QP_SCHEDULE_*: how problems that need many more
 	                         iterations than their neighbours are handled      */
-	uint32_t reserved;    /* 0                                                  */
+	uint32_t precision;   /* QP_PRECISION_F32 (0, the product: every entry point)
+	                         or QP_PRECISION_F64: the qf entry points
+	                         (qp_admm_qf_batch) solve in the reference's own
+	                         binary64 -- its iteration counts on its own
+	                         ill-conditioned test problems, x to ~1e-12; a
+	                         correctness path, n <= QP_MAX_DIM, one GPU.
+	                         QP_ERR_UNSUPPORTED in the float entry points       */
 } qp_options;
+#define QP_PRECISION_F32 0
+#define QP_PRECISION_F64 1
 
 /*
  * Scheduling of uneven iteration counts.  The reference's own test problems

@@ -17,6 +17,8 @@
 struct _matrix *admm_b200(struct _matrix *x0, unsigned iterations,
 			  struct _quadratic_form *qf);
 
+struct _matrix *admm_b200_f64(struct _matrix *x0, unsigned iterations,
+			      struct _quadratic_form *qf);
 struct _matrix *newton_b200(struct _matrix *x0, unsigned iterations,
 			    struct _quadratic_form *qf);
 struct _matrix *gradient_b200(struct _matrix *x0, unsigned iterations,
@@ -65,6 +67,44 @@ int compat_run(unsigned seed, double *x_ref, double *x_gpu, double *f_out,
 		f_out[1] = quadratic_form_eval(qf, b);
 		memcpy(P_out, p->elements, sizeof(double) * N_DIM * N_DIM);
 		memcpy(q_out, q->elements, sizeof(double) * N_DIM);
+	}
+	if (a)
+		matrix_free(a);
+	if (b)
+		matrix_free(b);
+	quadratic_form_free(qf);
+	matrix_free(x0);
+	matrix_free(q);
+	matrix_free(p);
+	return rc;
+}
+
+/* the binary64 drop-in against the reference's admm on the reference's own problem */
+int compat_run_f64(unsigned seed, double *x_ref, double *x_gpu)
+{
+	if (!ready) {
+		kmalloc_init();
+		ready = 1;
+	}
+	srand(seed);
+	struct _matrix *p = matrix_alloc(NxN);
+	struct _matrix *q = matrix_alloc(Nx1);
+	struct _matrix *x0 = matrix_alloc(Nx1);
+	struct _quadratic_form *qf = quadratic_form_alloc(p, q, 0);
+	if (!p || !q || !x0 || !qf)
+		return -1;
+	matirx_random_pos_def(p, P_RAND_ENTRY_MIN, P_RAND_ENTRY_MAX);
+	matrix_random(q, Q_RAND_ENTRY_MIN, Q_RAND_ENTRY_MAX);
+	matrix_random(x0, X_RAND_ENTRY_MIN, X_RAND_ENTRY_MAX);
+	test_optimizer(qf, ADMM_ITERATIONS, x0, "admm_b200_f64", admm_b200_f64);
+	struct _matrix *a = admm(x0, ADMM_ITERATIONS, qf);
+	struct _matrix *b = admm_b200_f64(x0, ADMM_ITERATIONS, qf);
+	int rc = 0;
+	if (!a || !b) {
+		rc = -2;
+	} else {
+		memcpy(x_ref, a->elements, sizeof(double) * N_DIM);
+		memcpy(x_gpu, b->elements, sizeof(double) * N_DIM);
 	}
 	if (a)
 		matrix_free(a);

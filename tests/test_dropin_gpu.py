@@ -47,6 +47,25 @@ def test_reference_harness_runs_with_admm_b200(qp, orc, capfd):
     assert out.count("admm_b200 gave:") == 3 and out.count("admm gave:") == 3
 
 
+def test_binary64_drop_in_reproduces_the_reference(qp, capfd):
+    """admm_b200_f64 (qp_options.precision = QP_PRECISION_F64) inside the reference's harness, on
+    problems drawn by the reference's own generators: the reference's x to 1e-9, i.e. the same
+    iteration count (a binary32 run stops an iteration early or late on one such problem in three)."""
+    qp.load_library()
+    lib = C.CDLL(LIB)
+    lib.compat_dim.restype = C.c_uint
+    n = lib.compat_dim()
+    d = C.POINTER(C.c_double)
+    lib.compat_run_f64.restype = C.c_int
+    lib.compat_run_f64.argtypes = [C.c_uint, d, d]
+    for seed in range(1, 9):
+        x_ref, x_gpu = np.zeros(n), np.zeros(n)
+        assert lib.compat_run_f64(seed, x_ref.ctypes.data_as(d), x_gpu.ctypes.data_as(d)) == 0
+        err = np.max(np.abs(x_gpu - x_ref)) / (1 + np.max(np.abs(x_ref)))
+        assert err <= 1e-9, (seed, err)
+    assert capfd.readouterr().out.count("admm_b200_f64 gave:") == 8
+
+
 def test_reference_harness_runs_with_newton_b200(qp, capfd):
     """The reference's second solver through the same function pointer
     (main.c:46-48): newton_method_with_line_search vs the drop-in newton_b200."""
