@@ -246,7 +246,9 @@ int launch_solver(KernelArgs a, int dev, cudaStream_t st, uint32_t forced, uint3
 	if (!fam)
 		return QP_ERR_UNSUPPORTED;
 	const char *se = std::getenv("QPB200_BPQ_STREAM"); // =0: list passes instead of the streaming pass
-	const bool stream = fam == QP_KERNEL_BPQ && !(se && se[0] == '0') && bpq_stream_eligible(a);
+	// (bit 31 of a problem index is a tag in the streaming kernel)
+	const bool stream = fam == QP_KERNEL_BPQ && !(se && se[0] == '0') && bpq_stream_eligible(a) &&
+			    a.count < 0x7ffffff0ull;
 	const PassPolicy pol = pass_policy(fam, stream);
 
 	// Shared matrices (qp_batch.p_share) in the lane-group kernels, where the elimination is

@@ -8,7 +8,7 @@
 //
 // Why: in qp_bpq.cuh the G problems of a warp (three at n = 40) run until the slowest one stops.
 // On BASELINE.json's condensed-MPC set (mean 35.8 iterations, median 25, maximum 2 783) the mean
-// over warps of the slowest of three is 60 iterations: 40 % of the lane-iterations wait.  A list
+// over warps of the slowest of three is 62 iterations: 42 % of the lane-iterations wait.  A list
 // pass that deals G stragglers to a warp has the same problem one level down, and a group that
 // fetched its next problem straight from HBM stalled the whole warp for the round trip
 // (profiles/README.md "Passes", rejected).  Here
@@ -101,7 +101,7 @@ qp_bpq_stream_kernel(const KernelArgs p)
 	const unsigned total1 = FRESH ? 0u : __ldcg(p.ps.list_count);
 	const unsigned total = FRESH ? unsigned(p.count) : total1 + (p.ps.list2 ? __ldcg(p.ps.list_count2) : 0u);
 	const unsigned ngroups = gridDim.x * BPQ_WARPS * G;
-	// the first three problems of a group are dealt (warp-major, as everywhere); after that tickets
+	// the first problem of a group is dealt (warp-major, as everywhere); after that tickets
 	const unsigned gid = (warp * gridDim.x + blockIdx.x) * G + grp;
 	// bytes of one slot fill: R, q, (lb, ub), z, u, (x) -- a fresh problem without a warm start
 	// brings neither z nor u
