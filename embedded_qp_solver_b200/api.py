@@ -28,6 +28,7 @@ QP_OK, QP_ERR_INVALID, QP_ERR_UNSUPPORTED, QP_ERR_CUDA, QP_ERR_NO_DEVICE = 0, -1
 QP_ERR_IO = -5
 MEM_HOST, MEM_DEVICE = 0, 1
 KERNEL_AUTO, KERNEL_TPQ, KERNEL_GPQ, KERNEL_BPQ, KERNEL_CPQ = 0, 1, 2, 3, 4
+KERNEL_GEN_SMEM, KERNEL_GEN_REG = 5, 6  # solve_general_batch only
 SCHEDULE_AUTO, SCHEDULE_SINGLE, SCHEDULE_PASSES = 0, 1, 2
 P_DENSE, P_UPPER = 0, 1
 
@@ -201,7 +202,7 @@ class Options:
     device: int = -1
     stream: int = 0
     chunk: int = 0
-    kernel: int = 0   # KERNEL_AUTO / KERNEL_TPQ / KERNEL_GPQ / KERNEL_BPQ / KERNEL_CPQ
+    kernel: int = 0   # KERNEL_AUTO / KERNEL_TPQ / KERNEL_GPQ / KERNEL_BPQ / KERNEL_CPQ (general rows: KERNEL_GEN_*)
     schedule: int = 0  # SCHEDULE_AUTO / SCHEDULE_SINGLE / SCHEDULE_PASSES
     precision: int = 0  # PRECISION_F32 / PRECISION_F64 (qf entry points only)
 

@@ -30,6 +30,7 @@ UNITS = {
     "k_gpq.cu": ["qp_gpq.cuh"],
     "k_cpq.cu": ["qp_cpq.cuh"],
     "k_aux.cu": ["qp_gen.cuh", "qp_newton.cuh"],
+    "k_genr.cu": ["qp_genr.cuh"],
     "k_f64.cu": ["qp_f64.cuh"],
     "qp_batch.cu": [],
     "qp_file.cpp": [],

@@ -93,6 +93,11 @@ template <int T> static int launch_gen_t(const GenArgs &a, int dev, cudaStream_t
 
 int launch_gen(const GenArgs &a, int dev, cudaStream_t st)
 {
+	if (a.force != 1) {
+		const int rc = launch_genr(a, dev, st);
+		if (rc != QP_ERR_UNSUPPORTED || a.force == 2)
+			return rc;
+	}
 	switch (gen_lanes(a.n, a.m)) {
 	case 4:  return launch_gen_t<4>(a, dev, st);
 	case 8:  return launch_gen_t<8>(a, dev, st);

@@ -45,6 +45,7 @@ struct GenArgs {
 	float eps_abs_pri, eps_abs_dual; // sqrt(m) abstol, sqrt(n) abstol
 	float reltol;
 	unsigned max_iter;
+	int force; // 0: the register kernel (qp_genr.cuh) where the shape fits; 1: qp_gen.cuh; 2: qp_genr.cuh or refuse
 };
 
 __host__ __device__ inline int gen_ld(int n)

@@ -132,6 +132,8 @@ int pick_kernel(const KernelArgs &a, uint32_t forced)
 	const bool c = a.n >= 1 && a.n <= QP_MAX_DIM_BOX;
 	if (a.p_packed) // packed upper triangles: the thread-per-QP kernels only
 		return (t && a.n >= 8 && (forced == QP_KERNEL_AUTO || forced == QP_KERNEL_TPQ)) ? QP_KERNEL_TPQ : 0;
+	if (forced > QP_KERNEL_CPQ) // the general-rows kernels do not take a box batch
+		return 0;
 	switch (forced) {
 	case QP_KERNEL_TPQ: return t ? QP_KERNEL_TPQ : 0;
 	case QP_KERNEL_BPQ: return b ? QP_KERNEL_BPQ : 0;
@@ -1763,6 +1765,12 @@ extern "C" int qp_solve_general_batch(const qp_general_batch *pb, const qp_gener
 	a.rho = opt.rho, a.alpha = opt.alpha, a.reltol = opt.reltol, a.max_iter = opt.max_iter;
 	a.eps_abs_pri = float(std::sqrt(double(m)) * double(opt.abstol));
 	a.eps_abs_dual = float(std::sqrt(double(n)) * double(opt.abstol));
+	switch (opt.kernel) {
+	case QP_KERNEL_AUTO: a.force = 0; break;
+	case QP_KERNEL_GEN_SMEM: a.force = 1; break;
+	case QP_KERNEL_GEN_REG: a.force = 2; break;
+	default: return QP_ERR_UNSUPPORTED; // a box kernel family
+	}
 	if (pb->mem == QP_MEM_DEVICE) {
 		a.P = pb->P, a.q = pb->q, a.A = pb->A, a.l = pb->l, a.u = pb->u, a.z0 = pb->z0, a.u0 = pb->u0;
 		a.x = sol->x, a.z = sol->z, a.y = sol->y, a.status = sol->status, a.iters = sol->iters;

@@ -94,6 +94,8 @@ int launch_newton(const NewtonArgs &a, int dev, cudaStream_t st);
 // qp_f64.cuh: the box ADMM in binary64 (qf entry points, qp_options.precision)
 int launch_admm64(const Admm64Args &a, int dev, cudaStream_t st);
 int launch_gen(const GenArgs &a, int dev, cudaStream_t st);
+// qp_genr.cuh (k_genr.cu): QP_ERR_UNSUPPORTED when n > 32 or m > 64
+int launch_genr(const GenArgs &a, int dev, cudaStream_t st);
 int launch_eval(const float *P, const float *q, const float *x, float r, float *f, int n,
 		unsigned long long count, int dev, cudaStream_t st);
 

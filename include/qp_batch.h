@@ -203,6 +203,9 @@ typedef struct qp_options {
 #define QP_KERNEL_GPQ  2 /* cyclic rows per lane:    any n <= 64                   */
 #define QP_KERNEL_BPQ  3 /* four rows per lane:      n = 8, 16, 24, 32, 40         */
 #define QP_KERNEL_CPQ  4 /* one CTA per QP:          any n <= 128 (auto: n > 64)   */
+/* qp_solve_general_batch() only (the box entry points answer QP_ERR_UNSUPPORTED): */
+#define QP_KERNEL_GEN_SMEM 5 /* operands in shared memory: n <= 64, m <= 128        */
+#define QP_KERNEL_GEN_REG  6 /* operands in registers:     n <= 32, m <= 64 (auto)  */
 
 void qp_options_default(qp_options *opt);
 

@@ -21,8 +21,11 @@ def main():
     ap.add_argument("--shapes", default="4,16,40")
     ap.add_argument("--count", type=int, default=1 << 16)
     ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--kernel", default="auto", choices=["auto", "smem", "reg"],
+                    help="auto: registers where n <= 32, m <= 64 (qp_genr.cuh), else shared memory (qp_gen.cuh)")
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
+    opt = qp.Options(kernel={"auto": qp.KERNEL_AUTO, "smem": qp.KERNEL_GEN_SMEM, "reg": qp.KERNEL_GEN_REG}[args.kernel])
     for n in [int(s) for s in args.shapes.split(",")]:
         m, count = 2 * n, args.count
         P, q = make_batch(count, n, 2026, dev)
@@ -31,16 +34,16 @@ def main():
         u = (0.5 * (0.2 + 0.8 * torch.rand((count, m), generator=gen, device=dev))).contiguous()
         l = (-u).contiguous()
         for _ in range(3):
-            out = qp.solve_general_batch(P, q, A, l, u)
+            out = qp.solve_general_batch(P, q, A, l, u, options=opt)
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(args.steps):
-            out = qp.solve_general_batch(P, q, A, l, u)
+            out = qp.solve_general_batch(P, q, A, l, u, options=opt)
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / args.steps
-        print(json.dumps({"shape": f"n={n},m={m} general rows", "count": count,
+        print(json.dumps({"shape": f"n={n},m={m} general rows", "count": count, "kernel": args.kernel,
                           "qp_per_s": count / (ms * 1e-3), "ms_per_step": ms,
                           "mean_iters": float(out["iters"].float().mean()),
                           "not_converged": int((out["status"] != 0).sum())}), flush=True)
