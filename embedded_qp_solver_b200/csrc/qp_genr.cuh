@@ -6,14 +6,17 @@
 // cites its reference line there).  What changes is where the operands live.  qp_gen.cuh keeps
 // P + rho A'A, its inverse R and A in shared memory and every FMA of an iteration waits for a
 // 32-bit shared-memory load; here a group of T lanes owns one problem and lane g keeps in
-// registers
-//   Rr[a][.]   rows i = g + T a (a < NR = NP/T) of R            NR x NP floats
-//   Ar[k][.]   rows j = g + T k (k < MR = MP/T) of A            MR x NP floats
-//   Ac[a][.]   columns i = g + T a of A (= rows of A')          NR x MP floats
-// (160 registers at the two larger shapes), and the four vectors of an iteration -- the
-// right-hand side, x, z and u -- are published to shared memory once and read by every lane
-// as 128-bit broadcasts.  Per iteration and lane: (2 NP + 2 MP) / 4 LDS.128 feed
-// (NR NP + MR NP + 2 NR MP) / 2 packed FMAs (FFMA2), against one LDS per FMA before.
+// registers, inside the iteration loop,
+//   Br[k][.]   rows j = g + T k (k < MR = MP/T) of B = A R      MR x NP floats
+//   Ac[a][.]   columns i = g + T a (a < NR = NP/T) of A         NR x MP floats
+// (128 registers at the two larger shapes).  The stop test (:205-253) needs A x, not x, so an
+// iteration goes from the right-hand side t = rho A'(z - u) - q straight to A x = B t, and
+// x = R t is formed once, from the last t, when the problem has stopped (R waits in shared
+// memory).  The three vectors of an iteration -- t, z and u -- are published to shared memory
+// and read by every lane as 128-bit broadcasts: per iteration and lane (NP + 2 MP) / 4 LDS.128
+// feed (MR NP + 2 NR MP) / 2 packed FMAs (FFMA2), against one LDS per FMA before, and two warp
+// barriers instead of four.  Setup keeps rows of P + rho A'A, then of R, and rows of A in
+// registers: the elimination publishes one pivot row per step, B is built from the rows of R.
 //   <NP, MP, T> = <8, 16, 4>   eight problems per warp
 //                 <16, 32, 8>  four problems per warp (the n = 16, m = 32 shape)
 //                 <32, 64, 32> one problem per warp
@@ -23,10 +26,11 @@
 //
 // P + rho A'A is summed over the rows of A in the order qp_gen.cuh uses, and inverted by the
 // same Gauss-Jordan arithmetic (pivot row scaled by 1/pivot, fma(-f, p, w) elsewhere), so R
-// has the same bits; the mat-vecs of the iteration keep four partial sums per row, so x
-// differs from qp_gen.cuh in the last bits.  With A = I every product has one non-zero term
-// and the kernel reproduces the reference's golden vectors under the same bars as the box
-// kernels; beyond A = I there is no reference behaviour -- PARITY UNPINNED, as for qp_gen.cuh.
+// has the same bits; A x = (A R) t instead of A (R t) and four partial sums per row in the
+// mat-vecs, so the iterates differ from qp_gen.cuh in the last bits.  With A = I every product
+// with A has one non-zero term, B = R bit for bit, and the kernel reproduces the reference's
+// golden vectors under the same bars as the box kernels; beyond A = I there is no reference
+// behaviour -- PARITY UNPINNED, as for qp_gen.cuh.
 #pragma once
 
 #include "qp_aux_args.h"
@@ -44,11 +48,17 @@ template <int NP, int MP, int T> struct GenrCfg {
 	static constexpr int LDP = NP + 4; // row stride of the staged [P; A]: 16-byte aligned, and
 					   // lanes reading consecutive rows hit different bank quads
 	static constexpr int RAW = (NP + MP) * LDP + 2 * NP + 2 * MP;
-	// groups start 4 banks apart: the broadcasts of a warp's groups do not collide
-	static constexpr int GS = RAW + (4 + 32 - RAW % 32) % 32;
+	// groups start T banks apart: neither the 128-bit broadcasts nor the lanes' 32-bit stores
+	// of a warp's groups collide
+	static constexpr int GS = RAW + (T % 32 + 32 - RAW % 32) % 32;
 	static constexpr size_t SMEM = size_t(GENR_WARPS) * G * GS * sizeof(float);
-	// NR NP + MR NP + NR MP floats of matrices per lane: 80 leave room for 12 warps per SM (168 registers)
-	static constexpr int MINB = (NR * NP + MR * NP + NR * MP) <= 80 ? 3 : 2;
+	// MR NP + NR MP floats of matrices per lane inside the loop: 64 leave room for three CTAs per
+	// SM (168 registers); 128 need ~215 registers with the loop's vectors and accumulators
+	static constexpr int MINB = (MR * NP + NR * MP) <= 64 ? 3 : 2;
+	// B = A R pays when a warp carries several problems.  With one problem per warp (T = 32)
+	// building B costs what it saves (n = 32, m = 64: 26.9 M QP/s without, 21.8 M with), so that
+	// shape keeps R and the rows of A in registers and does x = R t, A x per iteration.
+	static constexpr bool FUSE = G > 1;
 };
 
 template <int T> __device__ __forceinline__ float genr_group_sum(float v)
@@ -70,6 +80,7 @@ qp_genr_kernel(const GenArgs a)
 {
 	using C = GenrCfg<NP, MP, T>;
 	constexpr int G = C::G, NR = C::NR, MR = C::MR, LDP = C::LDP, NH = NP / 2, MH = MP / 2;
+	constexpr bool FUSE = C::FUSE;
 	constexpr unsigned FULL = 0xffffffffu;
 	extern __shared__ __align__(16) float gsm[];
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -139,8 +150,8 @@ qp_genr_kernel(const GenArgs a)
 		}
 		__syncwarp();
 
-		// ---- my rows and columns of A into registers -----------------------------------------
-		float2 Ar[MR][NH], Ac[NR][MH];
+		// ---- my rows of A into registers -----------------------------------------------------
+		float2 Ar[MR][NH];
 #pragma unroll
 		for (int k = 0; k < MR; ++k) {
 			const float4 *row = reinterpret_cast<const float4 *>(sA + (g + T * k) * LDP);
@@ -149,12 +160,6 @@ qp_genr_kernel(const GenArgs a)
 				const float4 v = row[c];
 				Ar[k][2 * c] = make_float2(v.x, v.y), Ar[k][2 * c + 1] = make_float2(v.z, v.w);
 			}
-		}
-#pragma unroll
-		for (int s = 0; s < NR; ++s) {
-#pragma unroll
-			for (int k = 0; k < MH; ++k)
-				Ac[s][k] = make_float2(sA[(2 * k) * LDP + g + T * s], sA[(2 * k + 1) * LDP + g + T * s]);
 		}
 
 		// ---- my rows of P + rho A'A: sum over the rows of A in order (as qp_gen.cuh) ---------
@@ -242,8 +247,57 @@ qp_genr_kernel(const GenArgs a)
 		}
 		__syncwarp();
 
+		// ---- R to shared memory (over the staged P), B = A R for my rows of A, then my columns of
+		// A into registers -----------------------------------------------------------------------
+		float *sR = sP;
+		float2 Br[MR][NH]; // B = A R (FUSE), else A itself
+		if constexpr (FUSE) {
+#pragma unroll
+		for (int s = 0; s < NR; ++s) {
+#pragma unroll
+			for (int c = 0; c < NP / 4; ++c)
+				*reinterpret_cast<float4 *>(sR + (g + T * s) * LDP + 4 * c) =
+					make_float4(Rr[s][2 * c].x, Rr[s][2 * c].y, Rr[s][2 * c + 1].x, Rr[s][2 * c + 1].y);
+		}
+		__syncwarp();
+#pragma unroll
+		for (int k = 0; k < MR; ++k) {
+#pragma unroll
+			for (int c = 0; c < NH; ++c)
+				Br[k][c] = make_float2(0.f, 0.f);
+		}
+#pragma unroll
+		for (int i = 0; i < NP; ++i) { // B[j][.] += A[j][i] R[i][.]
+			const float4 *row = reinterpret_cast<const float4 *>(sR + i * LDP);
+#pragma unroll
+			for (int c = 0; c < NP / 4; ++c) {
+				const float4 v = row[c];
+#pragma unroll
+				for (int k = 0; k < MR; ++k) {
+					const float e = genr_get(Ar[k], i);
+					Br[k][2 * c] = __ffma2_rn(make_float2(v.x, v.y), make_float2(e, e), Br[k][2 * c]);
+					Br[k][2 * c + 1] = __ffma2_rn(make_float2(v.z, v.w), make_float2(e, e), Br[k][2 * c + 1]);
+				}
+			}
+		}
+		} else {
+#pragma unroll
+		for (int k = 0; k < MR; ++k) {
+#pragma unroll
+			for (int c = 0; c < NH; ++c)
+				Br[k][c] = Ar[k][c];
+		}
+		}
+		float2 Ac[NR][MH];
+#pragma unroll
+		for (int s = 0; s < NR; ++s) {
+#pragma unroll
+			for (int k = 0; k < MH; ++k)
+				Ac[s][k] = make_float2(sA[(2 * k) * LDP + g + T * s], sA[(2 * k + 1) * LDP + g + T * s]);
+		}
+
 		// ---- helpers: products with the register-resident matrices, vector from shared memory
-		auto r_times = [&](const float *v, float (&o)[NR]) { // rows of R times v[0..NP)
+		auto r_times = [&](const float *v, float (&o)[NR]) { // my rows of R times v[0..NP)
 			float2 acc[NR][2];
 #pragma unroll
 			for (int s = 0; s < NR; ++s)
@@ -261,7 +315,7 @@ qp_genr_kernel(const GenArgs a)
 			for (int s = 0; s < NR; ++s)
 				o[s] = (acc[s][0].x + acc[s][1].x) + (acc[s][0].y + acc[s][1].y);
 		};
-		auto a_times = [&](const float *v, float (&o)[MR]) { // my rows of A times v[0..NP)
+		auto b_times = [&](const float *v, float (&o)[MR]) { // my rows of B (or A) times v[0..NP)
 			float2 acc[MR][2];
 #pragma unroll
 			for (int k = 0; k < MR; ++k)
@@ -271,8 +325,8 @@ qp_genr_kernel(const GenArgs a)
 				const float4 t = *reinterpret_cast<const float4 *>(v + 4 * c);
 #pragma unroll
 				for (int k = 0; k < MR; ++k) {
-					acc[k][0] = __ffma2_rn(Ar[k][2 * c], make_float2(t.x, t.y), acc[k][0]);
-					acc[k][1] = __ffma2_rn(Ar[k][2 * c + 1], make_float2(t.z, t.w), acc[k][1]);
+					acc[k][0] = __ffma2_rn(Br[k][2 * c], make_float2(t.x, t.y), acc[k][0]);
+					acc[k][1] = __ffma2_rn(Br[k][2 * c + 1], make_float2(t.z, t.w), acc[k][1]);
 				}
 			}
 #pragma unroll
@@ -315,30 +369,41 @@ qp_genr_kernel(const GenArgs a)
 		}
 
 		// ---- iterations: the warp's groups in lockstep; a group that has stopped keeps
-		// executing but no longer commits its state.  The loop is software-pipelined: the
-		// x-update of the NEXT iteration (it reads only A'z and A'u) is issued before the five
-		// group sums and the stop decision of this one are known, so the shuffle chains and the
-		// square roots overlap a mat-vec; one x-update per problem is wasted.  The stop test is
-		// taken on squares (as in qp_tpq.cuh) and the commit is a select: no branch in the loop.
+		// executing but no longer commits its state.  The loop is software-pipelined: A x of
+		// the NEXT iteration (it needs only A'z and A'u) is issued before the five group sums
+		// and the stop decision of this one are known, so the shuffle chains and the square
+		// roots overlap a mat-vec; one mat-vec per problem is wasted.  The stop test is taken
+		// on squares (as in qp_tpq.cuh) and the commit is a select: no branch in the loop.
 		int status = QP_STATUS_MAX_ITER;
 		unsigned it = 0;
 		bool active = !bad && a.max_iter > 0; // uniform inside a group
 		const float rho2 = rho * rho, relrho = a.reltol * rho;
-		float nx[NR];
-		// x-update (:146-159): (P + rho A'A) x = rho A'(z - u) - q
+		// x-update (:146-159): (P + rho A'A) x = t, t = rho A'(z - u) - q, and A x.  sT holds t
+		// (published, barrier passed); v = t itself (FUSE: A x = B t, x = R t waits for the end)
+		// or x = R t (then A x from the published x)
+		auto ax_from_t = [&](float (&v)[NR], float (&o)[MR]) {
+			if constexpr (FUSE) {
+				b_times(sT, o);
+			} else {
+				r_times(sT, v);
 #pragma unroll
-		for (int s = 0; s < NR; ++s)
-			sT[g + T * s] = fmaf(rho, w1[s] - w2[s], -q[s]);
+				for (int s = 0; s < NR; ++s)
+					sX[g + T * s] = v[s];
+				__syncwarp();
+				b_times(sX, o);
+			}
+		};
+		// vc = the v of the last iteration committed, vp = the v whose A x is in ax
+		float vc[NR], vp[NR], ax[MR];
+#pragma unroll
+		for (int s = 0; s < NR; ++s) {
+			vc[s] = vp[s] = fmaf(rho, w1[s] - w2[s], -q[s]);
+			sT[g + T * s] = vp[s];
+		}
 		__syncwarp();
-		r_times(sT, nx);
+		ax_from_t(vp, ax);
 		while (__any_sync(FULL, active)) {
-#pragma unroll
-			for (int s = 0; s < NR; ++s)
-				sX[g + T * s] = nx[s];
-			__syncwarp();
-			// rows of A x, relaxation (:161-174), clip (:176-190), dual update (:192-203)
-			float ax[MR];
-			a_times(sX, ax);
+			// relaxation (:161-174), clip (:176-190), dual update (:192-203) on my rows of A x
 			float rr = 0.f, nax = 0.f, nz = 0.f;
 			float zn[MR], un[MR];
 #pragma unroll
@@ -353,7 +418,7 @@ qp_genr_kernel(const GenArgs a)
 				sZ[g + T * k] = zn[k], sU[g + T * k] = un[k];
 			}
 			__syncwarp();
-			float n1[NR], n2[NR];
+			float n1[NR], n2[NR], vn[NR];
 			at_times2(sZ, sU, n1, n2); // A'z, A'u
 			float ss = 0.f, nu = 0.f;
 #pragma unroll
@@ -361,11 +426,12 @@ qp_genr_kernel(const GenArgs a)
 				const float d = n1[s] - w1[s];
 				ss = fmaf(d, d, ss);
 				nu = fmaf(n2[s], n2[s], nu);
-				sT[g + T * s] = fmaf(rho, n1[s] - n2[s], -q[s]); // the next x-update's right-hand side
+				vn[s] = fmaf(rho, n1[s] - n2[s], -q[s]); // the next x-update's right-hand side
+				sT[g + T * s] = vn[s];              // (its last readers passed the barrier above)
 			}
 			__syncwarp();
-			float nx2[NR];
-			r_times(sT, nx2);
+			float ax2[MR];
+			ax_from_t(vn, ax2);
 			rr = genr_group_sum<T>(rr), nax = genr_group_sum<T>(nax), nz = genr_group_sum<T>(nz);
 			ss = genr_group_sum<T>(ss), nu = genr_group_sum<T>(nu);
 			// stop test (:205-253, :308): r < eps_pri and s < eps_dual, on the squares
@@ -375,16 +441,47 @@ qp_genr_kernel(const GenArgs a)
 			// commit
 #pragma unroll
 			for (int s = 0; s < NR; ++s) {
-				x[s] = active ? nx[s] : x[s];
+				vc[s] = active ? vp[s] : vc[s];
 				w1[s] = active ? n1[s] : w1[s], w2[s] = active ? n2[s] : w2[s];
-				nx[s] = nx2[s];
+				vp[s] = vn[s];
 			}
 #pragma unroll
-			for (int k = 0; k < MR; ++k)
+			for (int k = 0; k < MR; ++k) {
 				z[k] = active ? zn[k] : z[k], u[k] = active ? un[k] : u[k];
+				ax[k] = ax2[k];
+			}
 			it += active ? 1u : 0u;
 			status = (active && conv) ? QP_STATUS_CONVERGED : status;
 			active = active && !conv && it < a.max_iter;
+		}
+		// FUSE: x = R t of the last iteration done (rows of R from shared memory)
+		__syncwarp();
+		if constexpr (!FUSE) {
+			if (it > 0) {
+#pragma unroll
+				for (int s = 0; s < NR; ++s)
+					x[s] = vc[s];
+			}
+		} else {
+#pragma unroll
+		for (int s = 0; s < NR; ++s)
+			sT[g + T * s] = vc[s];
+		__syncwarp();
+		if (it > 0) {
+#pragma unroll
+			for (int s = 0; s < NR; ++s) {
+				const float4 *row = reinterpret_cast<const float4 *>(sR + (g + T * s) * LDP);
+				float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
+#pragma unroll
+				for (int c = 0; c < NP / 4; ++c) {
+					const float4 rv = row[c];
+					const float4 t = *reinterpret_cast<const float4 *>(sT + 4 * c);
+					acc0 = __ffma2_rn(make_float2(rv.x, rv.y), make_float2(t.x, t.y), acc0);
+					acc1 = __ffma2_rn(make_float2(rv.z, rv.w), make_float2(t.z, t.w), acc1);
+				}
+				x[s] = (acc0.x + acc1.x) + (acc0.y + acc1.y);
+			}
+		}
 		}
 
 		// ---- results -------------------------------------------------------------------------

@@ -21,11 +21,12 @@ def main():
     ap.add_argument("--shapes", default="4,16,40")
     ap.add_argument("--count", type=int, default=1 << 16)
     ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--max-iter", type=int, default=10000, help="1: the cost of a solve without its iterations")
     ap.add_argument("--kernel", default="auto", choices=["auto", "smem", "reg"],
                     help="auto: registers where n <= 32, m <= 64 (qp_genr.cuh), else shared memory (qp_gen.cuh)")
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
-    opt = qp.Options(kernel={"auto": qp.KERNEL_AUTO, "smem": qp.KERNEL_GEN_SMEM, "reg": qp.KERNEL_GEN_REG}[args.kernel])
+    opt = qp.Options(max_iter=args.max_iter, kernel={"auto": qp.KERNEL_AUTO, "smem": qp.KERNEL_GEN_SMEM, "reg": qp.KERNEL_GEN_REG}[args.kernel])
     for n in [int(s) for s in args.shapes.split(",")]:
         m, count = 2 * n, args.count
         P, q = make_batch(count, n, 2026, dev)
@@ -43,7 +44,7 @@ def main():
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / args.steps
-        print(json.dumps({"shape": f"n={n},m={m} general rows", "count": count, "kernel": args.kernel,
+        print(json.dumps({"shape": f"n={n},m={m} general rows", "count": count, "kernel": args.kernel, "max_iter": args.max_iter,
                           "qp_per_s": count / (ms * 1e-3), "ms_per_step": ms,
                           "mean_iters": float(out["iters"].float().mean()),
                           "not_converged": int((out["status"] != 0).sum())}), flush=True)
