@@ -358,7 +358,31 @@ def run_shapes(args, qp, torch, device, hbm_peak, fp32_peak, traffic, sm_mhz):
           {"inputs": "1.07 GB > L2", "issue_ok": True})
     del P, q, q2, out, first, z0, u0
     torch.cuda.empty_cache()
-    run_shapes.beside = [shared_line]
+    # beside BASELINE.json's shapes: rows l <= A x <= u with a general A (SURVEY.md 8(f) rank 3;
+    # no reference behaviour beyond A = I -- parity unpinned), n = 16, m = 32, both kernels
+    n, m, count = 16, 32, 1 << 17
+    P, q = make_batch(count, n, args.seed, device)
+    gen = torch.Generator(device=device).manual_seed(args.seed + 7)
+    A = (torch.randn((count, m, n), generator=gen, device=device) / n ** 0.5).contiguous()
+    ub = (0.5 * (0.2 + 0.8 * torch.rand((count, m), generator=gen, device=device))).contiguous()
+    lb = (-ub).contiguous()
+    general = {"shape": "n=16,m=32 general rows l <= A x <= u, random A (not a BASELINE shape; parity unpinned beyond A = I)",
+               "n": n, "m": m, "count": count, "inputs": "403 MB > L2"}
+    for name, kern in (("registers (qp_genr.cuh, default)", qp.KERNEL_GEN_REG),
+                       ("shared memory (qp_gen.cuh)", qp.KERNEL_GEN_SMEM)):
+        o = qp.Options(kernel=kern)
+        outg = qp.solve_general_batch(P, q, A, lb, ub, options=o)
+        msg = time_steps(torch, lambda i: qp.solve_general_batch(P, q, A, lb, ub, options=o), steps)
+        k = float(outg["iters"].float().mean())
+        # flops of the iteration as stated (x = R t, A x, A'z, A'u: 2 (n^2 + 3 m n) per iteration) and of
+        # the setup (A'A: 2 m n^2, inverse: 2 n^3)
+        fl = k * 2.0 * (n * n + 3 * m * n) + 2.0 * m * n * n + 2.0 * n ** 3
+        general[name] = {"qp_per_s": count / (msg * 1e-3), "ms_per_step": msg, "mean_iters": k,
+                         "not_converged": int((outg["status"] != 0).sum()),
+                         "fp32_frac_algorithm_flops": fl * count / (msg * 1e-3) / (fp32_peak * 1e12) if fp32_peak else None}
+    del P, q, A, lb, ub, outg
+    torch.cuda.empty_cache()
+    run_shapes.beside = [shared_line, general]
     return lines
 
 # ------------------------------------------------------------------------------------------
