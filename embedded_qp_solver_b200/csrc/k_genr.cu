@@ -1,11 +1,37 @@
 // k_genr.cu -- the register-resident general-rows kernel (qp_genr.cuh) and its launcher.
 #include <algorithm>
+#include <atomic>
 #include <cstdlib>
+#include <mutex>
 
 #include "qp_internal.h"
 #include "qp_genr.cuh"
 
 namespace qpb {
+
+constexpr unsigned GENR_TICKETS = 256;
+static std::atomic<unsigned long long *> g_ticket_pool[MAX_DEVICES];
+static std::atomic<unsigned> g_ticket_next[MAX_DEVICES];
+static std::mutex g_ticket_mu;
+
+// the device's ticket counters, allocated on first use (never freed: 2 KB per device); null
+// when the allocation fails -- the launch then falls back to the static stride
+static unsigned long long *ticket_pool(int dev)
+{
+	unsigned long long *p = g_ticket_pool[dev].load(std::memory_order_acquire);
+	if (p)
+		return p;
+	std::lock_guard<std::mutex> lock(g_ticket_mu);
+	p = g_ticket_pool[dev].load(std::memory_order_acquire);
+	if (!p) {
+		if (cudaMalloc(reinterpret_cast<void **>(&p), GENR_TICKETS * sizeof(unsigned long long)) != cudaSuccess) {
+			cudaGetLastError();
+			return nullptr;
+		}
+		g_ticket_pool[dev].store(p, std::memory_order_release);
+	}
+	return p;
+}
 
 template <int NP, int MP, int T> static int launch_genr_t(const GenArgs &a, int dev, cudaStream_t st)
 {
@@ -24,7 +50,21 @@ template <int NP, int MP, int T> static int launch_genr_t(const GenArgs &a, int 
 	const unsigned long long need = (a.count + per_cta - 1) / per_cta;
 	const unsigned long long grid =
 		std::max(1ull, std::min((unsigned long long)dev_sms(dev) * ctas_per_sm.get(dev), need));
-	qp_genr_kernel<NP, MP, T><<<dim3((unsigned)grid), dim3(GENR_WARPS * 32), C::SMEM, st>>>(a);
+	// more than one wave: problems by ticket (qp_genr.cuh).  The counter is one of GENR_TICKETS
+	// slots of a per-device array, taken in rotation and zeroed on the launch's stream (the first
+	// round is dealt by position, the kernel adds its size to the tickets): a slot is reused after
+	// GENR_TICKETS further launches on this device, by which time its launch has long ended unless
+	// that many general-rows solves are in flight at once on different streams.
+	unsigned long long *ticket = nullptr;
+	static const bool no_ticket = [] { const char *e = std::getenv("QPB200_GENR_TICKET"); return e && e[0] == '0'; }();
+	if (need > grid && !no_ticket) {
+		unsigned long long *pool = ticket_pool(dev);
+		if (pool) {
+			ticket = pool + g_ticket_next[dev].fetch_add(1u, std::memory_order_relaxed) % GENR_TICKETS;
+			QP_CUDA(cudaMemsetAsync(ticket, 0, sizeof(unsigned long long), st));
+		}
+	}
+	qp_genr_kernel<NP, MP, T><<<dim3((unsigned)grid), dim3(GENR_WARPS * 32), C::SMEM, st>>>(a, ticket);
 	QP_CUDA(cudaGetLastError());
 	return QP_OK;
 }

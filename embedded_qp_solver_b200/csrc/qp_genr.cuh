@@ -76,7 +76,7 @@ __device__ __forceinline__ float genr_get(const float2 *row, int c)
 
 template <int NP, int MP, int T>
 __global__ void __launch_bounds__(GENR_WARPS * 32, GenrCfg<NP, MP, T>::MINB)
-qp_genr_kernel(const GenArgs a)
+qp_genr_kernel(const GenArgs a, unsigned long long *ticket)
 {
 	using C = GenrCfg<NP, MP, T>;
 	constexpr int G = C::G, NR = C::NR, MR = C::MR, LDP = C::LDP, NH = NP / 2, MH = MP / 2;
@@ -96,9 +96,20 @@ qp_genr_kernel(const GenArgs a)
 	const bool vec = (n == NP) &&
 			 (((reinterpret_cast<unsigned long long>(a.P) | reinterpret_cast<unsigned long long>(a.A)) & 15ull) == 0ull);
 
+	// Work is handed out G problems at a time.  With a ticket counter (batches longer than one
+	// wave) a warp takes its next G problems when it is done with the current ones: the warps'
+	// iteration counts differ (the slowest of G problems, 25 ... 60 iterations), and with a static
+	// stride the launch ends with its unluckiest warp (2^16 problems over 1 184 warps: 14 rounds
+	// each, the slowest warp ~15 % behind the mean).  The first round is dealt by position, the
+	// counter starts behind it, and the next ticket is drawn while the current problems are solved.
 	const unsigned long long nw = (unsigned long long)gridDim.x * GENR_WARPS * G;
-	for (unsigned long long base = ((unsigned long long)blockIdx.x * GENR_WARPS + warp) * G; base < a.count;
-	     base += nw) {
+	unsigned long long base = ((unsigned long long)blockIdx.x * GENR_WARPS + warp) * G;
+	for (; base < a.count;) {
+		unsigned long long next = base + nw;
+		if (ticket) {
+			if (lane == 0)
+				next = nw + atomicAdd(ticket, (unsigned long long)G); // the counter starts at 0
+		}
 		const bool valid = base + grp < a.count;
 		const unsigned long long prob = valid ? base + grp : base; // a tail group repeats the first problem
 		// ---- stage P and A (coalesced inside the group) ------------------------------------
@@ -514,6 +525,9 @@ qp_genr_kernel(const GenArgs a)
 			}
 		}
 		__syncwarp(); // the next problem's staging overwrites what this one's lanes may still read
+		if (ticket)
+			next = __shfl_sync(FULL, next, 0);
+		base = next;
 	}
 }
 
