@@ -86,7 +86,13 @@ template <int T> static int launch_gen_t(const GenArgs &a, int dev, cudaStream_t
 	const unsigned long long need = (a.count + per_cta - 1) / per_cta;
 	const unsigned long long grid =
 		std::max(1ull, std::min((unsigned long long)dev_sms(dev) * per_sm, need));
-	qp_gen_kernel<T><<<dim3((unsigned)grid), dim3(GEN_WARPS * 32), smem, st>>>(a);
+	unsigned long long *ticket = nullptr;
+	if (need > grid) {
+		const int rc = gen_ticket(dev, st, &ticket);
+		if (rc != QP_OK)
+			return rc;
+	}
+	qp_gen_kernel<T><<<dim3((unsigned)grid), dim3(GEN_WARPS * 32), smem, st>>>(a, ticket);
 	QP_CUDA(cudaGetLastError());
 	return QP_OK;
 }

@@ -33,15 +33,37 @@ static unsigned long long *ticket_pool(int dev)
 	return p;
 }
 
-template <int NP, int MP, int T> static int launch_genr_t(const GenArgs &a, int dev, cudaStream_t st)
+// A zeroed ticket counter for a launch on `st` that is longer than one wave (qp_genr.cuh,
+// qp_gen.cuh: the first round is dealt by position, the kernel adds its size to the tickets).
+// The counter is one of GENR_TICKETS slots of a per-device array, taken in rotation and zeroed
+// on the launch's stream: a slot is reused after GENR_TICKETS further launches on this device,
+// by which time its launch has long ended unless that many general-rows solves are in flight
+// at once on different streams.  *out stays null (static stride) with QPB200_GENR_TICKET=0 or
+// when the array cannot be allocated.
+int gen_ticket(int dev, cudaStream_t st, unsigned long long **out)
+{
+	static const bool no_ticket = [] { const char *e = std::getenv("QPB200_GENR_TICKET"); return e && e[0] == '0'; }();
+	*out = nullptr;
+	if (no_ticket)
+		return QP_OK;
+	unsigned long long *pool = ticket_pool(dev);
+	if (!pool)
+		return QP_OK;
+	unsigned long long *t = pool + g_ticket_next[dev].fetch_add(1u, std::memory_order_relaxed) % GENR_TICKETS;
+	QP_CUDA(cudaMemsetAsync(t, 0, sizeof(unsigned long long), st));
+	*out = t;
+	return QP_OK;
+}
+
+template <int NP, int MP, int T, bool RELAX> static int launch_genr_r(const GenArgs &a, int dev, cudaStream_t st)
 {
 	using C = GenrCfg<NP, MP, T>;
 	static PerDeviceOnce attr_done, ctas_per_sm;
 	if (!attr_done.get(dev)) {
-		QP_CUDA(cudaFuncSetAttribute(qp_genr_kernel<NP, MP, T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+		QP_CUDA(cudaFuncSetAttribute(qp_genr_kernel<NP, MP, T, RELAX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
 					     int(C::SMEM)));
 		int per_sm = 1;
-		QP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, qp_genr_kernel<NP, MP, T>,
+		QP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, qp_genr_kernel<NP, MP, T, RELAX>,
 								      GENR_WARPS * 32, C::SMEM));
 		ctas_per_sm.set(dev, std::max(1, per_sm));
 		attr_done.set(dev, 1);
@@ -50,23 +72,20 @@ template <int NP, int MP, int T> static int launch_genr_t(const GenArgs &a, int 
 	const unsigned long long need = (a.count + per_cta - 1) / per_cta;
 	const unsigned long long grid =
 		std::max(1ull, std::min((unsigned long long)dev_sms(dev) * ctas_per_sm.get(dev), need));
-	// more than one wave: problems by ticket (qp_genr.cuh).  The counter is one of GENR_TICKETS
-	// slots of a per-device array, taken in rotation and zeroed on the launch's stream (the first
-	// round is dealt by position, the kernel adds its size to the tickets): a slot is reused after
-	// GENR_TICKETS further launches on this device, by which time its launch has long ended unless
-	// that many general-rows solves are in flight at once on different streams.
 	unsigned long long *ticket = nullptr;
-	static const bool no_ticket = [] { const char *e = std::getenv("QPB200_GENR_TICKET"); return e && e[0] == '0'; }();
-	if (need > grid && !no_ticket) {
-		unsigned long long *pool = ticket_pool(dev);
-		if (pool) {
-			ticket = pool + g_ticket_next[dev].fetch_add(1u, std::memory_order_relaxed) % GENR_TICKETS;
-			QP_CUDA(cudaMemsetAsync(ticket, 0, sizeof(unsigned long long), st));
-		}
+	if (need > grid) {
+		const int rc = gen_ticket(dev, st, &ticket);
+		if (rc != QP_OK)
+			return rc;
 	}
-	qp_genr_kernel<NP, MP, T><<<dim3((unsigned)grid), dim3(GENR_WARPS * 32), C::SMEM, st>>>(a, ticket);
+	qp_genr_kernel<NP, MP, T, RELAX><<<dim3((unsigned)grid), dim3(GENR_WARPS * 32), C::SMEM, st>>>(a, ticket);
 	QP_CUDA(cudaGetLastError());
 	return QP_OK;
+}
+
+template <int NP, int MP, int T> static int launch_genr_t(const GenArgs &a, int dev, cudaStream_t st)
+{
+	return a.alpha == 1.0f ? launch_genr_r<NP, MP, T, false>(a, dev, st) : launch_genr_r<NP, MP, T, true>(a, dev, st);
 }
 
 int launch_genr(const GenArgs &a, int dev, cudaStream_t st)

@@ -78,7 +78,8 @@ __device__ __forceinline__ bool smem_gauss_jordan_group(float *W, int n, int ld,
 	return bad;
 }
 
-template <int T> __global__ void __launch_bounds__(GEN_WARPS * 32) qp_gen_kernel(const GenArgs a)
+template <int T>
+__global__ void __launch_bounds__(GEN_WARPS * 32) qp_gen_kernel(const GenArgs a, unsigned long long *ticket)
 {
 	constexpr int G = 32 / T; // problems per warp
 	extern __shared__ __align__(16) float gsm[];
@@ -93,9 +94,16 @@ template <int T> __global__ void __launch_bounds__(GEN_WARPS * 32) qp_gen_kernel
 	const bool h0 = i0 < n, h1 = i1 < n;
 	const float rho = a.rho, alpha = a.alpha;
 
+	// first round by position, then (batches longer than one wave) G problems per ticket, the
+	// next one drawn while these are solved -- see qp_genr.cuh
 	const unsigned long long nw = (unsigned long long)gridDim.x * GEN_WARPS * G;
-	for (unsigned long long base = ((unsigned long long)blockIdx.x * GEN_WARPS + warp) * G; base < a.count;
-	     base += nw) {
+	unsigned long long base = ((unsigned long long)blockIdx.x * GEN_WARPS + warp) * G;
+	for (; base < a.count;) {
+		unsigned long long next = base + nw;
+		if (ticket) {
+			if (lane == 0)
+				next = nw + atomicAdd(ticket, (unsigned long long)G);
+		}
 		const bool valid = base + grp < a.count;
 		const unsigned long long prob = valid ? base + grp : base; // a tail group repeats the first problem
 		// ---- load P, A (coalesced inside the group), q, l, u, warm start ---------------------
@@ -264,6 +272,9 @@ template <int T> __global__ void __launch_bounds__(GEN_WARPS * 32) qp_gen_kernel
 			}
 		}
 		__syncwarp();
+		if (ticket)
+			next = __shfl_sync(0xffffffffu, next, 0);
+		base = next;
 	}
 }
 

@@ -74,7 +74,8 @@ __device__ __forceinline__ float genr_get(const float2 *row, int c)
 	return (c & 1) ? row[c >> 1].y : row[c >> 1].x;
 }
 
-template <int NP, int MP, int T>
+// RELAX = false: alpha == 1, the relaxation (:161-174) is the identity and is not computed
+template <int NP, int MP, int T, bool RELAX>
 __global__ void __launch_bounds__(GENR_WARPS * 32, GenrCfg<NP, MP, T>::MINB)
 qp_genr_kernel(const GenArgs a, unsigned long long *ticket)
 {
@@ -388,7 +389,7 @@ qp_genr_kernel(const GenArgs a, unsigned long long *ticket)
 		int status = QP_STATUS_MAX_ITER;
 		unsigned it = 0;
 		bool active = !bad && a.max_iter > 0; // uniform inside a group
-		const float rho2 = rho * rho, relrho = a.reltol * rho;
+		const float rho2 = rho * rho, relrho = a.reltol * rho, oma = 1.0f - alpha;
 		// x-update (:146-159): (P + rho A'A) x = t, t = rho A'(z - u) - q, and A x.  sT holds t
 		// (published, barrier passed); v = t itself (FUSE: A x = B t, x = R t waits for the end)
 		// or x = R t (then A x from the published x)
@@ -419,7 +420,7 @@ qp_genr_kernel(const GenArgs a, unsigned long long *ticket)
 			float zn[MR], un[MR];
 #pragma unroll
 			for (int k = 0; k < MR; ++k) {
-				const float zh = fmaf(alpha, ax[k], (1.0f - alpha) * z[k]);
+				const float zh = RELAX ? fmaf(alpha, ax[k], oma * z[k]) : ax[k];
 				zn[k] = fminf(fmaxf(zh + u[k], lo[k]), hi[k]);
 				un[k] = u[k] + (zh - zn[k]);
 				const float dr = ax[k] - zn[k];

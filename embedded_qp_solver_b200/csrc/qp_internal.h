@@ -96,6 +96,7 @@ int launch_admm64(const Admm64Args &a, int dev, cudaStream_t st);
 int launch_gen(const GenArgs &a, int dev, cudaStream_t st);
 // qp_genr.cuh (k_genr.cu): QP_ERR_UNSUPPORTED when n > 32 or m > 64
 int launch_genr(const GenArgs &a, int dev, cudaStream_t st);
+int gen_ticket(int dev, cudaStream_t st, unsigned long long **out);
 int launch_eval(const float *P, const float *q, const float *x, float r, float *f, int n,
 		unsigned long long count, int dev, cudaStream_t st);
 
