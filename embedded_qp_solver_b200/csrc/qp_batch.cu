@@ -21,6 +21,7 @@
 #include <chrono>
 #include <condition_variable>
 #include <cstdlib>
+#include <deque>
 #include <functional>
 #include <cmath>
 #include <cstdio>
@@ -784,6 +785,67 @@ extern "C" int qp_host_path_packs(uint32_t n)
 // ----------------------------------------------------------------------------------------
 static constexpr int DEPTH = 3;
 
+// One thread per GPU that finishes chunks whose results go to PAGEABLE caller memory: it waits
+// for the chunk's event and copies the results from the slot's pinned buffer into the caller's
+// arrays, so that the enqueueing thread (which also feeds the packing pool) does neither.  Tasks
+// run in the order they were pushed -- the order the chunks were enqueued on their streams.
+class OutCopier {
+public:
+	OutCopier() : th_([this] { loop(); }) {}
+	~OutCopier()
+	{
+		{
+			std::lock_guard<std::mutex> lk(mu_);
+			stop_ = true;
+		}
+		cv_.notify_all();
+		th_.join();
+	}
+	void push(std::function<void()> f)
+	{
+		{
+			std::lock_guard<std::mutex> lk(mu_);
+			q_.push_back(std::move(f));
+			++open_;
+		}
+		cv_.notify_all();
+	}
+	// every task pushed so far has run
+	void drain()
+	{
+		std::unique_lock<std::mutex> lk(mu_);
+		done_.wait(lk, [this] { return open_ == 0; });
+	}
+
+private:
+	void loop()
+	{
+		for (;;) {
+			std::function<void()> f;
+			{
+				std::unique_lock<std::mutex> lk(mu_);
+				cv_.wait(lk, [this] { return stop_ || !q_.empty(); });
+				if (q_.empty())
+					return;
+				f = std::move(q_.front());
+				q_.pop_front();
+			}
+			f();
+			{
+				std::lock_guard<std::mutex> lk(mu_);
+				if (--open_ == 0)
+					done_.notify_all();
+			}
+		}
+	}
+	std::mutex mu_;
+	std::condition_variable cv_, done_;
+	std::deque<std::function<void()>> q_;
+	size_t open_ = 0;
+	bool stop_ = false;
+	std::thread th_; // last: the thread starts when everything above exists
+};
+
 struct Slot {
 	// device buffers for one chunk
 	float *dP = nullptr, *dq = nullptr, *dlb = nullptr, *dub = nullptr, *dz0 = nullptr,
@@ -800,12 +862,18 @@ struct Slot {
 	size_t first = 0, cnt = 0;
 	bool busy = false;
 	bool timed = false; // t0, t1 were recorded for the chunk in flight
+	// the chunk in flight is finished by the OutCopier: 1 while its task is open, then 0;
+	// copy_rc = what cudaEventSynchronize returned there
+	bool copier = false;
+	int copy_open = 0; // (accessed with __atomic builtins: Slot stays movable)
+	cudaError_t copy_rc = cudaSuccess;
 };
 
 struct DeviceCtx {
 	int dev = 0;
 	Slot slot[DEPTH];
 	HostPool *pool = nullptr; // packing workers of this device's shard
+	OutCopier *out = nullptr; // results to pageable caller memory (created on first use)
 	// pinned buffers of packed upper triangles (n = 8, 12, 16), filled in turn by the pool
 	// (one being filled, one filled and waiting, one being read by the copy engine);
 	// hpk_free[b] fires when the copy engine has read buffer b
@@ -896,6 +964,8 @@ void free_ctx(DeviceCtx &c)
 	}
 	delete c.pool;
 	c.pool = nullptr;
+	delete c.out;
+	c.out = nullptr;
 	for (int b = 0; b < DeviceCtx::NPK; ++b) {
 		cudaFreeHost(c.hpk[b]);
 		c.hpk[b] = nullptr;
@@ -980,10 +1050,12 @@ void quiesce(DeviceCtx &ctx)
 {
 	if (ctx.pool)
 		ctx.pool->wait();
+	if (ctx.out)
+		ctx.out->drain();
 	for (Slot &s : ctx.slot) {
 		if (s.stream)
 			cudaStreamSynchronize(s.stream);
-		s.busy = false, s.timed = false;
+		s.busy = false, s.timed = false, s.copier = false;
 	}
 	for (bool &b : ctx.hpk_busy)
 		b = false;
@@ -1085,14 +1157,21 @@ int run_shard_body(qp_workspace *ws, DeviceCtx &ctx, const qp_batch &pb, const q
 	auto retire = [&](Slot &s) -> int {
 		if (!s.busy)
 			return QP_OK;
-		QP_CUDA(cudaEventSynchronize(s.done));
+		if (s.copier) {
+			// (its task is at the front of the copier's queue or running: a short wait)
+			while (__atomic_load_n(&s.copy_open, __ATOMIC_ACQUIRE))
+				std::this_thread::sleep_for(std::chrono::microseconds(10));
+			QP_CUDA(s.copy_rc);
+		} else {
+			QP_CUDA(cudaEventSynchronize(s.done));
+		}
 		if (s.timed) {
 			float ms = 0.0f;
 			if (cudaEventElapsedTime(&ms, s.t0, s.t1) == cudaSuccess && ms > 0.0f)
 				ctx.h2d_bytes_per_s = double(s.cnt) * pk * 4.0 / (ms * 1e-3);
 			s.timed = false;
 		}
-		if (!pin_out) {
+		if (!pin_out && !s.copier) {
 			const size_t c = s.cnt, f = s.first;
 			const float *h = s.hout;
 			if (sol.x)
@@ -1107,9 +1186,11 @@ int run_shard_body(qp_workspace *ws, DeviceCtx &ctx, const qp_batch &pb, const q
 			if (sol.iters)
 				std::memcpy(sol.iters + f, hi32 + cap, c * 4);
 		}
-		s.busy = false;
+		s.busy = false, s.copier = false;
 		return QP_OK;
 	};
+	if (!pin_out && !ctx.out)
+		ctx.out = new OutCopier;
 
 	// pack the upper triangles of P on the host when the thread-per-QP kernel will run
 	const unsigned tpg = host_threads_per_gpu(unsigned(ws->devs.size()));
@@ -1230,7 +1311,9 @@ int run_shard_body(qp_workspace *ws, DeviceCtx &ctx, const qp_batch &pb, const q
 		if (ready.valid) {
 			pack = true, first = ready.first, c = ready.cnt, buf = ready.buf;
 			ready.valid = false;
-		} else if (job.valid && front < back) {
+		} else if (job.valid && front < back && pin_in) {
+			// (pageable inputs: a plain chunk would be staged by THIS thread, one core's memcpy
+			// of the full matrices, while the pool waits to be fed: packed chunks only)
 			c = std::min(chunk, back - front); // the pool is busy: a plain chunk from the back
 			first = back - c;
 			back -= c;
@@ -1349,6 +1432,33 @@ int run_shard_body(qp_workspace *ws, DeviceCtx &ctx, const qp_batch &pb, const q
 		}
 		QP_CUDA(cudaEventRecord(s.done, st));
 		s.busy = true;
+		if (!pin_out) {
+			s.copier = true;
+			__atomic_store_n(&s.copy_open, 1, __ATOMIC_RELAXED);
+			Slot *sp = &s;
+			const qp_batch_solution so = sol;
+			const size_t f = first, cc = c, nn = n, cp = cap;
+			const int dev = ctx.dev;
+			ctx.out->push([sp, so, f, cc, nn, cp, dev] {
+				cudaSetDevice(dev);
+				sp->copy_rc = cudaEventSynchronize(sp->done);
+				if (sp->copy_rc == cudaSuccess) {
+					const float *h = sp->hout;
+					if (so.x)
+						std::memcpy(so.x + f * nn, h, cc * nn * 4);
+					if (so.z)
+						std::memcpy(so.z + f * nn, h + cp * nn, cc * nn * 4);
+					if (so.lambda)
+						std::memcpy(so.lambda + f * nn, h + 2 * cp * nn, cc * nn * 4);
+					const int32_t *hi32 = reinterpret_cast<const int32_t *>(h + 3 * cp * nn);
+					if (so.status)
+						std::memcpy(so.status + f, hi32, cc * 4);
+					if (so.iters)
+						std::memcpy(so.iters + f, hi32 + cp, cc * 4);
+				}
+				__atomic_store_n(&sp->copy_open, 0, __ATOMIC_RELEASE);
+			});
+		}
 		++k;
 	}
 	// drain in issue order
