@@ -1189,7 +1189,11 @@ int run_shard_body(qp_workspace *ws, DeviceCtx &ctx, const qp_batch &pb, const q
 		s.busy = false, s.copier = false;
 		return QP_OK;
 	};
-	if (!pin_out && !ctx.out)
+	// (QPB200_OUT_COPIER=0, measurements: results copied out by this thread, plain chunks staged
+	// by this thread while the pool packs -- the path as it was)
+	static const bool copier_on = [] { const char *e = std::getenv("QPB200_OUT_COPIER"); return !(e && e[0] == '0'); }();
+	const bool use_copier = !pin_out && copier_on;
+	if (use_copier && !ctx.out)
 		ctx.out = new OutCopier;
 
 	// pack the upper triangles of P on the host when the thread-per-QP kernel will run
@@ -1311,7 +1315,7 @@ int run_shard_body(qp_workspace *ws, DeviceCtx &ctx, const qp_batch &pb, const q
 		if (ready.valid) {
 			pack = true, first = ready.first, c = ready.cnt, buf = ready.buf;
 			ready.valid = false;
-		} else if (job.valid && front < back && pin_in) {
+		} else if (job.valid && front < back && (pin_in || !copier_on)) {
 			// (pageable inputs: a plain chunk would be staged by THIS thread, one core's memcpy
 			// of the full matrices, while the pool waits to be fed: packed chunks only)
 			c = std::min(chunk, back - front); // the pool is busy: a plain chunk from the back
@@ -1432,7 +1436,7 @@ int run_shard_body(qp_workspace *ws, DeviceCtx &ctx, const qp_batch &pb, const q
 		}
 		QP_CUDA(cudaEventRecord(s.done, st));
 		s.busy = true;
-		if (!pin_out) {
+		if (use_copier) {
 			s.copier = true;
 			__atomic_store_n(&s.copy_open, 1, __ATOMIC_RELAXED);
 			Slot *sp = &s;
