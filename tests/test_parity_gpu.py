@@ -572,10 +572,41 @@ def test_host_path_equals_device_path(qp, n):
     assert np.array_equal(hw["x"], dw["x"]) and np.array_equal(hw["iters"], dw["iters"])
 
 
+@pytest.mark.parametrize("n", [16, 40])
+def test_host_path_many_chunks_pageable_results_leave_through_the_copier_thread(qp, n):
+    """Forty chunks through the three-slot ring.  Results for PAGEABLE caller arrays are copied out
+    by the workspace's copier thread (one per GPU, waits for each chunk's event); pinned arrays are
+    written by the copy engine in place.  Every mix of pinned / pageable inputs and outputs, and
+    outputs left out, gives the device path's bits; twice over, so that the slots and the thread
+    are reused."""
+    count = 40_003
+    P, q, lb, ub = problems.wellcond(count, n, seed=170 + n, beta=0.5)
+    d = solve_dev(qp, P, q, lb, ub)
+    opt = qp.Options(chunk=1024)
+    pin = [torch.from_numpy(a).pin_memory() for a in (P, q, lb, ub)]
+
+    def pinned_out():
+        out = {k: torch.empty((count, n), dtype=torch.float32).pin_memory() for k in ("x", "z", "lam")}
+        out.update({k: torch.empty(count, dtype=torch.int32).pin_memory() for k in ("status", "iters")})
+        return out
+
+    for _ in range(2):
+        for args, out in (((P, q, lb, ub), None), (pin, None), ((P, q, lb, ub), pinned_out()),
+                          (pin, pinned_out())):
+            h = qp.solve_batch(*args, options=opt, out=out)
+            for k in ("x", "z", "lam", "iters", "status"):
+                assert np.array_equal(np.asarray(h[k]), d[k]), (k, out is None)
+        hx = qp.solve_batch(P, q, lb, ub, options=opt, want=("x", "status"))
+        assert sorted(hx) == ["status", "x"] and np.array_equal(hx["x"], d["x"])
+        assert np.array_equal(hx["status"], d["status"])
+
+
 @pytest.mark.parametrize("n", [3, 4, 5, 7, 16, 24, 40, 64, 96])
 def test_small_host_batches_take_the_one_copy_path(qp, n):
-    """A handful of problems in host memory (what the drop-in admm_b200() hands over: one) go
-    through one staging copy in, one launch, one copy out.  Same bits as the device path for
+    """A handful of problems in host memory (what the drop-in admm_b200() hands over: one) are
+    laid out in the slot's pinned staging buffer and solved there: the kernel reads and writes the
+    mapped buffer over PCIe, one launch and one wait (QPB200_ZERO_COPY_BYTES=0: one staging copy
+    in, one launch, one copy out).  Same bits as the device path for
     every count around the piece-alignment and slot-capacity edges, with every optional array,
     pageable and pinned, and with outputs left out."""
     rng = np.random.default_rng(n)
