@@ -9,7 +9,7 @@
 // registers, inside the iteration loop,
 //   Br[k][.]   rows j = g + T k (k < MR = MP/T) of B = A R      MR x NP floats
 //   Ac[a][.]   columns i = g + T a (a < NR = NP/T) of A         NR x MP floats
-// (128 registers at the two larger shapes).  The stop test (:205-253) needs A x, not x, so an
+// (128 registers at n = 16, m = 32).  The stop test (:205-253) needs A x, not x, so an
 // iteration goes from the right-hand side t = rho A'(z - u) - q straight to A x = B t, and
 // x = R t is formed once, from the last t, when the problem has stopped (R waits in shared
 // memory).  The three vectors of an iteration -- t, z and u -- are published to shared memory
@@ -17,6 +17,9 @@
 // feed (MR NP + 2 NR MP) / 2 packed FMAs (FFMA2), against one LDS per FMA before, and two warp
 // barriers instead of four.  Setup keeps rows of P + rho A'A, then of R, and rows of A in
 // registers: the elimination publishes one pivot row per step, B is built from the rows of R.
+// (GenrCfg::FUSE = false, one problem per warp: R and the rows of A stay in registers instead of
+// B, x = R t and A x are two steps of an iteration -- see there.)  Problems are handed out by
+// ticket when a batch is longer than one wave (k_genr.cu, gen_ticket).
 //   <NP, MP, T> = <8, 16, 4>   eight problems per warp
 //                 <16, 32, 8>  four problems per warp (the n = 16, m = 32 shape)
 //                 <32, 64, 32> one problem per warp
