@@ -650,6 +650,21 @@ def host_path_packs(n: int) -> bool:
     return bool(load_library().qp_host_path_packs(n))
 
 
+def active_set(z, lb, ub):
+    """The active set of a solution (outputs the reference lacks): +1 where
+    the coordinate sits on its upper bound, -1 on its lower bound, 0 where it is free.  z is
+    produced by clipping (qp_solvers.c:186-187), so exact equality is what "active" means; the
+    sign agrees with that of lambda = rho u wherever lambda is not zero.  numpy arrays or torch
+    tensors; lb, ub scalars or arrays that broadcast against z."""
+    if hasattr(z, "device") and hasattr(z, "new_tensor"):  # torch
+        import torch
+        lbt = lb if hasattr(lb, "device") else z.new_tensor(lb)
+        ubt = ub if hasattr(ub, "device") else z.new_tensor(ub)
+        return (z == ubt).to(torch.int8) - (z == lbt).to(torch.int8)
+    z = np.asarray(z)
+    return (z == np.asarray(ub, dtype=z.dtype)).astype(np.int8) - (z == np.asarray(lb, dtype=z.dtype)).astype(np.int8)
+
+
 def kernel_for(n: int, aligned16: bool = True) -> str:
     return load_library().qp_kernel_for(n, int(aligned16)).decode()
 

@@ -187,3 +187,18 @@ def test_host_packing_of_upper_triangles(n):
                 if rc != QP_OK:
                     pytest.skip("no AVX-512 on this CPU")
                 assert np.array_equal(got, want[first: first + cnt]), (wide, first, cnt)
+
+
+def test_active_set_helper_follows_the_sign_of_lambda():
+    """qp.active_set (outputs the reference lacks): +1 on the upper bound, -1 on the
+    lower one, the convention of lambda = rho u in include/qp_batch.h; host logic only."""
+    import numpy as np
+    import embedded_qp_solver_b200 as qp
+    z = np.array([[0.5, -0.5, 0.1, 0.5], [-0.25, 0.0, 0.25, -0.5]], np.float32)
+    assert np.array_equal(qp.active_set(z, -0.5, 0.5), [[1, -1, 0, 1], [0, 0, 0, -1]])
+    lb = np.full_like(z, -0.25)
+    ub = np.array([0.5, 0.5, 0.25, 0.5], np.float32)
+    assert np.array_equal(qp.active_set(z, lb, ub), [[1, 0, 0, 1], [-1, 0, 1, 0]])
+    import torch
+    assert torch.equal(qp.active_set(torch.from_numpy(z), -0.5, 0.5),
+                       torch.tensor([[1, -1, 0, 1], [0, 0, 0, -1]], dtype=torch.int8))

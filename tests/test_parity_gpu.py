@@ -218,6 +218,10 @@ def test_kkt_at_tight_tolerance(qp, n):
     assert np.max(np.abs(lam[inside])) <= 1e-4
     assert np.all(lam[z == ub] >= -1e-5) and np.all(lam[z == lb] <= 1e-5)
     assert np.max(np.abs(res["x"] - res["z"])) <= 1e-4
+    # qp.active_set: the sign of lambda wherever lambda is not (numerically) zero
+    act = qp.active_set(res["z"], lb, ub)
+    big = np.abs(res["lam"]) > 1e-4
+    assert np.array_equal(act[big], np.sign(res["lam"][big]).astype(np.int8))
 
 
 def test_over_relaxation_and_rho(qp, orc):
