@@ -279,6 +279,12 @@ int qp_gradient_batch(const qp_batch *prob, const float *x0, unsigned iterations
  * With A = I it is the reference's iteration line by line (and is tested against the same
  * golden vectors); for other A there is no reference behaviour to match.
  * n <= QP_MAX_DIM, m <= QP_MAX_ROWS.  P + rho A'A must be positive definite.
+ * Two kernels: operands in registers for n <= 32 and m <= 64 (csrc/qp_genr.cuh), in shared
+ * memory beyond (csrc/qp_gen.cuh); qp_options.kernel = QP_KERNEL_GEN_REG / QP_KERNEL_GEN_SMEM
+ * forces one (QP_ERR_UNSUPPORTED when the shape does not fit, or for a box kernel family).
+ * QP_MEM_DEVICE: launched on qp_options.stream, no synchronisation; batches longer than one
+ * wave draw their problems from one of 256 per-device ticket counters, zeroed on that stream.
+ * QP_MEM_HOST: one staging allocation, synchronous copies (not pipelined like qp_solve_batch).
  */
 #define QP_MAX_ROWS 128
 typedef struct qp_general_batch {
