@@ -389,10 +389,13 @@ def eval_batch(P, q, x, r: float = 0.0):
     return f
 
 
-def solve_general_batch(P, q, A, l, u, z0=None, u0=None, options: Optional[Options] = None):
+def solve_general_batch(P, q, A, l, u, z0=None, u0=None, options: Optional[Options] = None,
+                        out: Optional[dict] = None):
     """``l <= A x <= u`` rows (``qp_solve_general_batch``): the reference's ADMM iteration for
     the splitting A x = z.  Returns dict(x, z, y, status, iters); device tensors in, device
-    tensors out; numpy in, numpy out."""
+    tensors out; numpy in, numpy out.  Host arrays: ``out`` may hold preallocated result arrays
+    (numpy or pinned torch tensors, any subset of the keys); the library cuts the batch into
+    chunks that alternate between two device buffers and two streams."""
     lib = load_library()
     count, n = int(P.shape[0]), int(P.shape[1])
     m = int(A.shape[1])
@@ -418,8 +421,16 @@ def solve_general_batch(P, q, A, l, u, z0=None, u0=None, options: Optional[Optio
         copt.stream = C.c_void_p(torch.cuda.current_stream(d).cuda_stream or None)
         addr = {k: v.data_ptr() for k, v in out.items()}
     else:
-        out = {k: np.empty(sh, np.float32 if t == "f" else np.int32) for k, (sh, t) in shapes.items()}
-        addr = {k: v.ctypes.data for k, v in out.items()}
+        # host arrays; `out` may bring preallocated ones (e.g. pinned torch tensors, which the copy
+        # engine then writes in place), missing keys are allocated here
+        res = {} if out is None else out
+        for k, (sh, t) in shapes.items():
+            if k not in res:
+                res[k] = np.empty(sh, np.float32 if t == "f" else np.int32)
+            elif tuple(res[k].shape) != sh:
+                raise ValueError(f"out[{k!r}] must have shape {sh}")
+        out = res
+        addr = {k: (v.data_ptr() if _is_torch(v) else v.ctypes.data) for k, v in out.items()}
     sol = qp_general_solution(addr["x"], addr["z"], addr["y"], addr["status"], addr["iters"])
     rc = lib.qp_solve_general_batch(C.byref(pb), C.byref(sol), C.byref(copt))
     if rc != QP_OK:

@@ -1866,6 +1866,18 @@ extern "C" int qp_gradient_batch(const qp_batch *pb, const float *x0, unsigned i
 // ----------------------------------------------------------------------------------------
 // general rows l <= A x <= u (qp_gen.cuh)
 // ----------------------------------------------------------------------------------------
+// device staging of qp_solve_general_batch() with host pointers: two buffers and two streams per
+// device, kept for the life of the process (they only grow; 2 x ~32 MB unless one problem is larger)
+namespace {
+struct GenStage {
+	std::mutex mu;
+	float *d[2] = { nullptr, nullptr };
+	size_t floats = 0; // capacity of each buffer
+	cudaStream_t st[2] = { nullptr, nullptr };
+};
+GenStage g_gen_stage[qpb::MAX_DEVICES];
+} // namespace
+
 extern "C" int qp_solve_general_batch(const qp_general_batch *pb, const qp_general_solution *sol,
 				      const qp_options *opt_in)
 {
@@ -1912,42 +1924,82 @@ extern "C" int qp_solve_general_batch(const qp_general_batch *pb, const qp_gener
 		a.x = sol->x, a.z = sol->z, a.y = sol->y, a.status = sol->status, a.iters = sol->iters;
 		return launch_gen(a, dev, static_cast<cudaStream_t>(opt.stream));
 	}
-	// host pointers: one staging allocation, synchronous
-	const size_t fin = c * (n * n + n + m * n + 4 * m), fout = c * (n + 2 * m + 2);
-	float *d = nullptr;
-	QP_CUDA(cudaMalloc(&d, (fin + fout) * 4));
-	float *dP = d, *dq = dP + c * n * n, *dA = dq + c * n, *dl = dA + c * m * n, *du = dl + c * m,
-	      *dz0 = du + c * m, *du0 = dz0 + c * m, *dx = du0 + c * m, *dz = dx + c * n, *dy = dz + c * m;
-	int32_t *dst = reinterpret_cast<int32_t *>(dy + c * m), *dit = dst + c;
-	struct Cp {
-		void *dst;
-		const void *src;
-		size_t bytes;
-	} ins[] = { { dP, pb->P, c * n * n * 4 }, { dq, pb->q, c * n * 4 },  { dA, pb->A, c * m * n * 4 },
-		    { dl, pb->l, c * m * 4 },     { du, pb->u, c * m * 4 },  { dz0, pb->z0, c * m * 4 },
-		    { du0, pb->u0, c * m * 4 } };
-	cudaError_t e = cudaSuccess;
-	for (const Cp &cp : ins)
-		if (cp.src && e == cudaSuccess)
-			e = cudaMemcpy(cp.dst, cp.src, cp.bytes, cudaMemcpyHostToDevice);
-	rc = QP_OK;
-	if (e == cudaSuccess) {
-		a.P = dP, a.q = dq, a.A = dA, a.l = dl, a.u = du;
-		a.z0 = pb->z0 ? dz0 : nullptr, a.u0 = pb->u0 ? du0 : nullptr;
-		a.x = dx, a.z = dz, a.y = dy, a.status = dst, a.iters = dit;
-		rc = launch_gen(a, dev, nullptr);
-		Cp outs[] = { { sol->x, dx, c * n * 4 },      { sol->z, dz, c * m * 4 },
-			      { sol->y, dy, c * m * 4 },      { sol->status, dst, c * 4 },
-			      { sol->iters, dit, c * 4 } };
-		for (const Cp &cp : outs)
-			if (cp.dst && rc == QP_OK && e == cudaSuccess)
-				e = cudaMemcpy(cp.dst, cp.src, cp.bytes, cudaMemcpyDeviceToHost);
+	// host pointers: chunks of ~32 MB alternate between two device buffers and two streams, so
+	// the copy-in of a chunk overlaps the solve and the copy-out of the one before (copies on one
+	// stream are ordered: a buffer is not overwritten before its previous results have left).  The
+	// buffers are kept per device and only grow; calls on one device take turns.
+	GenStage &gs = g_gen_stage[dev];
+	std::lock_guard<std::mutex> lock(gs.mu);
+	const size_t per = n * n + n + m * n + 4 * m + n + 2 * m + 2; // floats per problem, in and out
+	size_t capc = std::min<size_t>(c, std::max<size_t>(4, (size_t(32) << 20) / 4 / per));
+	capc = (capc + 3) / 4 * 4; // every piece of a buffer stays 16-byte aligned
+	if (gs.floats < capc * per) {
+		for (float *&p : gs.d) {
+			cudaFree(p);
+			p = nullptr;
+		}
+		gs.floats = 0;
+		for (float *&p : gs.d)
+			QP_CUDA(cudaMalloc(&p, capc * per * 4));
+		gs.floats = capc * per;
 	}
-	cudaFree(d);
+	for (cudaStream_t &st : gs.st)
+		if (!st)
+			QP_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+	cudaError_t e = cudaSuccess;
+	rc = QP_OK;
+	size_t k = 0;
+	for (size_t f = 0; f < c && e == cudaSuccess && rc == QP_OK; f += capc, ++k) {
+		const size_t cc = std::min(capc, c - f);
+		cudaStream_t st = gs.st[k & 1];
+		float *d = gs.d[k & 1];
+		float *dP = d, *dq = dP + capc * n * n, *dA = dq + capc * n, *dl = dA + capc * m * n,
+		      *du = dl + capc * m, *dz0 = du + capc * m, *du0 = dz0 + capc * m, *dx = du0 + capc * m,
+		      *dz = dx + capc * n, *dy = dz + capc * m;
+		int32_t *dst = reinterpret_cast<int32_t *>(dy + capc * m), *dit = dst + capc;
+		struct Cp {
+			void *dst;
+			const void *src;
+			size_t bytes;
+		} ins[] = { { dP, pb->P + f * n * n, cc * n * n * 4 },
+			    { dq, pb->q + f * n, cc * n * 4 },
+			    { dA, pb->A + f * m * n, cc * m * n * 4 },
+			    { dl, pb->l + f * m, cc * m * 4 },
+			    { du, pb->u + f * m, cc * m * 4 },
+			    { dz0, pb->z0 ? pb->z0 + f * m : nullptr, cc * m * 4 },
+			    { du0, pb->u0 ? pb->u0 + f * m : nullptr, cc * m * 4 } };
+		for (const Cp &cp : ins)
+			if (cp.src && e == cudaSuccess)
+				e = cudaMemcpyAsync(cp.dst, cp.src, cp.bytes, cudaMemcpyHostToDevice, st);
+		if (e != cudaSuccess)
+			break;
+		GenArgs ac = a;
+		ac.count = cc;
+		ac.P = dP, ac.q = dq, ac.A = dA, ac.l = dl, ac.u = du;
+		ac.z0 = pb->z0 ? dz0 : nullptr, ac.u0 = pb->u0 ? du0 : nullptr;
+		ac.x = dx, ac.z = dz, ac.y = dy, ac.status = dst, ac.iters = dit;
+		rc = launch_gen(ac, dev, st);
+		if (rc != QP_OK)
+			break;
+		Cp outs[] = { { sol->x + f * n, dx, cc * n * 4 },
+			      { sol->z ? sol->z + f * m : nullptr, dz, cc * m * 4 },
+			      { sol->y ? sol->y + f * m : nullptr, dy, cc * m * 4 },
+			      { sol->status ? sol->status + f : nullptr, dst, cc * 4 },
+			      { sol->iters ? sol->iters + f : nullptr, dit, cc * 4 } };
+		for (const Cp &cp : outs)
+			if (cp.dst && e == cudaSuccess)
+				e = cudaMemcpyAsync(cp.dst, cp.src, cp.bytes, cudaMemcpyDeviceToHost, st);
+	}
+	for (cudaStream_t st : gs.st) {
+		const cudaError_t es = cudaStreamSynchronize(st);
+		if (e == cudaSuccess)
+			e = es;
+	}
 	if (rc != QP_OK)
 		return rc;
 	if (e != cudaSuccess) {
 		g_err = std::string("qp_solve_general_batch: ") + cudaGetErrorString(e);
+		cudaGetLastError();
 		return QP_ERR_CUDA;
 	}
 	return QP_OK;

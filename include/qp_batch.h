@@ -284,7 +284,10 @@ int qp_gradient_batch(const qp_batch *prob, const float *x0, unsigned iterations
  * forces one (QP_ERR_UNSUPPORTED when the shape does not fit, or for a box kernel family).
  * QP_MEM_DEVICE: launched on qp_options.stream, no synchronisation; batches longer than one
  * wave draw their problems from one of 256 per-device ticket counters, zeroed on that stream.
- * QP_MEM_HOST: one staging allocation, synchronous copies (not pipelined like qp_solve_batch).
+ * QP_MEM_HOST: chunks of ~32 MB alternate between two device buffers and two streams (kept per
+ * device), copy-in overlapping the solve and copy-out of the chunk before; synchronous call.
+ * Pin the arrays (cudaHostRegister) for full PCIe speed: pageable arrays go through the
+ * driver's staged copies.
  */
 #define QP_MAX_ROWS 128
 typedef struct qp_general_batch {

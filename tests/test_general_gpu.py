@@ -181,6 +181,23 @@ def test_register_kernel_full_batch_properties(qp):
                                 l[perm].contiguous(), u[perm].contiguous())
     for k in ("x", "z", "y", "iters", "status"):
         assert torch.equal(rp[k], r[k][perm]), k
+    # host pointers: chunks alternate between two device buffers and two streams (four chunks
+    # here, the last one ragged); pageable and pinned arrays, the device path's bits
+    part = 30_001
+    host = [t[:part].cpu() for t in (P, q, A, l, u)]
+    for pinned in (False, True):
+        args = [t.pin_memory() if pinned else t.numpy() for t in host]
+        out = None
+        if pinned:  # results written in place by the copy engine; x and iters preallocated only
+            out = {"x": torch.empty((part, n)).pin_memory(),
+                   "iters": torch.empty(part, dtype=torch.int32).pin_memory()}
+        for _ in range(2):
+            h = qp.solve_general_batch(*args, out=out)
+            assert out is None or h is out
+            for k in ("x", "z", "y", "iters", "status"):
+                assert np.array_equal(np.asarray(h[k]), r[k][:part].cpu().numpy()), (k, pinned)
+    with pytest.raises(ValueError):
+        qp.solve_general_batch(*[t.numpy() for t in host], out={"x": np.empty((3, n), np.float32)})
 
 
 @pytest.mark.parametrize("kernel", ["auto", "smem"])
