@@ -202,3 +202,30 @@ def test_active_set_helper_follows_the_sign_of_lambda():
     import torch
     assert torch.equal(qp.active_set(torch.from_numpy(z), -0.5, 0.5),
                        torch.tensor([[1, -1, 0, 1], [0, 0, 0, -1]], dtype=torch.int8))
+
+
+def test_python_mirror_constants_match_the_header():
+    """Every #define of include/qp_batch.h that the ctypes mirror restates (kernel families,
+    schedules, precisions, statuses, memory kinds, layouts, limits) has the header's value."""
+    import os
+    import re
+    import embedded_qp_solver_b200 as qp
+    from embedded_qp_solver_b200 import api
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = open(os.path.join(root, "include", "qp_batch.h")).read()
+    defs = {k: int(v, 0) for k, v in re.findall(r"#define\s+(QP_[A-Z0-9_]+)\s+\(?(-?(?:0x)?[0-9a-fA-F]+)u?\)?\s", src)}
+    checked = 0
+    for name, value in defs.items():
+        short = name[3:]  # QP_KERNEL_TPQ -> KERNEL_TPQ
+        for holder in (qp, api):
+            if hasattr(holder, short):
+                assert getattr(holder, short) == value, name
+                checked += 1
+                break
+            if hasattr(holder, name):
+                assert getattr(holder, name) == value, name
+                checked += 1
+                break
+    assert checked >= 15, (checked, sorted(defs))
+    for must in ("QP_KERNEL_GEN_SMEM", "QP_KERNEL_GEN_REG", "QP_KERNEL_CPQ", "QP_SCHEDULE_PASSES"):
+        assert must in defs
